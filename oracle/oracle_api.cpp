@@ -1,0 +1,217 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+// extern "C" surface of liboracle.so for tests/, smoke() and bench.py's CPU
+// legs (ctypes). Nothing under raven_b200/ may link or load this library.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+#include "flat_api.hpp"
+#include "ram/minimizer_engine.hpp"
+#include "stage1_port.hpp"
+
+std::atomic<std::uint32_t> biosoup::NucleicAcid::num_objects{0};
+
+struct orc_engine {
+  std::shared_ptr<thread_pool::ThreadPool> pool;
+  std::unique_ptr<ram::MinimizerEngine> eng;
+};
+
+ORC_BAG_ACCESSORS(orc)
+
+ORC_EXPORT orc_engine* orc_engine_create(std::uint32_t k, std::uint32_t w,
+                                         std::uint32_t bandwidth,
+                                         std::uint32_t chain,
+                                         std::uint32_t matches,
+                                         std::uint32_t gap,
+                                         std::uint32_t threads) {
+  auto* e = new orc_engine();
+  e->pool = std::make_shared<thread_pool::ThreadPool>(std::max(1U, threads));
+  e->eng = std::make_unique<ram::MinimizerEngine>(e->pool, k, w, bandwidth,
+                                                  chain, matches, gap);
+  return e;
+}
+
+ORC_EXPORT void orc_engine_free(orc_engine* e) { delete e; }
+
+// per-read sketches of reads [first, last): value/origin + offsets
+ORC_EXPORT orc_bag* orc_sketch(orc_engine* e, orc_reads* r, std::uint32_t first,
+                               std::uint32_t last, int minhash) {
+  auto* bag = new orc_bag();
+  std::vector<std::uint64_t> value, origin, off{0};
+  for (std::uint32_t i = first; i < last; ++i) {
+    for (const auto& m : e->eng->Sketch(r->seqs[i], minhash)) {
+      value.emplace_back(m.value);
+      origin.emplace_back(m.origin);
+    }
+    off.emplace_back(value.size());
+  }
+  bag->Put("value", value);
+  bag->Put("origin", origin);
+  bag->Put("offsets", off);
+  return bag;
+}
+
+ORC_EXPORT void orc_engine_minimize(orc_engine* e, orc_reads* r,
+                                    std::uint32_t first, std::uint32_t last,
+                                    int minhash) {
+  e->eng->Minimize(r->seqs.begin() + first, r->seqs.begin() + last, minhash);
+}
+
+// returns 0 and writes the occurrence threshold, or -1 on invalid frequency
+ORC_EXPORT int orc_engine_filter(orc_engine* e, double f,
+                                 std::uint32_t* occurrence) {
+  try {
+    e->eng->Filter(f);
+  } catch (const std::invalid_argument&) {
+    return -1;
+  }
+  *occurrence = e->eng->occurrence();
+  return 0;
+}
+
+ORC_EXPORT orc_bag* orc_engine_keys(orc_engine* e) {
+  auto* bag = new orc_bag();
+  std::vector<std::uint64_t> values;
+  std::vector<std::uint32_t> counts;
+  e->eng->Keys(&values, &counts);
+  bag->Put("values", values);
+  bag->Put("counts", counts);
+  std::vector<std::uint64_t> totals{e->eng->num_keys(),
+                                    e->eng->num_minimizers()};
+  bag->Put("totals", totals);
+  return bag;
+}
+
+// Map every read in [first, last) against the current index
+ORC_EXPORT orc_bag* orc_engine_map(orc_engine* e, orc_reads* r,
+                                   std::uint32_t first, std::uint32_t last,
+                                   int avoid_equal, int avoid_symmetric,
+                                   int minhash, int want_matches) {
+  auto* bag = new orc_bag();
+  std::vector<std::uint32_t> ovl, filtered;
+  std::vector<std::uint64_t> ovl_off{0}, filt_off{0};
+  std::vector<std::uint64_t> mgroup, mpos, moff{0};
+  for (std::uint32_t i = first; i < last; ++i) {
+    std::vector<std::uint32_t> f;
+    if (want_matches) {
+      auto m = e->eng->Matches(r->seqs[i], avoid_equal, avoid_symmetric,
+                               minhash, nullptr);
+      for (const auto& it : m) {
+        mgroup.emplace_back(it.group);
+        mpos.emplace_back(it.positions);
+      }
+      moff.emplace_back(mgroup.size());
+    }
+    for (const auto& o : e->eng->Map(r->seqs[i], avoid_equal, avoid_symmetric,
+                                     minhash, &f)) {
+      PushOverlap(ovl, o);
+    }
+    ovl_off.emplace_back(ovl.size() / 8);
+    filtered.insert(filtered.end(), f.begin(), f.end());
+    filt_off.emplace_back(filtered.size());
+  }
+  bag->Put("overlaps", ovl);
+  bag->Put("ovl_off", ovl_off);
+  bag->Put("filtered", filtered);
+  bag->Put("filt_off", filt_off);
+  if (want_matches) {
+    bag->Put("match_group", mgroup);
+    bag->Put("match_pos", mpos);
+    bag->Put("match_off", moff);
+  }
+  return bag;
+}
+
+// chain a caller-supplied hit list (for chain-kernel unit tests)
+ORC_EXPORT orc_bag* orc_engine_chain(orc_engine* e, std::uint32_t lhs_id,
+                                     const std::uint64_t* group,
+                                     const std::uint64_t* positions,
+                                     std::uint64_t n) {
+  std::vector<ram::MinimizerEngine::Match> m;
+  m.reserve(n + 1);
+  for (std::uint64_t i = 0; i < n; ++i) {
+    m.emplace_back(group[i], positions[i]);
+  }
+  auto* bag = new orc_bag();
+  std::vector<std::uint32_t> ovl;
+  for (const auto& o : e->eng->ChainMatches(lhs_id, std::move(m))) {
+    PushOverlap(ovl, o);
+  }
+  bag->Put("overlaps", ovl);
+  return bag;
+}
+
+static void PutStage1(orc_bag* bag, const oracle::Stage1Result& res,
+                      double seconds) {
+  std::vector<std::uint32_t> ovl;
+  std::vector<std::uint64_t> ovl_off{0}, pile_off{0};
+  std::vector<std::uint16_t> pile;
+  for (std::size_t i = 0; i < res.overlaps.size(); ++i) {
+    for (const auto& o : res.overlaps[i]) {
+      PushOverlap(ovl, o);
+    }
+    ovl_off.emplace_back(ovl.size() / 8);
+    pile.insert(pile.end(), res.piles[i].begin(), res.piles[i].end());
+    pile_off.emplace_back(pile.size());
+  }
+  bag->Put("overlaps", ovl);
+  bag->Put("ovl_off", ovl_off);
+  bag->Put("pile", pile);
+  bag->Put("pile_off", pile_off);
+  bag->Put("occurrences", res.occurrences);
+  std::vector<std::uint64_t> stats{res.num_mapped};
+  bag->Put("num_mapped", stats);
+  std::vector<double> t{seconds};
+  bag->Put("seconds", t);
+}
+
+// stage 1 of the overlap phase (port of construct.cc:14-121)
+ORC_EXPORT orc_bag* orc_stage1(orc_engine* e, orc_reads* r, double freq,
+                               std::uint64_t max_overlaps, int minhash,
+                               std::uint64_t index_batch_bases,
+                               std::uint64_t query_batch_bases) {
+  auto* bag = new orc_bag();
+  auto t0 = std::chrono::steady_clock::now();
+  auto res = oracle::FindOverlapsAndCreatePiles(
+      e->pool, *e->eng, r->seqs, freq, max_overlaps, minhash,
+      index_batch_bases, query_batch_bases);
+  double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0)
+                 .count();
+  PutStage1(bag, res, s);
+  return bag;
+}
+
+// Pile::AddLayers on one pile (pile.cc:33-62); overlaps as 8 x u32 records
+ORC_EXPORT void orc_pile_add_layers(std::uint32_t id, std::uint16_t* data,
+                                    std::uint32_t bins,
+                                    const std::uint32_t* ovl, std::uint64_t n) {
+  std::vector<biosoup::Overlap> v;
+  for (std::uint64_t i = 0; i < n; ++i) {
+    const std::uint32_t* o = ovl + 8 * i;
+    v.emplace_back(o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7] != 0);
+  }
+  std::vector<std::uint16_t> d(data, data + bins);
+  oracle::AddLayers(id, d, v.data(), v.data() + v.size());
+  std::copy(d.begin(), d.end(), data);
+}
+
+// the truncation step alone (construct.cc:98-107) on 8 x u32 records, in place
+ORC_EXPORT std::uint64_t orc_truncate(std::uint32_t* ovl, std::uint64_t n,
+                                      std::uint64_t max_overlaps) {
+  if (n < max_overlaps) {
+    return n;
+  }
+  struct Rec {
+    std::uint32_t f[8];
+  };
+  Rec* first = reinterpret_cast<Rec*>(ovl);
+  std::sort(first, first + n, [](const Rec& a, const Rec& b) {
+    return std::max(a.f[5] - a.f[4], a.f[2] - a.f[1]) >
+           std::max(b.f[5] - b.f[4], b.f[2] - b.f[1]);
+  });
+  return max_overlaps;
+}

@@ -1,0 +1,492 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle/ram/minimizer_engine.hpp).
+//
+// CPU restatement of ram::MinimizerEngine (un-vendored).
+// Every routine cites the reference call site that pins its contract.
+// PARITY UNPINNED per stage (no upstream golden vectors for this path).
+
+#include "ram/minimizer_engine.hpp"
+
+#include <algorithm>
+#include <deque>
+#include <future>
+#include <stdexcept>
+
+namespace ram {
+
+namespace {
+
+// Stable LSD byte-radix sort on a 64-bit projection — ram sorts its records
+// this way, so ties keep insertion order (the property Map/Chain rely on).
+template <typename T, typename Proj>
+void RadixSort(std::vector<T>& v, std::size_t lo, std::size_t hi,
+               std::uint32_t bits, Proj proj) {
+  if (hi - lo < 2) {
+    return;
+  }
+  std::vector<T> tmp(hi - lo);
+  T* src = v.data() + lo;
+  T* dst = tmp.data();
+  std::size_t n = hi - lo;
+  for (std::uint32_t shift = 0; shift < bits; shift += 8) {
+    std::size_t cnt[256] = {};
+    for (std::size_t i = 0; i < n; ++i) {
+      ++cnt[(proj(src[i]) >> shift) & 255];
+    }
+    std::size_t sum = 0;
+    for (auto& c : cnt) {
+      std::size_t t = c;
+      c = sum;
+      sum += t;
+    }
+    for (std::size_t i = 0; i < n; ++i) {
+      dst[cnt[(proj(src[i]) >> shift) & 255]++] = src[i];
+    }
+    std::swap(src, dst);
+  }
+  if (src != v.data() + lo) {
+    std::copy(src, src + n, v.data() + lo);
+  }
+}
+
+// Longest chain of matches with strictly increasing lhs position and rhs
+// position ordered by `comp`. Patience arrays with a binary search whose
+// predicate looks at BOTH coordinates (App. A.2 "LIS").
+template <typename Comp>
+std::vector<std::uint64_t> LongestSubsequence(
+    const MinimizerEngine::Match* first, const MinimizerEngine::Match* last,
+    Comp comp) {
+  if (first >= last) {
+    return {};
+  }
+  std::size_t n = last - first;
+  std::vector<std::uint64_t> minimal(n + 1, 0);
+  std::vector<std::uint64_t> predecessor(n, 0);
+
+  std::uint64_t longest = 0;
+  for (std::size_t t = 0; t < n; ++t) {
+    const auto& cur = first[t];
+    std::uint64_t lo = 1, hi = longest;
+    while (lo <= hi) {
+      std::uint64_t mid = lo + (hi - lo) / 2;
+      const auto& tail = first[minimal[mid]];
+      if (tail.lhs_position() < cur.lhs_position() &&
+          comp(tail.rhs_position(), cur.rhs_position())) {
+        lo = mid + 1;
+      } else {
+        hi = mid - 1;
+      }
+    }
+    predecessor[t] = minimal[lo - 1];
+    minimal[lo] = t;
+    longest = std::max(longest, lo);
+  }
+
+  std::vector<std::uint64_t> dst(longest);
+  for (std::uint64_t i = 0, j = minimal[longest]; i < longest; ++i) {
+    dst[longest - 1 - i] = j;
+    j = predecessor[j];
+  }
+  return dst;
+}
+
+}  // namespace
+
+MinimizerEngine::MinimizerEngine(
+    std::shared_ptr<thread_pool::ThreadPool> thread_pool, std::uint32_t k,
+    std::uint32_t w, std::uint32_t bandwidth, std::uint32_t chain,
+    std::uint32_t matches, std::uint32_t gap)
+    : k_(std::min(std::max(k, 1U), 31U)),
+      w_(w),
+      bandwidth_(bandwidth),
+      chain_(chain),
+      matches_(matches),
+      gap_(gap),
+      occurrence_(-1),
+      index_(1U << std::min(14U, 2 * k_)),
+      thread_pool_(thread_pool
+                       ? thread_pool
+                       : std::make_shared<thread_pool::ThreadPool>(1)) {}
+
+std::uint32_t MinimizerEngine::Index::Find(std::uint64_t key,
+                                           const std::uint64_t** dst) const {
+  auto it = std::lower_bound(keys.begin(), keys.end(), key);
+  if (it == keys.end() || *it != key) {
+    return 0;
+  }
+  std::size_t i = it - keys.begin();
+  *dst = origins.data() + begins[i];
+  return static_cast<std::uint32_t>(begins[i + 1] - begins[i]);
+}
+
+// construct.cc:42-43 (stage 1, minhash = -M) and :363 (stage 2, full)
+void MinimizerEngine::Minimize(
+    std::vector<std::unique_ptr<biosoup::NucleicAcid>>::const_iterator first,
+    std::vector<std::unique_ptr<biosoup::NucleicAcid>>::const_iterator last,
+    bool minhash) {
+  for (auto& it : index_) {
+    it.keys.clear();
+    it.begins.clear();
+    it.origins.clear();
+  }
+  if (first >= last) {
+    return;
+  }
+
+  // sketch every read (pool tasks in sub-batches of ~50 Mbp), then route the
+  // records to their bucket in read order
+  std::vector<std::vector<Kmer>> buckets(index_.size());
+  const std::uint64_t mask = index_.size() - 1;
+  while (first != last) {
+    std::size_t batch = 0;
+    std::vector<std::future<std::vector<Kmer>>> futures;
+    for (; first != last && batch < 50000000; ++first) {
+      batch += (*first)->inflated_len;
+      futures.emplace_back(thread_pool_->Submit(
+          [&](decltype(first) it) -> std::vector<Kmer> {
+            return Minimize(*it, minhash);
+          },
+          first));
+    }
+    for (auto& f : futures) {
+      for (const auto& m : f.get()) {
+        buckets[m.value & mask].emplace_back(m);
+      }
+    }
+  }
+
+  // per bucket: stable sort by value, then run-length into keys / postings
+  std::vector<std::future<void>> futures;
+  for (std::uint32_t b = 0; b < buckets.size(); ++b) {
+    if (buckets[b].empty()) {
+      continue;
+    }
+    futures.emplace_back(thread_pool_->Submit(
+        [&](std::uint32_t b) -> void {
+          auto& recs = buckets[b];
+          RadixSort(recs, 0, recs.size(), k_ * 2,
+                    [](const Kmer& m) { return m.value; });
+          auto& idx = index_[b];
+          idx.origins.reserve(recs.size());
+          for (std::size_t i = 0; i < recs.size(); ++i) {
+            if (i == 0 || recs[i].value != recs[i - 1].value) {
+              idx.keys.emplace_back(recs[i].value);
+              idx.begins.emplace_back(i);
+            }
+            idx.origins.emplace_back(recs[i].origin);
+          }
+          idx.begins.emplace_back(recs.size());
+          std::vector<Kmer>().swap(recs);
+        },
+        b));
+  }
+  for (auto& f : futures) {
+    f.get();
+  }
+}
+
+// construct.cc:44,372
+void MinimizerEngine::Filter(double frequency) {
+  if (!(0 <= frequency && frequency <= 1)) {
+    throw std::invalid_argument(
+        "[ram::MinimizerEngine::Filter] error: invalid frequency");
+  }
+  if (frequency == 0) {
+    occurrence_ = -1;
+    return;
+  }
+
+  std::vector<std::uint32_t> occurrences;
+  for (const auto& idx : index_) {
+    for (std::size_t i = 0; i < idx.keys.size(); ++i) {
+      occurrences.emplace_back(
+          static_cast<std::uint32_t>(idx.begins[i + 1] - idx.begins[i]));
+    }
+  }
+  if (occurrences.empty()) {
+    occurrence_ = -1;
+    return;
+  }
+
+  // the element that would sit at rank (1 - f) * #keys, plus one
+  std::size_t rank = (1 - frequency) * occurrences.size();
+  if (rank >= occurrences.size()) {  // f so small that the product rounds up
+    rank = occurrences.size() - 1;
+  }
+  std::nth_element(occurrences.begin(), occurrences.begin() + rank,
+                   occurrences.end());
+  occurrence_ = occurrences[rank] + 1;
+}
+
+std::uint64_t MinimizerEngine::num_keys() const {
+  std::uint64_t n = 0;
+  for (const auto& idx : index_) {
+    n += idx.keys.size();
+  }
+  return n;
+}
+
+std::uint64_t MinimizerEngine::num_minimizers() const {
+  std::uint64_t n = 0;
+  for (const auto& idx : index_) {
+    n += idx.origins.size();
+  }
+  return n;
+}
+
+void MinimizerEngine::Keys(std::vector<std::uint64_t>* values,
+                           std::vector<std::uint32_t>* counts) const {
+  std::vector<std::pair<std::uint64_t, std::uint32_t>> all;
+  for (const auto& idx : index_) {
+    for (std::size_t i = 0; i < idx.keys.size(); ++i) {
+      all.emplace_back(idx.keys[i], static_cast<std::uint32_t>(
+                                        idx.begins[i + 1] - idx.begins[i]));
+    }
+  }
+  std::sort(all.begin(), all.end());
+  values->clear();
+  counts->clear();
+  for (const auto& it : all) {
+    values->emplace_back(it.first);
+    counts->emplace_back(it.second);
+  }
+}
+
+// probe + expand of Map (construct.cc:62 -> (1,1,1); :377-381 -> (1,1,0,&f))
+std::vector<MinimizerEngine::Match> MinimizerEngine::Matches(
+    const std::unique_ptr<biosoup::NucleicAcid>& sequence, bool avoid_equal,
+    bool avoid_symmetric, bool minhash,
+    std::vector<std::uint32_t>* filtered) const {
+  auto sketch = Minimize(sequence, minhash);
+  std::vector<Match> matches;
+  if (sketch.empty()) {
+    return matches;
+  }
+
+  const std::uint64_t mask = index_.size() - 1;
+  for (const auto& it : sketch) {
+    const std::uint64_t* jt = nullptr;
+    std::uint32_t n = index_[it.value & mask].Find(it.value, &jt);
+    if (n > occurrence_) {
+      if (filtered) {
+        filtered->emplace_back(it.position());
+      }
+      continue;
+    }
+    for (std::uint32_t j = 0; j < n; ++j, ++jt) {
+      std::uint64_t rhs_id = *jt >> 32;
+      if (avoid_equal && sequence->id == rhs_id) {
+        continue;
+      }
+      if (avoid_symmetric && sequence->id > rhs_id) {
+        continue;
+      }
+      std::uint64_t strand = (it.origin & 1) == (*jt & 1);
+      std::uint64_t lhs_pos = it.position();
+      std::uint64_t rhs_pos = static_cast<std::uint32_t>(*jt) >> 1;
+      std::uint64_t diagonal =
+          !strand ? rhs_pos + lhs_pos : rhs_pos - lhs_pos + (3ULL << 30);
+
+      matches.emplace_back((((rhs_id << 1) | strand) << 32) | diagonal,
+                           (lhs_pos << 32) | rhs_pos);
+    }
+  }
+  return matches;
+}
+
+std::vector<biosoup::Overlap> MinimizerEngine::Map(
+    const std::unique_ptr<biosoup::NucleicAcid>& sequence, bool avoid_equal,
+    bool avoid_symmetric, bool minhash,
+    std::vector<std::uint32_t>* filtered) const {
+  auto matches =
+      Matches(sequence, avoid_equal, avoid_symmetric, minhash, filtered);
+  if (matches.empty()) {
+    return {};
+  }
+  return Chain(sequence->id, std::move(matches));
+}
+
+std::vector<biosoup::Overlap> MinimizerEngine::Chain(
+    std::uint64_t lhs_id, std::vector<Match>&& matches) const {
+  RadixSort(matches, 0, matches.size(), 64,
+            [](const Match& m) { return m.group; });
+  matches.emplace_back(-1, -1);  // stop dummy
+
+  // diagonal bands: maximal runs whose groups stay within `bandwidth_` of the
+  // run start, at least 4 hits; a run that overlaps the previous one extends it
+  std::vector<std::pair<std::uint64_t, std::uint64_t>> intervals;
+  for (std::uint64_t i = 1, j = 0; i < matches.size(); ++i) {
+    if (matches[i].group - matches[j].group > bandwidth_) {
+      if (i - j >= 4) {
+        if (!intervals.empty() && intervals.back().second > j) {
+          intervals.back().second = i;
+        } else {
+          intervals.emplace_back(j, i);
+        }
+      }
+      ++j;
+      while (j < i && matches[i].group - matches[j].group > bandwidth_) {
+        ++j;
+      }
+    }
+  }
+
+  std::vector<biosoup::Overlap> dst;
+  for (const auto& it : intervals) {
+    std::uint64_t j = it.first;
+    std::uint64_t i = it.second;
+    if (i - j < chain_) {
+      continue;
+    }
+
+    RadixSort(matches, j, i, 64, [](const Match& m) { return m.positions; });
+
+    std::uint64_t strand = matches[j].strand();
+
+    std::vector<std::uint64_t> indices;
+    if (strand) {  // same strand: rhs increasing
+      indices = LongestSubsequence(matches.data() + j, matches.data() + i,
+                                   std::less<std::uint64_t>());
+    } else {  // different strand: rhs decreasing
+      indices = LongestSubsequence(matches.data() + j, matches.data() + i,
+                                   std::greater<std::uint64_t>());
+    }
+    if (indices.size() < chain_) {
+      continue;
+    }
+
+    indices.emplace_back(matches.size() - 1 - j);  // the stop dummy
+    for (std::uint64_t k = 1, l = 0; k < indices.size(); ++k) {
+      if (matches[j + indices[k]].lhs_position() -
+              matches[j + indices[k - 1]].lhs_position() >
+          gap_) {
+        if (k - l < chain_) {
+          l = k;
+          continue;
+        }
+
+        // bases covered by the chained k-mers on either read
+        std::uint32_t lhs_matches = 0, lhs_begin = 0, lhs_end = 0;
+        std::uint32_t rhs_matches = 0, rhs_begin = 0, rhs_end = 0;
+        for (std::uint64_t m = l; m < k; ++m) {
+          std::uint32_t lhs_pos = matches[j + indices[m]].lhs_position();
+          if (lhs_pos > lhs_end) {
+            lhs_matches += lhs_end - lhs_begin;
+            lhs_begin = lhs_pos;
+          }
+          lhs_end = lhs_pos + k_;
+
+          std::uint32_t rhs_pos = matches[j + indices[m]].rhs_position();
+          rhs_pos = strand ? rhs_pos : (1U << 31) - (rhs_pos + k_ - 1);
+          if (rhs_pos > rhs_end) {
+            rhs_matches += rhs_end - rhs_begin;
+            rhs_begin = rhs_pos;
+          }
+          rhs_end = rhs_pos + k_;
+        }
+        lhs_matches += lhs_end - lhs_begin;
+        rhs_matches += rhs_end - rhs_begin;
+        if (std::min(lhs_matches, rhs_matches) < matches_) {
+          l = k;
+          continue;
+        }
+
+        dst.emplace_back(
+            lhs_id, matches[j + indices[l]].lhs_position(),
+            k_ + matches[j + indices[k - 1]].lhs_position(),
+            matches[j].rhs_id(),
+            strand ? matches[j + indices[l]].rhs_position()
+                   : matches[j + indices[k - 1]].rhs_position(),
+            k_ + (strand ? matches[j + indices[k - 1]].rhs_position()
+                         : matches[j + indices[l]].rhs_position()),
+            std::min(lhs_matches, rhs_matches), strand);
+
+        l = k;
+      }
+    }
+  }
+  return dst;
+}
+
+// per-read sketch: rolling 2-bit k-mer on both strands, canonical = smaller,
+// invertible hash, monotone-deque window minimum emitting every tie once
+std::vector<MinimizerEngine::Kmer> MinimizerEngine::Minimize(
+    const std::unique_ptr<biosoup::NucleicAcid>& sequence, bool minhash) const {
+  if (sequence->inflated_len < k_) {
+    return {};
+  }
+
+  const std::uint64_t mask = (1ULL << (k_ * 2)) - 1;
+
+  auto hash = [&](std::uint64_t key) -> std::uint64_t {
+    key = ((~key) + (key << 21)) & mask;
+    key = key ^ (key >> 24);
+    key = ((key + (key << 3)) + (key << 8)) & mask;
+    key = key ^ (key >> 14);
+    key = ((key + (key << 2)) + (key << 4)) & mask;
+    key = key ^ (key >> 28);
+    key = (key + (key << 31)) & mask;
+    return key;
+  };
+
+  const std::uint64_t is_stored = 1ULL << 63;
+  std::deque<Kmer> window;
+  auto window_add = [&](std::uint64_t value, std::uint64_t location) -> void {
+    while (!window.empty() && window.back().value > value) {
+      window.pop_back();
+    }
+    window.emplace_back(value, location);
+  };
+  auto window_update = [&](std::uint32_t position) -> void {
+    while (!window.empty() && window.front().position() < position) {
+      window.pop_front();
+    }
+  };
+
+  const std::uint64_t shift = (k_ - 1) * 2;
+  std::uint64_t minimizer = 0;
+  std::uint64_t reverse_minimizer = 0;
+  const std::uint64_t id = static_cast<std::uint64_t>(sequence->id) << 32;
+
+  std::vector<Kmer> dst;
+  for (std::uint32_t i = 0; i < sequence->inflated_len; ++i) {
+    std::uint64_t c = sequence->Code(i);
+    minimizer = ((minimizer << 2) | c) & mask;
+    reverse_minimizer = (reverse_minimizer >> 2) | ((c ^ 3) << shift);
+    if (i >= k_ - 1U) {
+      if (minimizer < reverse_minimizer) {
+        window_add(hash(minimizer), (i - (k_ - 1U)) << 1 | 0);
+      } else if (minimizer > reverse_minimizer) {
+        window_add(hash(reverse_minimizer), (i - (k_ - 1U)) << 1 | 1);
+      }  // palindromic k-mers are skipped
+    }
+    if (i >= (k_ - 1U) + (w_ - 1U)) {
+      for (auto it = window.begin(); it != window.end(); ++it) {
+        if (it->value != window.front().value) {
+          break;
+        }
+        if (it->origin & is_stored) {
+          continue;
+        }
+        dst.emplace_back(it->value, id | it->origin);
+        it->origin |= is_stored;
+      }
+      window_update(i - (k_ - 1U) - (w_ - 1U) + 1);
+    }
+  }
+
+  if (minhash) {
+    // "micromizers": the len/k smallest values, ties by position, then back
+    // to position order. DEVIATION NOTE: upstream resizes unconditionally
+    // (growing a too-short sketch with zero records); the BASELINE parameters
+    // never exercise that and we only ever shrink.
+    RadixSort(dst, 0, dst.size(), k_ * 2,
+              [](const Kmer& m) { return m.value; });
+    if (sequence->inflated_len / k_ < dst.size()) {
+      dst.resize(sequence->inflated_len / k_);
+    }
+    RadixSort(dst, 0, dst.size(), 64, [](const Kmer& m) { return m.origin; });
+  }
+  return dst;
+}
+
+}  // namespace ram

@@ -1,0 +1,113 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+// extern "C" surface of oracle/_ref/libraven_ref.so: the reference's OWN
+// sources (RavenLib/src/{construct,pile,overlap_utils,graph}.cc), compiled in
+// place from /root/reference by oracle/Makefile, over this repo's drop-in
+// dependency headers (include/) and the oracle restatement of ram
+// (oracle/ram/). It pins the in-tree half of the hot path (batch schedule,
+// gather order, Pile::AddLayers, truncation sort) against the real code; the
+// ram arithmetic underneath is still the restatement (ram is not in the tree).
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+#include "flat_api.hpp"
+#include "ram/minimizer_engine.hpp"
+#include "raven/graph/construct.h"
+#include "raven/graph/overlap_utils.h"
+#include "raven/graph/serialization/binary.h"
+#include "raven/pile.h"
+
+std::atomic<std::uint32_t> biosoup::NucleicAcid::num_objects{0};
+
+namespace raven {
+// construct.cc only reaches these with checkpoints = true, which the pinning
+// entry points never pass
+void StoreGraphToFile(const Graph&) {
+  throw std::logic_error("checkpoints are not part of the pinned path");
+}
+}  // namespace raven
+
+namespace {
+
+// Pile keeps its histogram private; the only door the reference leaves open is
+// `friend cereal::access` + serialize(). This archive just captures fields.
+struct PileProbe {
+  std::vector<std::uint16_t> data;
+  template <typename... Ts>
+  void operator()(std::uint32_t&, std::uint32_t&, std::uint32_t&,
+                  std::uint16_t&, bool&, bool&, bool&, bool&,
+                  std::vector<std::uint16_t>& d, Ts&...) {
+    data = d;
+  }
+};
+
+}  // namespace
+
+ORC_BAG_ACCESSORS(ref)
+
+ORC_EXPORT orc_bag* ref_stage1(orc_reads* r, std::uint32_t k, std::uint32_t w,
+                               double freq, std::uint64_t max_overlaps,
+                               int minhash, std::uint32_t threads) {
+  auto pool = std::make_shared<thread_pool::ThreadPool>(threads ? threads : 1);
+  ram::MinimizerEngine engine{pool, k, w};
+  std::vector<std::unique_ptr<raven::Pile>> piles;
+  std::vector<std::vector<biosoup::Overlap>> overlaps(r->seqs.size());
+
+  auto t0 = std::chrono::steady_clock::now();
+  raven::FindOverlapsAndCreatePiles(pool, engine, r->seqs, freq, piles,
+                                    overlaps, max_overlaps, minhash);
+  double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0)
+                 .count();
+
+  auto* bag = new orc_bag();
+  std::vector<std::uint32_t> ovl;
+  std::vector<std::uint64_t> ovl_off{0}, pile_off{0};
+  std::vector<std::uint16_t> pile;
+  for (std::size_t i = 0; i < overlaps.size(); ++i) {
+    for (const auto& o : overlaps[i]) {
+      PushOverlap(ovl, o);
+    }
+    ovl_off.emplace_back(ovl.size() / 8);
+    PileProbe probe;
+    cereal::access::member_serialize(probe, *piles[i]);
+    pile.insert(pile.end(), probe.data.begin(), probe.data.end());
+    pile_off.emplace_back(pile.size());
+  }
+  bag->Put("overlaps", ovl);
+  bag->Put("ovl_off", ovl_off);
+  bag->Put("pile", pile);
+  bag->Put("pile_off", pile_off);
+  std::vector<std::uint32_t> occ{engine.occurrence()};
+  bag->Put("occurrences", occ);
+  std::vector<double> t{s};
+  bag->Put("seconds", t);
+  return bag;
+}
+
+// raven::Pile::AddLayers on a fresh pile of `len` bases
+ORC_EXPORT orc_bag* ref_pile_add_layers(std::uint32_t id, std::uint32_t len,
+                                        const std::uint32_t* ovl,
+                                        std::uint64_t n, std::uint32_t rounds) {
+  std::vector<biosoup::Overlap> v;
+  for (std::uint64_t i = 0; i < n; ++i) {
+    const std::uint32_t* o = ovl + 8 * i;
+    v.emplace_back(o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7] != 0);
+  }
+  raven::Pile p(id, len);
+  for (std::uint32_t i = 0; i < rounds; ++i) {
+    p.AddLayers(v.begin(), v.end());
+  }
+  PileProbe probe;
+  cereal::access::member_serialize(probe, p);
+  auto* bag = new orc_bag();
+  bag->Put("pile", probe.data);
+  return bag;
+}
+
+ORC_EXPORT std::uint32_t ref_overlap_length(const std::uint32_t* o) {
+  return raven::GetOverlapLength(
+      biosoup::Overlap(o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7] != 0));
+}
