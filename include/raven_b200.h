@@ -1,0 +1,167 @@
+/* raven_b200 — C ABI of the B200-native overlap engine.
+ *
+ * This is the drop-in boundary for the reference's overlap hot path. The
+ * reference has no FFI layer of its own: RavenLib calls C++ classes of
+ * un-vendored dependencies directly. Every entry point below replaces one of
+ * those call sites (file:line are into lbcb-sci/raven @ v1.8.3):
+ *
+ *   rvn_engine_configure   ram::MinimizerEngine ctor   RavenLib/src/construct.cc:661-662
+ *   rvn_reads_upload       biosoup::NucleicAcid fields RavenLib/include/raven/graph/graph.h:13-18
+ *   rvn_minimize           MinimizerEngine::Minimize   RavenLib/src/construct.cc:42-43,363
+ *   rvn_filter             MinimizerEngine::Filter     RavenLib/src/construct.cc:44,372
+ *   rvn_map                MinimizerEngine::Map        RavenLib/src/construct.cc:59-64,377-381
+ *   rvn_pile_add_layers    raven::Pile::AddLayers      RavenLib/src/pile.cc:33-62
+ *   rvn_find_overlaps_and_create_piles
+ *                          raven::FindOverlapsAndCreatePiles
+ *                                                      RavenLib/src/construct.cc:14-121
+ *
+ * The C++ facade over this ABI (include/ram/minimizer_engine.hpp and
+ * raven_b200/host/) keeps the reference's class and function signatures, so
+ * RavenLib's own sources compile against it unchanged.
+ *
+ * Conventions: plain pointers and sizes, POD structs, `int` status (0 = ok,
+ * negative = error; text via rvn_last_error). No exceptions or C++ types
+ * cross this line. Output arrays are owned by the context and stay valid
+ * until the next call on the same context that produces the same kind of
+ * output, or rvn_ctx_destroy. A context is not thread-safe; use one per
+ * host thread / GPU. There is NO CPU fallback: every compute entry point
+ * fails with RVN_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef RAVEN_B200_H_
+#define RAVEN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVN_OK 0
+#define RVN_ERR_INVALID (-1) /* bad argument (mirrors std::invalid_argument) */
+#define RVN_ERR_CUDA (-2)    /* CUDA runtime / no device */
+#define RVN_ERR_STATE (-3)   /* call order (e.g. map before minimize) */
+#define RVN_ERR_LIMIT (-4)   /* input beyond a documented limit */
+
+typedef struct rvn_ctx rvn_ctx;
+
+/* biosoup::Overlap without the alignment string
+ * (field order: RavenLib/src/overlap_utils.cc:5-8) */
+typedef struct rvn_overlap {
+  uint32_t lhs_id, lhs_begin, lhs_end;
+  uint32_t rhs_id, rhs_begin, rhs_end;
+  uint32_t score;
+  uint32_t strand; /* 1 = same strand */
+} rvn_overlap;
+
+/* Counters of the last rvn_map / stage-1 call; the roofline's algorithmic
+ * bytes are computed from these (DESIGN.md "algorithmic bytes"). */
+typedef struct rvn_stats {
+  uint64_t index_bases;     /* bases sketched for the index */
+  uint64_t index_records;   /* minimizer records indexed */
+  uint64_t index_keys;      /* distinct minimizer values */
+  uint64_t query_bases;     /* bases sketched as queries */
+  uint64_t query_records;   /* query minimizers probed */
+  uint64_t hits;            /* seed hits expanded */
+  uint64_t overlaps;        /* overlaps emitted by chaining */
+  uint64_t pile_bins;       /* pile bins updated */
+  uint64_t kernel_launches; /* kernels of this library launched */
+  uint32_t occurrence;      /* frequency threshold in force */
+  uint32_t reserved;
+} rvn_stats;
+
+int rvn_version(void);
+
+/* device: CUDA ordinal. stream: a cudaStream_t to run on (e.g. torch's
+ * current stream) or NULL for a stream owned by the context. */
+int rvn_ctx_create(int device, void* stream, rvn_ctx** out);
+void rvn_ctx_destroy(rvn_ctx* ctx);
+const char* rvn_last_error(const rvn_ctx* ctx);
+
+/* ram::MinimizerEngine(pool, k, w, bandwidth, chain, matches, gap);
+ * k is clamped to [1, 31] like the reference engine. Drops any index. */
+int rvn_engine_configure(rvn_ctx* ctx, uint32_t k, uint32_t w,
+                         uint32_t bandwidth, uint32_t chain, uint32_t matches,
+                         uint32_t gap);
+
+/* The read set, in the biosoup wire format: read i is words[word_off[i] ..
+ * word_off[i+1]) (32 bases per word, base j at bits [(j<<1)&63,+1] of word
+ * j>>5), lens[i] bases, id = i. Host buffers; copied to the device. */
+int rvn_reads_upload(rvn_ctx* ctx, const uint64_t* words,
+                     const uint64_t* word_off, const uint32_t* lens,
+                     uint32_t n_reads);
+
+/* Minimize(reads[first..last), minhash): sketch and index. */
+int rvn_minimize(rvn_ctx* ctx, uint32_t first, uint32_t last, int minhash);
+
+/* Filter(frequency): occurrence threshold of the current index.
+ * frequency outside [0,1] -> RVN_ERR_INVALID (reference throws). */
+int rvn_filter(rvn_ctx* ctx, double frequency, uint32_t* occurrence);
+
+/* Map(read, avoid_equal, avoid_symmetric, minhash[, &filtered]) for every
+ * read in [first, last) against the current index. Overlaps come back
+ * grouped by query in ascending id, each group in the reference engine's
+ * emission order; ovl_off has (last-first)+1 entries. `filtered` are the
+ * positions of over-frequent query minimizers (only if want_filtered). */
+int rvn_map(rvn_ctx* ctx, uint32_t first, uint32_t last, int avoid_equal,
+            int avoid_symmetric, int minhash, int want_filtered);
+int rvn_map_results(rvn_ctx* ctx, const rvn_overlap** overlaps,
+                    const uint64_t** ovl_off, uint64_t* n_overlaps,
+                    const uint32_t** filtered, const uint64_t** filt_off);
+
+/* Pile::AddLayers on a batch of piles: pile i has bins[i] uint16 counters at
+ * data + bin_off[i]; every overlap adds +1 to bins [(begin>>4)+1, (end>>4)-1)
+ * of the pile of its lhs and of its rhs read, saturating at 65535.
+ * Precondition (holds for every chained overlap): *_end >= 16. */
+int rvn_pile_add_layers(rvn_ctx* ctx, uint16_t* data, const uint64_t* bin_off,
+                        uint32_t n_piles, const rvn_overlap* overlaps,
+                        uint64_t n_overlaps);
+
+/* raven::FindOverlapsAndCreatePiles over the uploaded read set: index batches
+ * of >= index_batch_bases (reference: 1<<32), query flushes of >=
+ * query_batch_bases (reference: 1<<30); pass 0 for the reference values.
+ * Results: per read the kept overlaps (<= max_overlaps after the reference's
+ * truncation rule) and the pile histogram (len>>4 uint16 bins). */
+int rvn_find_overlaps_and_create_piles(rvn_ctx* ctx, double frequency,
+                                       uint64_t max_overlaps, int minhash,
+                                       uint64_t index_batch_bases,
+                                       uint64_t query_batch_bases);
+int rvn_stage1_results(rvn_ctx* ctx, const rvn_overlap** overlaps,
+                       const uint64_t** ovl_off, const uint16_t** pile,
+                       const uint64_t** pile_off, uint64_t* n_mapped);
+
+/* ---- introspection (parity tests, profiling) ---- */
+
+/* Per-read sketches of reads [first,last) exactly as the reference engine's
+ * Minimize(sequence, minhash) returns them: value[], origin[] and
+ * (last-first)+1 offsets. */
+int rvn_sketch(rvn_ctx* ctx, uint32_t first, uint32_t last, int minhash,
+               const uint64_t** value, const uint64_t** origin,
+               const uint64_t** offsets, uint64_t* n_records);
+
+/* The index as sorted (value, origin) records + distinct-key statistics. */
+int rvn_index_records(rvn_ctx* ctx, const uint64_t** value,
+                      const uint64_t** origin, uint64_t* n_records,
+                      uint64_t* n_keys);
+
+/* Seed hits of the last rvn_map call with keep_hits set via rvn_set_option:
+ * group[], positions[] and per-query offsets, unsorted within a query. */
+int rvn_map_hits(rvn_ctx* ctx, const uint64_t** group,
+                 const uint64_t** positions, const uint64_t** hit_off,
+                 uint64_t* n_hits);
+
+int rvn_get_stats(rvn_ctx* ctx, rvn_stats* out);
+
+/* options: "keep_hits" (0/1). Unknown name -> RVN_ERR_INVALID. */
+int rvn_set_option(rvn_ctx* ctx, const char* name, int64_t value);
+
+/* Device time (ms, CUDA events on the context's stream) of the phases of the
+ * last stage-1 / minimize / map call: names[] are static strings. */
+int rvn_get_timings(rvn_ctx* ctx, const char* const** names,
+                    const float** ms, uint32_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RAVEN_B200_H_ */

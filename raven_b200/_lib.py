@@ -1,0 +1,82 @@
+"""ctypes loader of the C ABI (include/raven_b200.h).  The shared library is
+built in-tree by __graft_entry__.build(); there is no fallback of any kind:
+a missing library or a missing GPU is an error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libraven_b200.so")
+
+U64P = C.POINTER(C.c_uint64)
+U32P = C.POINTER(C.c_uint32)
+U16P = C.POINTER(C.c_uint16)
+
+
+class Overlap(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in (
+        "lhs_id", "lhs_begin", "lhs_end", "rhs_id", "rhs_begin", "rhs_end",
+        "score", "strand")]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "index_bases", "index_records", "index_keys", "query_bases",
+        "query_records", "hits", "overlaps", "pile_bins", "kernel_launches")] + [
+        ("occurrence", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+OVLP = C.POINTER(Overlap)
+
+# every symbol include/raven_b200.h declares, with its signature
+SIGNATURES = {
+    "rvn_version": (C.c_int, []),
+    "rvn_ctx_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "rvn_ctx_destroy": (None, [C.c_void_p]),
+    "rvn_last_error": (C.c_char_p, [C.c_void_p]),
+    "rvn_engine_configure": (C.c_int, [C.c_void_p] + [C.c_uint32] * 6),
+    "rvn_reads_upload": (C.c_int, [C.c_void_p, U64P, U64P, U32P, C.c_uint32]),
+    "rvn_minimize": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]),
+    "rvn_filter": (C.c_int, [C.c_void_p, C.c_double, U32P]),
+    "rvn_map": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                          C.c_int, C.c_int]),
+    "rvn_map_results": (C.c_int, [C.c_void_p, C.POINTER(OVLP), C.POINTER(U64P),
+                                  U64P, C.POINTER(U32P), C.POINTER(U64P)]),
+    "rvn_pile_add_layers": (C.c_int, [C.c_void_p, U16P, U64P, C.c_uint32, OVLP,
+                                      C.c_uint64]),
+    "rvn_find_overlaps_and_create_piles": (
+        C.c_int, [C.c_void_p, C.c_double, C.c_uint64, C.c_int, C.c_uint64,
+                  C.c_uint64]),
+    "rvn_stage1_results": (C.c_int, [C.c_void_p, C.POINTER(OVLP), C.POINTER(U64P),
+                                     C.POINTER(U16P), C.POINTER(U64P), U64P]),
+    "rvn_sketch": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
+                             C.POINTER(U64P), C.POINTER(U64P), C.POINTER(U64P),
+                             U64P]),
+    "rvn_index_records": (C.c_int, [C.c_void_p, C.POINTER(U64P), C.POINTER(U64P),
+                                    U64P, U64P]),
+    "rvn_map_hits": (C.c_int, [C.c_void_p, C.POINTER(U64P), C.POINTER(U64P),
+                               C.POINTER(U64P), U64P]),
+    "rvn_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "rvn_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "rvn_get_timings": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(C.c_char_p)),
+                                  C.POINTER(C.POINTER(C.c_float)), U32P]),
+}
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python __graft_entry__.py` to "
+                "build the CUDA extension (there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

@@ -1,0 +1,475 @@
+// raven_b200 — the C ABI (include/raven_b200.h) over the overlap engine, and
+// the stage-1 driver that replaces raven::FindOverlapsAndCreatePiles
+// (RavenLib/src/construct.cc:14-121).
+#include <algorithm>
+#include <cstring>
+#include <thread>
+
+#include "engine.cuh"
+
+using namespace rvn;
+
+struct rvn_ctx {
+  Ctx c;
+};
+
+namespace {
+
+template <typename F>
+int Guard(rvn_ctx* ctx, F&& f) {
+  if (!ctx) return RVN_ERR_INVALID;
+  try {
+    RVN_CUDA(cudaSetDevice(ctx->c.device));
+    f(ctx->c);
+    ctx->c.err.clear();
+    return RVN_OK;
+  } catch (const InvalidArgument& e) {
+    ctx->c.err = e.what();
+    return RVN_ERR_INVALID;
+  } catch (const StateError& e) {
+    ctx->c.err = e.what();
+    return RVN_ERR_STATE;
+  } catch (const LimitError& e) {
+    ctx->c.err = e.what();
+    return RVN_ERR_LIMIT;
+  } catch (const CudaError& e) {
+    ctx->c.err = e.what();
+    return RVN_ERR_CUDA;
+  } catch (const std::exception& e) {
+    ctx->c.err = e.what();
+    return RVN_ERR_CUDA;
+  }
+}
+
+void CheckRange(const Ctx& c, uint32_t first, uint32_t last) {
+  if (first > last || last > c.n_reads) {
+    throw InvalidArgument("read range out of bounds");
+  }
+}
+
+inline rvn_overlap Reverse(const rvn_overlap& o) {  // overlap_utils.cc:5-8
+  return rvn_overlap{o.rhs_id, o.rhs_begin, o.rhs_end, o.lhs_id,
+                     o.lhs_begin, o.lhs_end, o.score, o.strand};
+}
+
+inline uint32_t Length(const rvn_overlap& o) {  // overlap_utils.cc:10-12
+  return std::max(o.rhs_end - o.rhs_begin, o.lhs_end - o.lhs_begin);
+}
+
+template <typename F>
+void ParallelFor(size_t n, F&& f) {
+  unsigned t = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+  if (n < 4096 || t == 1) {
+    for (size_t i = 0; i < n; ++i) f(i);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t chunk = (n + t - 1) / t;
+  for (unsigned k = 0; k < t; ++k) {
+    const size_t b = k * chunk, e = std::min(n, b + chunk);
+    if (b >= e) break;
+    th.emplace_back([b, e, &f] {
+      for (size_t i = b; i < e; ++i) f(i);
+    });
+  }
+  for (auto& x : th) x.join();
+}
+
+// raven::FindOverlapsAndCreatePiles, same batch / flush schedule as the
+// reference; GPU for Minimize, Filter, Map and AddLayers, host for the serial
+// gather and the (libstdc++ std::sort) truncation rule.
+void Stage1(Ctx& c, double freq, uint64_t kmax, bool minhash, uint64_t ib,
+            uint64_t qb) {
+  if (ib == 0) ib = 1ULL << 32;
+  if (qb == 0) qb = 1ULL << 30;
+  if (!(0 <= freq && freq <= 1)) {
+    throw InvalidArgument(
+        "[ram::MinimizerEngine::Filter] error: invalid frequency");
+  }
+  c.st_valid = false;
+  TimerReset(c);
+  std::memset(&c.stats, 0, sizeof(c.stats));
+  const uint64_t launches0 = c.launches;
+  const uint32_t n = c.n_reads;
+
+  // piles: len >> 4 bins each (pile.cc:19-31)
+  c.st_pile_off.assign(n + 1ULL, 0);
+  for (uint32_t i = 0; i < n; ++i) {
+    c.st_pile_off[i + 1] = c.st_pile_off[i] + (c.h_len[i] >> 4);
+  }
+  const uint64_t total_bins = c.st_pile_off[n];
+  uint16_t* d_pile = c.p_data.reserve(total_bins + 1);
+  uint64_t* d_poff = c.p_off.reserve(n + 1ULL);
+  RVN_CUDA(cudaMemsetAsync(d_pile, 0, (total_bins + 1) * sizeof(uint16_t), c.stream));
+  RVN_CUDA(cudaMemcpyAsync(d_poff, c.st_pile_off.data(), (n + 1ULL) * 8,
+                           cudaMemcpyHostToDevice, c.stream));
+
+  std::vector<std::vector<rvn_overlap>> lists(n);
+  std::vector<uint8_t> touched(n, 0);
+  std::vector<uint32_t> touched_ids;
+  c.st_mapped = 0;
+
+  uint64_t bases = 0;
+  for (uint32_t i = 0, j = 0; i < n; ++i) {
+    bases += c.h_len[i];
+    if (i != n - 1 && bases < ib) continue;
+    bases = 0;
+
+    BuildIndex(c, j, i + 1, minhash);
+    FilterIndex(c, freq);
+
+    for (uint32_t k = 0, k0 = 0; k < i + 1; ++k) {
+      bases += c.h_len[k];
+      if (k != i && bases < qb) continue;
+      bases = 0;
+
+      MapRange(c, k0, k + 1, true, true, true, false);
+      PileAddLayersDevice(c, d_pile, d_poff, c.st_pile_off.data(), n,
+                          c.m_ovl.get(), c.r_n_ovl);
+
+      // serial gather in query order: forward record, then mirrored record
+      touched_ids.clear();
+      const rvn_overlap* o = c.r_ovl.get();
+      for (uint64_t e = 0; e < c.r_n_ovl; ++e) {
+        lists[o[e].lhs_id].push_back(o[e]);
+        lists[o[e].rhs_id].push_back(Reverse(o[e]));
+        if (!touched[o[e].lhs_id]) {
+          touched[o[e].lhs_id] = 1;
+          touched_ids.push_back(o[e].lhs_id);
+        }
+        if (!touched[o[e].rhs_id]) {
+          touched[o[e].rhs_id] = 1;
+          touched_ids.push_back(o[e].rhs_id);
+        }
+      }
+      c.st_mapped += c.r_n_ovl;
+      // keep the kmax longest of every list that grew (construct.cc:92-107)
+      ParallelFor(touched_ids.size(), [&](size_t t) {
+        auto& l = lists[touched_ids[t]];
+        touched[touched_ids[t]] = 0;
+        if (l.size() < kmax) return;
+        std::sort(l.begin(), l.end(),
+                  [](const rvn_overlap& a, const rvn_overlap& b) {
+                    return Length(a) > Length(b);
+                  });
+        l.resize(kmax);
+      });
+      k0 = k + 1;
+    }
+    j = i + 1;
+  }
+
+  c.st_ovl_off.assign(n + 1ULL, 0);
+  for (uint32_t i = 0; i < n; ++i) {
+    c.st_ovl_off[i + 1] = c.st_ovl_off[i] + lists[i].size();
+  }
+  c.st_ovl.resize(c.st_ovl_off[n]);
+  ParallelFor(n, [&](size_t i) {
+    std::copy(lists[i].begin(), lists[i].end(), c.st_ovl.begin() + c.st_ovl_off[i]);
+  });
+  c.st_pile.resize(total_bins);
+  RVN_CUDA(cudaMemcpyAsync(c.st_pile.data(), d_pile, total_bins * sizeof(uint16_t),
+                           cudaMemcpyDeviceToHost, c.stream));
+  RVN_CUDA(cudaStreamSynchronize(c.stream));
+  TimerCollect(c);
+  c.stats.kernel_launches = c.launches - launches0;
+  c.stats.occurrence = c.occurrence;
+  c.st_valid = true;
+}
+
+}  // namespace
+
+extern "C" {
+
+#define RVN_API __attribute__((visibility("default")))
+
+RVN_API int rvn_version(void) { return 100; }
+
+RVN_API int rvn_ctx_create(int device, void* stream, rvn_ctx** out) {
+  if (!out) return RVN_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    return RVN_ERR_CUDA;  // no CPU fallback: a usable device is mandatory
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+    return RVN_ERR_CUDA;
+  }
+  auto* ctx = new rvn_ctx();
+  ctx->c.device = device;
+  int rc = Guard(ctx, [&](Ctx& c) {
+    if (stream) {
+      c.stream = static_cast<cudaStream_t>(stream);
+    } else {
+      RVN_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+      c.own_stream = true;
+    }
+  });
+  if (rc != RVN_OK) {
+    delete ctx;
+    return rc;
+  }
+  *out = ctx;
+  return RVN_OK;
+}
+
+RVN_API void rvn_ctx_destroy(rvn_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->c.device);
+  cudaStreamSynchronize(ctx->c.stream);
+  for (auto& p : ctx->c.timer.pending) {
+    if (p.first) cudaEventDestroy(p.first);
+    if (p.second) cudaEventDestroy(p.second);
+  }
+  for (auto e : ctx->c.timer.pool) cudaEventDestroy(e);
+  if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
+  delete ctx;
+}
+
+RVN_API const char* rvn_last_error(const rvn_ctx* ctx) {
+  return ctx ? ctx->c.err.c_str() : "null context";
+}
+
+RVN_API int rvn_engine_configure(rvn_ctx* ctx, uint32_t k, uint32_t w,
+                                 uint32_t bandwidth, uint32_t chain,
+                                 uint32_t matches, uint32_t gap) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (w == 0) throw InvalidArgument("window length must be positive");
+    if (w > kMaxWindow) throw LimitError("window length above 256");
+    c.prm.k = std::min(std::max(k, 1u), 31u);
+    c.prm.w = w;
+    c.prm.bandwidth = bandwidth;
+    c.prm.chain = chain;
+    c.prm.matches = matches;
+    c.prm.gap = gap;
+    c.s_valid = c.q_valid = c.i_valid = c.r_valid = false;
+    c.occurrence = 0xFFFFFFFFu;
+  });
+}
+
+RVN_API int rvn_reads_upload(rvn_ctx* ctx, const uint64_t* words,
+                             const uint64_t* word_off, const uint32_t* lens,
+                             uint32_t n_reads) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (n_reads && (!word_off || !lens)) throw InvalidArgument("null read set");
+    c.s_valid = c.q_valid = c.i_valid = c.r_valid = c.st_valid = false;
+    c.tiles_k = 0;
+    c.n_reads = n_reads;
+    c.h_woff.assign(word_off, word_off + n_reads + (n_reads ? 1 : 0));
+    if (!n_reads) c.h_woff.assign(1, 0);
+    c.h_len.assign(lens, lens + n_reads);
+    for (uint32_t i = 0; i < n_reads; ++i) {
+      const uint64_t have = c.h_woff[i + 1] - c.h_woff[i];
+      if (have < ((static_cast<uint64_t>(lens[i]) + 31) >> 5)) {
+        throw InvalidArgument("read shorter than its declared length");
+      }
+      if (lens[i] >= (1u << 31)) throw LimitError("read of 2^31 or more bases");
+    }
+    c.n_words = c.h_woff[n_reads];
+    uint64_t* dw = c.d_words.reserve(c.n_words + 2);
+    uint64_t* dwo = c.d_woff.reserve(n_reads + 1ULL);
+    uint32_t* dl = c.d_len.reserve(n_reads + 1ULL);
+    if (c.n_words) {
+      RVN_CUDA(cudaMemcpyAsync(dw, words, c.n_words * 8, cudaMemcpyHostToDevice,
+                               c.stream));
+    }
+    RVN_CUDA(cudaMemcpyAsync(dwo, c.h_woff.data(), (n_reads + 1ULL) * 8,
+                             cudaMemcpyHostToDevice, c.stream));
+    if (n_reads) {
+      RVN_CUDA(cudaMemcpyAsync(dl, c.h_len.data(), n_reads * 4ULL,
+                               cudaMemcpyHostToDevice, c.stream));
+    }
+    RVN_CUDA(cudaStreamSynchronize(c.stream));
+  });
+}
+
+RVN_API int rvn_minimize(rvn_ctx* ctx, uint32_t first, uint32_t last,
+                         int minhash) {
+  return Guard(ctx, [&](Ctx& c) {
+    CheckRange(c, first, last);
+    BuildIndex(c, first, last, minhash != 0);
+  });
+}
+
+RVN_API int rvn_filter(rvn_ctx* ctx, double frequency, uint32_t* occurrence) {
+  return Guard(ctx, [&](Ctx& c) {
+    uint32_t occ = FilterIndex(c, frequency);
+    if (occurrence) *occurrence = occ;
+  });
+}
+
+RVN_API int rvn_map(rvn_ctx* ctx, uint32_t first, uint32_t last,
+                    int avoid_equal, int avoid_symmetric, int minhash,
+                    int want_filtered) {
+  return Guard(ctx, [&](Ctx& c) {
+    CheckRange(c, first, last);
+    MapRange(c, first, last, avoid_equal != 0, avoid_symmetric != 0,
+             minhash != 0, want_filtered != 0);
+    TimerCollect(c);
+  });
+}
+
+RVN_API int rvn_map_results(rvn_ctx* ctx, const rvn_overlap** overlaps,
+                            const uint64_t** ovl_off, uint64_t* n_overlaps,
+                            const uint32_t** filtered,
+                            const uint64_t** filt_off) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (!c.r_valid) throw StateError("no map results");
+    if (overlaps) *overlaps = c.r_ovl.get();
+    if (ovl_off) *ovl_off = c.r_ovl_off.get();
+    if (n_overlaps) *n_overlaps = c.r_n_ovl;
+    if (filtered) *filtered = c.r_filtered.get();
+    if (filt_off) *filt_off = c.r_filt_off.get();
+  });
+}
+
+RVN_API int rvn_pile_add_layers(rvn_ctx* ctx, uint16_t* data,
+                                const uint64_t* bin_off, uint32_t n_piles,
+                                const rvn_overlap* overlaps,
+                                uint64_t n_overlaps) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (n_piles == 0) return;
+    if (!data || !bin_off) throw InvalidArgument("null piles");
+    const uint64_t bins = bin_off[n_piles];
+    uint16_t* d = c.p_data.reserve(bins + 1);
+    uint64_t* off = c.p_off.reserve(n_piles + 1ULL);
+    rvn_overlap* o = c.p_ovl.reserve(n_overlaps + 1);
+    RVN_CUDA(cudaMemcpyAsync(d, data, bins * 2, cudaMemcpyHostToDevice, c.stream));
+    RVN_CUDA(cudaMemcpyAsync(off, bin_off, (n_piles + 1ULL) * 8,
+                             cudaMemcpyHostToDevice, c.stream));
+    RVN_CUDA(cudaMemcpyAsync(o, overlaps, n_overlaps * sizeof(rvn_overlap),
+                             cudaMemcpyHostToDevice, c.stream));
+    PileAddLayersDevice(c, d, off, bin_off, n_piles, o, n_overlaps);
+    RVN_CUDA(cudaMemcpyAsync(data, d, bins * 2, cudaMemcpyDeviceToHost, c.stream));
+    RVN_CUDA(cudaStreamSynchronize(c.stream));
+    TimerCollect(c);
+  });
+}
+
+RVN_API int rvn_find_overlaps_and_create_piles(rvn_ctx* ctx, double frequency,
+                                               uint64_t max_overlaps,
+                                               int minhash,
+                                               uint64_t index_batch_bases,
+                                               uint64_t query_batch_bases) {
+  return Guard(ctx, [&](Ctx& c) {
+    Stage1(c, frequency, max_overlaps, minhash != 0, index_batch_bases,
+           query_batch_bases);
+  });
+}
+
+RVN_API int rvn_stage1_results(rvn_ctx* ctx, const rvn_overlap** overlaps,
+                               const uint64_t** ovl_off, const uint16_t** pile,
+                               const uint64_t** pile_off, uint64_t* n_mapped) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (!c.st_valid) throw StateError("no stage-1 results");
+    if (overlaps) *overlaps = c.st_ovl.data();
+    if (ovl_off) *ovl_off = c.st_ovl_off.data();
+    if (pile) *pile = c.st_pile.data();
+    if (pile_off) *pile_off = c.st_pile_off.data();
+    if (n_mapped) *n_mapped = c.st_mapped;
+  });
+}
+
+RVN_API int rvn_sketch(rvn_ctx* ctx, uint32_t first, uint32_t last, int minhash,
+                       const uint64_t** value, const uint64_t** origin,
+                       const uint64_t** offsets, uint64_t* n_records) {
+  return Guard(ctx, [&](Ctx& c) {
+    CheckRange(c, first, last);
+    const uint32_t nr = last - first;
+    const uint64_t *dv, *dorg;
+    const std::vector<uint64_t>* hoff;
+    uint64_t total;
+    EnsureSketch(c, first, last);
+    if (minhash) {
+      EnsureMicromizers(c, first, last);
+      dv = c.q_val.get();
+      dorg = c.q_org.get();
+      hoff = &c.h_q_off;
+      total = c.q_n;
+    } else {
+      dv = c.s_val.get();
+      dorg = c.s_org.get();
+      hoff = &c.h_s_off;
+      total = c.s_n;
+    }
+    uint64_t* hv = c.x_val.reserve(total + 1);
+    uint64_t* ho = c.x_org.reserve(total + 1);
+    uint64_t* hf = c.x_off.reserve(nr + 2ULL);
+    RVN_CUDA(cudaMemcpyAsync(hv, dv, total * 8, cudaMemcpyDeviceToHost, c.stream));
+    RVN_CUDA(cudaMemcpyAsync(ho, dorg, total * 8, cudaMemcpyDeviceToHost, c.stream));
+    for (uint32_t i = 0; i <= nr; ++i) hf[i] = (*hoff)[i];
+    RVN_CUDA(cudaStreamSynchronize(c.stream));
+    TimerCollect(c);
+    if (value) *value = hv;
+    if (origin) *origin = ho;
+    if (offsets) *offsets = hf;
+    if (n_records) *n_records = total;
+  });
+}
+
+RVN_API int rvn_index_records(rvn_ctx* ctx, const uint64_t** value,
+                              const uint64_t** origin, uint64_t* n_records,
+                              uint64_t* n_keys) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (!c.i_valid) throw StateError("no index");
+    uint64_t* hv = c.x_val.reserve(c.i_n + 1);
+    uint64_t* ho = c.x_org.reserve(c.i_n + 1);
+    RVN_CUDA(cudaMemcpyAsync(hv, c.i_val.get(), c.i_n * 8, cudaMemcpyDeviceToHost,
+                             c.stream));
+    RVN_CUDA(cudaMemcpyAsync(ho, c.i_org.get(), c.i_n * 8, cudaMemcpyDeviceToHost,
+                             c.stream));
+    RVN_CUDA(cudaStreamSynchronize(c.stream));
+    if (value) *value = hv;
+    if (origin) *origin = ho;
+    if (n_records) *n_records = c.i_n;
+    if (n_keys) *n_keys = c.i_keys;
+  });
+}
+
+RVN_API int rvn_map_hits(rvn_ctx* ctx, const uint64_t** group,
+                         const uint64_t** positions, const uint64_t** hit_off,
+                         uint64_t* n_hits) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (!c.r_valid || !c.keep_hits) throw StateError("hits were not kept");
+    if (group) *group = c.r_hit_grp.get();
+    if (positions) *positions = c.r_hit_pos.get();
+    if (hit_off) *hit_off = c.r_hit_off.get();
+    if (n_hits) *n_hits = c.r_n_hits;
+  });
+}
+
+RVN_API int rvn_get_stats(rvn_ctx* ctx, rvn_stats* out) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (!out) throw InvalidArgument("null stats");
+    *out = c.stats;
+    out->occurrence = c.occurrence;
+    out->kernel_launches = c.launches;
+  });
+}
+
+RVN_API int rvn_set_option(rvn_ctx* ctx, const char* name, int64_t value) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (name && std::strcmp(name, "keep_hits") == 0) {
+      c.keep_hits = value != 0;
+    } else if (name && std::strcmp(name, "reset_stats") == 0) {
+      std::memset(&c.stats, 0, sizeof(c.stats));
+      c.launches = 0;
+      TimerReset(c);
+    } else {
+      throw InvalidArgument("unknown option");
+    }
+  });
+}
+
+RVN_API int rvn_get_timings(rvn_ctx* ctx, const char* const** names,
+                            const float** ms, uint32_t* n) {
+  return Guard(ctx, [&](Ctx& c) {
+    TimerCollect(c);
+    if (names) *names = c.timer.names.data();
+    if (ms) *ms = c.timer.ms.data();
+    if (n) *n = static_cast<uint32_t>(c.timer.names.size());
+  });
+}
+
+}  // extern "C"

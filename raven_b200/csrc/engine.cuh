@@ -1,0 +1,169 @@
+// raven_b200 — overlap engine context and stage entry points (host side).
+//
+// Data layout in HBM (all SoA, 8-byte fields):
+//   reads      words[]           2-bit packed, biosoup layout, 0.25 B/base
+//   sketch     s_val[], s_org[]  minimizer records in (read, position) order
+//   queries    q_val[], q_org[]  micromizers (len/k smallest per read)
+//   index      i_val[], i_org[]  sketch stably sorted by value + bucket table
+//   hits       h_grp[], h_pos[]  ram "Match" records grouped by query read
+//   overlaps   rvn_overlap[]     32 B records grouped by query read
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "../../include/raven_b200.h"
+#include "common.cuh"
+
+namespace rvn {
+
+struct Params {
+  uint32_t k = 15, w = 5, bandwidth = 500, chain = 4, matches = 100;
+  uint32_t gap = 10000;
+};
+
+// k-mer positions handled by one CTA of the sketch kernels
+constexpr uint32_t kSketchTile = 2048;
+constexpr uint32_t kSketchThreads = 256;
+constexpr uint32_t kMaxWindow = 256;  // w limit (halo staged in shared memory)
+
+struct PhaseTimer {
+  std::vector<const char*> names;
+  std::vector<float> ms;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  std::vector<cudaEvent_t> pool;
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  Params prm;
+  bool keep_hits = false;
+  rvn_stats stats{};
+
+  // ---- reads ----
+  uint32_t n_reads = 0;
+  uint64_t n_words = 0;
+  DevBuf<uint64_t> d_words, d_woff;
+  DevBuf<uint32_t> d_len;
+  std::vector<uint64_t> h_woff;
+  std::vector<uint32_t> h_len;
+  // sketch tiles: tile_off[r] = first tile of read r (depends on k)
+  std::vector<uint64_t> h_tile_off;
+  DevBuf<uint64_t> d_tile_off;
+  uint32_t tiles_k = 0;
+
+  // ---- current sketch (full minimizers of reads [s_first, s_last)) ----
+  bool s_valid = false;
+  uint32_t s_first = 0, s_last = 0;
+  uint64_t s_n = 0;
+  DevBuf<uint64_t> s_val, s_org, s_off;  // s_off: (s_last-s_first)+1
+  std::vector<uint64_t> h_s_off;
+  DevBuf<uint32_t> tile_cnt;
+  DevBuf<uint64_t> tile_out;
+
+  // ---- current micromizer set (of reads [q_first, q_last)) ----
+  bool q_valid = false;
+  uint32_t q_first = 0, q_last = 0;
+  uint64_t q_n = 0;
+  DevBuf<uint64_t> q_val, q_org, q_off;
+  std::vector<uint64_t> h_q_off;
+
+  // ---- index ----
+  bool i_valid = false;
+  uint32_t i_first = 0, i_last = 0;
+  uint64_t i_n = 0, i_keys = 0;
+  DevBuf<uint64_t> i_val, i_org, i_val_alt, i_org_alt;
+  DevBuf<uint32_t> i_bucket;
+  int i_bucket_bits = 0;
+  DevBuf<uint32_t> i_run_start;  // first record of every distinct key
+  uint32_t occurrence = 0xFFFFFFFFu;
+  DevBuf<uint8_t> sort_tmp;
+
+  // ---- map ----
+  DevBuf<uint32_t> m_cnt, m_first;
+  DevBuf<uint8_t> m_filt;
+  DevBuf<uint64_t> m_hit_off;  // per query record (+1)
+  DevBuf<uint64_t> h_grp, h_pos;
+  DevBuf<uint64_t> m_read_hit_off;  // per query read (+1)
+  DevBuf<uint64_t> m_scratch64;     // oversize chain scratch
+  DevBuf<uint32_t> m_scratch32;
+  DevBuf<rvn_overlap> m_ovl_raw, m_ovl;
+  DevBuf<uint64_t> m_ovl_loc;  // per read: base<<24 | count  (raw placement)
+  DevBuf<uint64_t> m_ovl_off;
+  DevBuf<uint64_t> m_counter;
+  DevBuf<uint32_t> m_filtered;
+  DevBuf<uint64_t> m_filt_off;
+  DevBuf<uint64_t> scan_tmp;
+  uint64_t m_hits = 0;
+  uint32_t m_first_read = 0, m_last_read = 0;
+
+  // host-side results of the last map
+  PinBuf<rvn_overlap> r_ovl;
+  PinBuf<uint64_t> r_ovl_off;
+  PinBuf<uint32_t> r_filtered;
+  PinBuf<uint64_t> r_filt_off;
+  uint64_t r_n_ovl = 0;
+  bool r_valid = false;
+  PinBuf<uint64_t> r_hit_grp, r_hit_pos, r_hit_off;
+  uint64_t r_n_hits = 0;
+
+  // introspection staging
+  PinBuf<uint64_t> x_val, x_org, x_off;
+
+  // ---- piles ----
+  DevBuf<int32_t> p_diff;
+  DevBuf<uint16_t> p_data;
+  DevBuf<uint64_t> p_off;
+  DevBuf<rvn_overlap> p_ovl;
+
+  // ---- stage-1 results ----
+  std::vector<rvn_overlap> st_ovl;
+  std::vector<uint64_t> st_ovl_off;
+  std::vector<uint16_t> st_pile;
+  std::vector<uint64_t> st_pile_off;
+  uint64_t st_mapped = 0;
+  bool st_valid = false;
+
+  // pinned scalars for small D2H reads
+  PinBuf<uint64_t> pin64;
+
+  PhaseTimer timer;
+  uint64_t launches = 0;
+};
+
+// ---- utilities (scan.cu) ----
+// out[i] = sum_{j<i} in[j] for i in [0, n]; out has n + 1 entries.
+void ExclusiveScanU32(Ctx& c, const uint32_t* in, uint64_t* out, uint64_t n);
+uint64_t ReadU64(Ctx& c, const uint64_t* dptr);  // sync D2H of one value
+
+void TimerBegin(Ctx& c, const char* name);
+void TimerEnd(Ctx& c);
+void TimerCollect(Ctx& c);
+void TimerReset(Ctx& c);
+
+// ---- sketch.cu ----
+void EnsureTiles(Ctx& c);
+// full minimizers of reads [first,last) into c.s_* (no-op if already there)
+void EnsureSketch(Ctx& c, uint32_t first, uint32_t last);
+// micromizers of reads [first,last) into c.q_* (needs the sketch of a range
+// that contains [first,last))
+void EnsureMicromizers(Ctx& c, uint32_t first, uint32_t last);
+
+// ---- index.cu ----
+void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash);
+uint32_t FilterIndex(Ctx& c, double frequency);
+
+// ---- map.cu ----
+void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
+              bool avoid_symmetric, bool minhash, bool want_filtered);
+
+// ---- pile.cu ----
+// data: device u16 bins, off: device u64 offsets (n_piles + 1)
+void PileAddLayersDevice(Ctx& c, uint16_t* d_data, const uint64_t* d_off,
+                         const uint64_t* h_off, uint32_t n_piles,
+                         const rvn_overlap* d_ovl, uint64_t n_ovl);
+
+}  // namespace rvn

@@ -1,0 +1,97 @@
+// raven_b200 — pile-o-gram coverage update on sm_100a.
+//
+// Replaces raven::Pile::AddLayers (RavenLib/src/pile.cc:33-62; bins of 16
+// bases, kPSS = 4, pile.h:21). The reference sorts begin/end marks per pile
+// and sweeps; here every overlap side drops +1/-1 into a per-bin difference
+// array (atomics), and one warp per pile turns the differences into coverage
+// with a shuffle scan and adds it to the uint16 bins, saturating at 65535.
+// The running coverage is kept modulo 2^32 exactly like the reference's
+// unsigned counter, so the result is bit-identical.
+#include "engine.cuh"
+
+namespace rvn {
+
+namespace {
+
+__global__ void ScatterMarks(const rvn_overlap* __restrict__ ovl, uint64_t n,
+                             const uint64_t* __restrict__ bin_off,
+                             uint32_t n_piles, int32_t* __restrict__ diff) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const rvn_overlap o = ovl[i];
+  // pile p owns diff[bin_off[p] + p .. bin_off[p+1] + p]  (bins + 1 slots)
+  if (o.lhs_id < n_piles) {
+    const uint64_t base = bin_off[o.lhs_id] + o.lhs_id;
+    const uint64_t bins = bin_off[o.lhs_id + 1] - bin_off[o.lhs_id];
+    const uint32_t b = (o.lhs_begin >> 4) + 1, e = (o.lhs_end >> 4) - 1;
+    if (b <= bins && e <= bins) {
+      atomicAdd(diff + base + b, 1);
+      atomicAdd(diff + base + e, -1);
+    }
+  }
+  if (o.rhs_id < n_piles) {
+    const uint64_t base = bin_off[o.rhs_id] + o.rhs_id;
+    const uint64_t bins = bin_off[o.rhs_id + 1] - bin_off[o.rhs_id];
+    const uint32_t b = (o.rhs_begin >> 4) + 1, e = (o.rhs_end >> 4) - 1;
+    if (b <= bins && e <= bins) {
+      atomicAdd(diff + base + b, 1);
+      atomicAdd(diff + base + e, -1);
+    }
+  }
+}
+
+// one warp per pile: inclusive scan of the differences, saturating add,
+// and the differences are cleared for the next call
+__global__ void __launch_bounds__(256)
+ApplyCoverage(uint16_t* __restrict__ data, const uint64_t* __restrict__ bin_off,
+              uint32_t n_piles, int32_t* __restrict__ diff) {
+  const uint32_t p = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (p >= n_piles) return;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t b0 = bin_off[p];
+  const uint32_t bins = static_cast<uint32_t>(bin_off[p + 1] - b0);
+  int32_t* d = diff + b0 + p;
+  uint16_t* out = data + b0;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base <= bins; base += 32) {
+    const uint32_t i = base + lane;
+    uint32_t v = i <= bins ? static_cast<uint32_t>(d[i]) : 0u;
+    if (i <= bins && v) d[i] = 0;
+    uint32_t incl = v;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, s);
+      if (lane >= s) incl += o;
+    }
+    const uint32_t cov = carry + incl;
+    if (i < bins && cov != 0) {
+      const uint32_t sum = static_cast<uint32_t>(out[i]) + cov;  // wraps like the reference
+      out[i] = sum < 65535u ? static_cast<uint16_t>(sum) : 65535;
+    }
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+}  // namespace
+
+void PileAddLayersDevice(Ctx& c, uint16_t* d_data, const uint64_t* d_off,
+                         const uint64_t* h_off, uint32_t n_piles,
+                         const rvn_overlap* d_ovl, uint64_t n_ovl) {
+  if (n_piles == 0 || n_ovl == 0) return;
+  const uint64_t slots = h_off[n_piles] + n_piles;
+  if (c.p_diff.cap < slots) {
+    int32_t* d = c.p_diff.reserve(slots);
+    RVN_CUDA(cudaMemsetAsync(d, 0, c.p_diff.cap * sizeof(int32_t), c.stream));
+  }
+  TimerBegin(c, "pile");
+  ScatterMarks<<<CeilDiv(n_ovl, 256), 256, 0, c.stream>>>(d_ovl, n_ovl, d_off,
+                                                          n_piles, c.p_diff.get());
+  ApplyCoverage<<<CeilDiv(n_piles, 8), 256, 0, c.stream>>>(d_data, d_off, n_piles,
+                                                           c.p_diff.get());
+  RVN_LAUNCH_CHECK();
+  c.launches += 2;
+  TimerEnd(c);
+  c.stats.pile_bins += h_off[n_piles];
+}
+
+}  // namespace rvn

@@ -1,0 +1,394 @@
+// raven_b200 — minimizer sketching on sm_100a.
+//
+// Replaces ram::MinimizerEngine::Minimize(sequence, minhash) (un-vendored;
+// call sites RavenLib/src/construct.cc:42-43,62,363,377-381; algorithm
+// SURVEY.md App. A.2). The reference walks each read with a rolling k-mer and
+// a monotone deque. Here every k-mer position is independent:
+//   * the 2k-bit k-mer is cut straight out of the 2-bit packed words (staged
+//     in shared memory), the reverse complement is ~lo & mask and the forward
+//     k-mer the 2-bit-group reversal of lo — no rolling state;
+//   * position q is a minimizer iff its hash is <= every valid hash in at
+//     least one of the w-wide windows that contain it, i.e. iff
+//     left_run(q) + right_run(q) >= w - 1 where *_run counts consecutive
+//     neighbours with hash >= hash(q) (capped at w-1 and at the read ends).
+//     This is exactly the deque's "emit every tie of the window minimum
+//     once" rule, and emission order equals position order.
+// One CTA sketches kSketchTile positions of one read (+ w-1 halo each side).
+// Pass 1 counts, a device scan places tiles, pass 2 writes (value, origin)
+// records in (read, position) order — the order the index build relies on.
+#include "engine.cuh"
+
+namespace rvn {
+
+namespace {
+
+constexpr uint64_t kInvalid = ~0ULL;
+
+__device__ __forceinline__ uint64_t MixHash(uint64_t key, uint64_t mask) {
+  key = ((~key) + (key << 21)) & mask;
+  key = key ^ (key >> 24);
+  key = ((key + (key << 3)) + (key << 8)) & mask;
+  key = key ^ (key >> 14);
+  key = ((key + (key << 2)) + (key << 4)) & mask;
+  key = key ^ (key >> 28);
+  key = (key + (key << 31)) & mask;
+  return key;
+}
+
+// reverse the order of the 32 two-bit groups of x
+__device__ __forceinline__ uint64_t ReverseGroups(uint64_t x) {
+  x = __brevll(x);
+  return ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+}
+
+// read index of tile t: last r with tile_off[r] <= t
+__device__ __forceinline__ uint32_t FindRead(const uint64_t* __restrict__ tile_off,
+                                             uint32_t lo, uint32_t hi, uint64_t t) {
+  // invariant: tile_off[lo] <= t < tile_off[hi]
+  while (hi - lo > 1) {
+    uint32_t mid = lo + (hi - lo) / 2;
+    if (tile_off[mid] <= t) {
+      lo = mid;
+    } else {
+      hi = mid;
+    }
+  }
+  return lo;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kSketchThreads)
+SketchKernel(const uint64_t* __restrict__ words,
+             const uint64_t* __restrict__ woff,
+             const uint32_t* __restrict__ lens,
+             const uint64_t* __restrict__ tile_off, uint32_t first_read,
+             uint32_t last_read, uint32_t k, uint32_t w,
+             uint32_t* __restrict__ tile_cnt,
+             const uint64_t* __restrict__ tile_out,
+             uint64_t* __restrict__ out_val, uint64_t* __restrict__ out_org) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: hash values | strand bytes | packed words | scan scratch
+  const uint32_t halo = w - 1;
+  const uint32_t span = kSketchTile + 2 * halo;
+  uint64_t* sh_hash = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* sh_words = sh_hash + span;
+  const uint32_t max_words = (span + 31 + 31) / 32 + 2;
+  uint32_t* sh_scan = reinterpret_cast<uint32_t*>(sh_words + max_words);
+  unsigned char* sh_strand = reinterpret_cast<unsigned char*>(sh_scan + 34);
+  __shared__ uint32_t sh_read;
+
+  const uint64_t tile0 = tile_off[first_read];
+  const uint64_t t = tile0 + blockIdx.x;
+  if (threadIdx.x == 0) {
+    sh_read = FindRead(tile_off, first_read, last_read, t);
+  }
+  __syncthreads();
+  const uint32_t r = sh_read;
+  const uint32_t len = lens[r];
+  const uint32_t L = len - k + 1;  // k-mer positions (tiles exist only if L >= w)
+  const uint32_t q0 = static_cast<uint32_t>(t - tile_off[r]) * kSketchTile;
+  const uint32_t q1 = min(q0 + kSketchTile, L);
+  // hashed range incl. halo
+  const uint32_t hs = q0 >= halo ? q0 - halo : 0;
+  const uint32_t he = min(q1 + halo, L);
+
+  // ---- stage the packed words this tile touches ----
+  const uint64_t* rw = words + woff[r];
+  const uint32_t nwords = static_cast<uint32_t>(woff[r + 1] - woff[r]);
+  const uint32_t w_lo = hs >> 5;
+  const uint32_t w_hi = ((he - 1 + k - 1) >> 5) + 2;  // one spare for the funnel
+  for (uint32_t i = w_lo + threadIdx.x; i < w_hi; i += kSketchThreads) {
+    sh_words[i - w_lo] = i < nwords ? __ldg(rw + i) : 0ULL;
+  }
+  __syncthreads();
+
+  // ---- canonical k-mer hash of every position in [hs, he) ----
+  const uint64_t mask = (1ULL << (2 * k)) - 1;
+  for (uint32_t p = hs + threadIdx.x; p < he; p += kSketchThreads) {
+    const uint32_t wi = (p >> 5) - w_lo;
+    const uint32_t sh = (p & 31) << 1;
+    uint64_t lo = sh_words[wi] >> sh;
+    if (sh) lo |= sh_words[wi + 1] << (64 - sh);
+    lo &= mask;
+    const uint64_t rv = (~lo) & mask;
+    const uint64_t fw = ReverseGroups(lo) >> (64 - 2 * k);
+    uint64_t h = kInvalid;  // palindromic k-mers never enter a window
+    unsigned char strand = 0;
+    if (fw < rv) {
+      h = MixHash(fw, mask);
+    } else if (fw > rv) {
+      h = MixHash(rv, mask);
+      strand = 1;
+    }
+    sh_hash[p - hs] = h;
+    sh_strand[p - hs] = strand;
+  }
+  __syncthreads();
+
+  // ---- select: each thread owns ITEMS consecutive positions ----
+  constexpr uint32_t ITEMS = kSketchTile / kSketchThreads;
+  uint32_t flags = 0;
+  const uint32_t qa = q0 + threadIdx.x * ITEMS;
+#pragma unroll
+  for (uint32_t i = 0; i < ITEMS; ++i) {
+    const uint32_t q = qa + i;
+    if (q >= q1) break;
+    const uint64_t h = sh_hash[q - hs];
+    if (h == kInvalid) continue;
+    // consecutive left neighbours with hash >= h (capped)
+    const uint32_t lcap = min(halo, q);
+    uint32_t ra = 0;
+    while (ra < lcap && sh_hash[q - hs - ra - 1] >= h) ++ra;
+    const uint32_t rcap = min(halo, L - 1 - q);
+    if (ra + rcap < halo) continue;
+    uint32_t rb = 0;
+    const uint32_t need = halo - ra;
+    while (rb < rcap && rb < need && sh_hash[q - hs + rb + 1] >= h) ++rb;
+    if (ra + rb >= halo) flags |= 1u << i;
+  }
+
+  uint32_t total;
+  const uint32_t ex = BlockExclusiveSum<uint32_t, kSketchThreads>(
+      __popc(flags), sh_scan, &total);
+  if (!WRITE) {
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
+    return;
+  }
+  uint64_t dst = tile_out[blockIdx.x] + ex;
+  const uint64_t id = static_cast<uint64_t>(r) << 32;
+  while (flags) {
+    const uint32_t i = __ffs(flags) - 1;
+    flags &= flags - 1;
+    const uint32_t q = qa + i;
+    out_val[dst] = sh_hash[q - hs];
+    out_org[dst] = id | (static_cast<uint64_t>(q) << 1) | sh_strand[q - hs];
+    ++dst;
+  }
+}
+
+__global__ void GatherReadOffsets(const uint64_t* __restrict__ tile_off,
+                                  const uint64_t* __restrict__ tile_out,
+                                  uint32_t first_read, uint32_t n_reads,
+                                  uint64_t* __restrict__ read_off) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n_reads) return;
+  // tile_out has (#tiles + 1) entries, so i == n_reads lands on the total
+  read_off[i] = tile_out[tile_off[first_read + i] - tile_off[first_read]];
+}
+
+// ---- micromizers: the len/k smallest values of a read's sketch, ties by
+// position, back in position order ("minhash") ----
+constexpr int kMicroThreads = 256;
+
+__global__ void __launch_bounds__(kMicroThreads)
+MicromizeKernel(const uint64_t* __restrict__ s_val,
+                const uint64_t* __restrict__ s_org,
+                const uint64_t* __restrict__ s_off,  // per read of the sketch
+                uint32_t s_first, const uint64_t* __restrict__ q_off,
+                uint32_t q_first, uint32_t k,
+                uint64_t* __restrict__ q_val, uint64_t* __restrict__ q_org) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t sh_scan[34];
+  __shared__ uint32_t sh_digit, sh_want;
+
+  const uint32_t r = q_first + blockIdx.x;
+  const uint64_t b = s_off[r - s_first];
+  const uint32_t cnt = static_cast<uint32_t>(s_off[r - s_first + 1] - b);
+  const uint64_t ob = q_off[blockIdx.x];
+  const uint32_t m = static_cast<uint32_t>(q_off[blockIdx.x + 1] - ob);
+  const uint64_t* val = s_val + b;
+  const uint64_t* org = s_org + b;
+  if (m == 0) return;
+  if (m >= cnt) {  // keep everything
+    for (uint32_t i = threadIdx.x; i < cnt; i += kMicroThreads) {
+      q_val[ob + i] = val[i];
+      q_org[ob + i] = org[i];
+    }
+    return;
+  }
+
+  // radix select of the value with ascending rank m-1
+  uint64_t prefix = 0, prefix_mask = 0;
+  uint32_t want = m - 1;
+  for (int shift = static_cast<int>((2 * k + 7) / 8 - 1) * 8; shift >= 0;
+       shift -= 8) {
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < cnt; i += kMicroThreads) {
+      const uint64_t v = val[i];
+      if ((v & prefix_mask) == prefix) {
+        atomicAdd(&hist[(v >> shift) & 255], 1u);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t cum = 0, d = 0;
+      for (; d < 256; ++d) {
+        if (cum + hist[d] > want) break;
+        cum += hist[d];
+      }
+      sh_digit = d;
+      sh_want = want - cum;
+    }
+    __syncthreads();
+    prefix |= static_cast<uint64_t>(sh_digit) << shift;
+    prefix_mask |= 255ULL << shift;
+    want = sh_want;
+    __syncthreads();
+  }
+  const uint64_t T = prefix;
+  const uint32_t need_eq = want + 1;  // first need_eq records equal to T
+
+  // ordered compaction, one chunk of kMicroThreads records at a time
+  uint32_t kept = 0, eq_seen = 0;
+  for (uint32_t base = 0; base < cnt; base += kMicroThreads) {
+    const uint32_t i = base + threadIdx.x;
+    uint64_t v = 0, o = 0;
+    uint32_t is_eq = 0, is_lt = 0;
+    if (i < cnt) {
+      v = val[i];
+      o = org[i];
+      is_eq = v == T;
+      is_lt = v < T;
+    }
+    uint32_t tot;
+    const uint32_t packed = BlockExclusiveSum<uint32_t, kMicroThreads>(
+        is_eq << 16 | is_lt, sh_scan, &tot);
+    const uint32_t eq_before = eq_seen + (packed >> 16);
+    const uint32_t lt_before = packed & 0xFFFF;
+    const uint32_t eq_kept_before =
+        min(eq_before, need_eq) - min(eq_seen, need_eq);
+    const bool keep = is_lt || (is_eq && eq_before < need_eq);
+    if (keep) {
+      const uint64_t d = ob + kept + lt_before + eq_kept_before;
+      q_val[d] = v;
+      q_org[d] = o;
+    }
+    const uint32_t eq_tot = tot >> 16, lt_tot = tot & 0xFFFF;
+    kept += lt_tot + (min(eq_seen + eq_tot, need_eq) - min(eq_seen, need_eq));
+    eq_seen += eq_tot;
+  }
+}
+
+size_t SketchSmemBytes(uint32_t w) {
+  const uint32_t halo = w - 1;
+  const uint32_t span = kSketchTile + 2 * halo;
+  const uint32_t max_words = (span + 31 + 31) / 32 + 2;
+  return span * 8 + max_words * 8 + 34 * 4 + span + 16;
+}
+
+}  // namespace
+
+void EnsureTiles(Ctx& c) {
+  if (c.tiles_k == c.prm.k && c.h_tile_off.size() == c.n_reads + 1ULL) return;
+  c.h_tile_off.assign(c.n_reads + 1ULL, 0);
+  for (uint32_t r = 0; r < c.n_reads; ++r) {
+    const uint32_t len = c.h_len[r];
+    uint64_t tiles = 0;
+    if (len >= c.prm.k) {
+      const uint32_t L = len - c.prm.k + 1;
+      if (L >= c.prm.w) tiles = (L + kSketchTile - 1) / kSketchTile;
+    }
+    c.h_tile_off[r + 1] = c.h_tile_off[r] + tiles;
+  }
+  uint64_t* d = c.d_tile_off.reserve(c.n_reads + 1ULL);
+  RVN_CUDA(cudaMemcpyAsync(d, c.h_tile_off.data(),
+                           (c.n_reads + 1ULL) * sizeof(uint64_t),
+                           cudaMemcpyHostToDevice, c.stream));
+  RVN_CUDA(cudaStreamSynchronize(c.stream));
+  c.tiles_k = c.prm.k;
+  c.s_valid = c.q_valid = false;
+}
+
+void EnsureSketch(Ctx& c, uint32_t first, uint32_t last) {
+  if (c.s_valid && c.s_first == first && c.s_last == last) return;
+  EnsureTiles(c);
+  c.s_valid = false;
+  c.q_valid = false;
+  const uint32_t nr = last - first;
+  const uint64_t n_tiles = c.h_tile_off[last] - c.h_tile_off[first];
+  if (n_tiles >= (1ULL << 31)) throw LimitError("too many sketch tiles");
+
+  uint64_t* read_off = c.s_off.reserve(nr + 1ULL);
+  c.h_s_off.assign(nr + 1ULL, 0);
+  uint64_t total = 0;
+  if (n_tiles > 0) {
+    TimerBegin(c, "sketch");
+    const size_t smem = SketchSmemBytes(c.prm.w);
+    uint32_t* tcnt = c.tile_cnt.reserve(n_tiles);
+    uint64_t* tout = c.tile_out.reserve(n_tiles + 1);
+    SketchKernel<false><<<static_cast<unsigned>(n_tiles), kSketchThreads, smem,
+                          c.stream>>>(c.d_words.get(), c.d_woff.get(),
+                                      c.d_len.get(), c.d_tile_off.get(), first,
+                                      last, c.prm.k, c.prm.w, tcnt, nullptr,
+                                      nullptr, nullptr);
+    RVN_LAUNCH_CHECK();
+    ++c.launches;
+    ExclusiveScanU32(c, tcnt, tout, n_tiles);
+    total = ReadU64(c, tout + n_tiles);
+    uint64_t* val = c.s_val.reserve(total);
+    uint64_t* org = c.s_org.reserve(total);
+    SketchKernel<true><<<static_cast<unsigned>(n_tiles), kSketchThreads, smem,
+                         c.stream>>>(c.d_words.get(), c.d_woff.get(),
+                                     c.d_len.get(), c.d_tile_off.get(), first,
+                                     last, c.prm.k, c.prm.w, nullptr, tout, val,
+                                     org);
+    RVN_LAUNCH_CHECK();
+    ++c.launches;
+    GatherReadOffsets<<<CeilDiv(nr + 1ULL, 256), 256, 0, c.stream>>>(
+        c.d_tile_off.get(), tout, first, nr, read_off);
+    RVN_LAUNCH_CHECK();
+    ++c.launches;
+    TimerEnd(c);
+    RVN_CUDA(cudaMemcpyAsync(c.h_s_off.data(), read_off,
+                             (nr + 1ULL) * sizeof(uint64_t),
+                             cudaMemcpyDeviceToHost, c.stream));
+    RVN_CUDA(cudaStreamSynchronize(c.stream));
+  } else {
+    RVN_CUDA(cudaMemsetAsync(read_off, 0, (nr + 1ULL) * sizeof(uint64_t),
+                             c.stream));
+  }
+  c.s_first = first;
+  c.s_last = last;
+  c.s_n = total;
+  c.s_valid = true;
+}
+
+void EnsureMicromizers(Ctx& c, uint32_t first, uint32_t last) {
+  if (c.q_valid && c.q_first == first && c.q_last == last) return;
+  if (!c.s_valid || first < c.s_first || last > c.s_last) {
+    EnsureSketch(c, first, last);
+  }
+  c.q_valid = false;
+  const uint32_t nr = last - first;
+  c.h_q_off.assign(nr + 1ULL, 0);
+  for (uint32_t i = 0; i < nr; ++i) {
+    const uint32_t r = first + i;
+    const uint64_t cnt = c.h_s_off[r - c.s_first + 1] - c.h_s_off[r - c.s_first];
+    const uint64_t m = c.h_len[r] / c.prm.k;
+    c.h_q_off[i + 1] = c.h_q_off[i] + (m < cnt ? m : cnt);
+  }
+  const uint64_t total = c.h_q_off[nr];
+  uint64_t* qoff = c.q_off.reserve(nr + 1ULL);
+  RVN_CUDA(cudaMemcpyAsync(qoff, c.h_q_off.data(),
+                           (nr + 1ULL) * sizeof(uint64_t),
+                           cudaMemcpyHostToDevice, c.stream));
+  uint64_t* qv = c.q_val.reserve(total);
+  uint64_t* qo = c.q_org.reserve(total);
+  if (nr > 0 && total > 0) {
+    TimerBegin(c, "micromize");
+    MicromizeKernel<<<nr, kMicroThreads, 0, c.stream>>>(
+        c.s_val.get(), c.s_org.get(), c.s_off.get(), c.s_first, qoff, first,
+        c.prm.k, qv, qo);
+    RVN_LAUNCH_CHECK();
+    ++c.launches;
+    TimerEnd(c);
+  }
+  RVN_CUDA(cudaStreamSynchronize(c.stream));  // h_q_off staging is reusable
+  c.q_first = first;
+  c.q_last = last;
+  c.q_n = total;
+  c.q_valid = true;
+}
+
+}  // namespace rvn

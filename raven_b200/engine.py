@@ -1,0 +1,174 @@
+"""Host-side mirror of the reference's overlap interface over the C ABI.
+
+``Engine`` keeps the names and argument meaning of the reference calls it
+stands in for:
+
+* ``minimize / filter / map``  ->  ``ram::MinimizerEngine::{Minimize,Filter,Map}``
+  (call sites RavenLib/src/construct.cc:42-44,59-64,363,372,377-381)
+* ``find_overlaps_and_create_piles``  ->  ``raven::FindOverlapsAndCreatePiles``
+  (RavenLib/src/construct.cc:14-121; Python binding of the reference:
+  PythonLib/src/ravenpy.cc:214-218)
+
+Errors: the reference throws ``std::invalid_argument`` for a frequency outside
+[0, 1]; here that is ``ValueError``.  Everything else the C ABI reports is a
+``RuntimeError``.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import OVLP, U16P, U32P, U64P, Overlap, Stats
+
+_ERR = {-1: ValueError, -2: RuntimeError, -3: RuntimeError, -4: OverflowError}
+
+
+def _arr(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    addr = C.cast(ptr, C.c_void_p).value
+    buf = (C.c_uint8 * (n * np.dtype(dtype).itemsize)).from_address(addr)
+    return np.frombuffer(buf, dtype=dtype).copy()
+
+
+class Engine:
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.rvn_ctx_create(device, C.c_void_p(stream) if stream else None,
+                                     C.byref(h))
+        if rc != 0:
+            raise RuntimeError(
+                f"rvn_ctx_create failed ({rc}): no usable sm_100 CUDA device "
+                "(raven_b200 has no CPU fallback)")
+        self.h = h
+        self.n_reads = 0
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rvn_ctx_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.rvn_last_error(self.h).decode()
+            raise _ERR.get(rc, RuntimeError)(msg)
+
+    # ---- ram::MinimizerEngine ----
+    def configure(self, k=15, w=5, bandwidth=500, chain=4, matches=100, gap=10000):
+        self._check(self.lib.rvn_engine_configure(self.h, k, w, bandwidth, chain,
+                                                  matches, gap))
+
+    def upload(self, rs):
+        words = np.ascontiguousarray(rs.words, dtype=np.uint64)
+        woff = np.ascontiguousarray(rs.word_off, dtype=np.uint64)
+        lens = np.ascontiguousarray(rs.lens, dtype=np.uint32)
+        self._keep = (words, woff, lens)
+        self._check(self.lib.rvn_reads_upload(
+            self.h, words.ctypes.data_as(U64P), woff.ctypes.data_as(U64P),
+            lens.ctypes.data_as(U32P), rs.n))
+        self.n_reads = rs.n
+
+    def minimize(self, first, last, minhash=False):
+        self._check(self.lib.rvn_minimize(self.h, first, last, int(minhash)))
+
+    def filter(self, frequency):
+        occ = C.c_uint32(0)
+        self._check(self.lib.rvn_filter(self.h, float(frequency), C.byref(occ)))
+        return occ.value
+
+    def map(self, first, last, avoid_equal=True, avoid_symmetric=True,
+            minhash=False, want_filtered=False):
+        self._check(self.lib.rvn_map(self.h, first, last, int(avoid_equal),
+                                     int(avoid_symmetric), int(minhash),
+                                     int(want_filtered)))
+        o, off, n = OVLP(), U64P(), C.c_uint64(0)
+        f, foff = U32P(), U64P()
+        self._check(self.lib.rvn_map_results(self.h, C.byref(o), C.byref(off),
+                                             C.byref(n), C.byref(f), C.byref(foff)))
+        nr = last - first
+        res = dict(overlaps=_arr(o, n.value * 8, np.uint32).reshape(-1, 8),
+                   ovl_off=_arr(off, nr + 1, np.uint64))
+        fo = _arr(foff, nr + 1, np.uint64)
+        res["filt_off"] = fo
+        res["filtered"] = _arr(f, int(fo[-1]) if want_filtered else 0, np.uint32)
+        return res
+
+    def map_hits(self, nr):
+        g, p, off, n = U64P(), U64P(), U64P(), C.c_uint64(0)
+        self._check(self.lib.rvn_map_hits(self.h, C.byref(g), C.byref(p),
+                                          C.byref(off), C.byref(n)))
+        return dict(group=_arr(g, n.value, np.uint64),
+                    positions=_arr(p, n.value, np.uint64),
+                    hit_off=_arr(off, nr + 1, np.uint64))
+
+    def sketch(self, first, last, minhash=False):
+        v, o, off, n = U64P(), U64P(), U64P(), C.c_uint64(0)
+        self._check(self.lib.rvn_sketch(self.h, first, last, int(minhash),
+                                        C.byref(v), C.byref(o), C.byref(off),
+                                        C.byref(n)))
+        return dict(value=_arr(v, n.value, np.uint64),
+                    origin=_arr(o, n.value, np.uint64),
+                    offsets=_arr(off, last - first + 1, np.uint64))
+
+    def index_records(self):
+        v, o, n, nk = U64P(), U64P(), C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.rvn_index_records(self.h, C.byref(v), C.byref(o),
+                                               C.byref(n), C.byref(nk)))
+        return dict(value=_arr(v, n.value, np.uint64),
+                    origin=_arr(o, n.value, np.uint64), n_keys=nk.value)
+
+    # ---- raven::Pile::AddLayers ----
+    def pile_add_layers(self, data, bin_off, overlaps):
+        d = np.ascontiguousarray(data, dtype=np.uint16).copy()
+        off = np.ascontiguousarray(bin_off, dtype=np.uint64)
+        o = np.ascontiguousarray(overlaps, dtype=np.uint32).reshape(-1, 8)
+        self._check(self.lib.rvn_pile_add_layers(
+            self.h, d.ctypes.data_as(U16P), off.ctypes.data_as(U64P), off.size - 1,
+            C.cast(o.ctypes.data, OVLP), o.shape[0]))
+        return d
+
+    # ---- raven::FindOverlapsAndCreatePiles ----
+    def find_overlaps_and_create_piles(self, freq=0.001, max_overlaps=32,
+                                       use_minhash=False, index_batch_bases=0,
+                                       query_batch_bases=0, fetch=True):
+        self._check(self.lib.rvn_find_overlaps_and_create_piles(
+            self.h, float(freq), max_overlaps, int(use_minhash), index_batch_bases,
+            query_batch_bases))
+        if not fetch:
+            return None
+        o, off, p, poff, nm = OVLP(), U64P(), U16P(), U64P(), C.c_uint64(0)
+        self._check(self.lib.rvn_stage1_results(self.h, C.byref(o), C.byref(off),
+                                                C.byref(p), C.byref(poff),
+                                                C.byref(nm)))
+        n = self.n_reads
+        ovl_off = _arr(off, n + 1, np.uint64)
+        pile_off = _arr(poff, n + 1, np.uint64)
+        return dict(overlaps=_arr(o, int(ovl_off[-1]) * 8, np.uint32).reshape(-1, 8),
+                    ovl_off=ovl_off, pile=_arr(p, int(pile_off[-1]), np.uint16),
+                    pile_off=pile_off, num_mapped=nm.value)
+
+    # ---- bookkeeping ----
+    def set_option(self, name, value):
+        self._check(self.lib.rvn_set_option(self.h, name.encode(), int(value)))
+
+    def stats(self):
+        s = Stats()
+        self._check(self.lib.rvn_get_stats(self.h, C.byref(s)))
+        return {n: getattr(s, n) for n, _ in Stats._fields_ if n != "reserved"}
+
+    def timings(self):
+        names = C.POINTER(C.c_char_p)()
+        ms = C.POINTER(C.c_float)()
+        n = C.c_uint32(0)
+        self._check(self.lib.rvn_get_timings(self.h, C.byref(names), C.byref(ms),
+                                             C.byref(n)))
+        out = {}
+        for i in range(n.value):
+            out[names[i].decode()] = out.get(names[i].decode(), 0.0) + ms[i]
+        return out

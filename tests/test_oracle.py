@@ -1,0 +1,197 @@
+"""CPU tests: the oracle against the committed golden vectors, against the
+reference's own compiled sources (oracle/_ref, when built), and against
+independent numpy restatements of the small pieces."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from raven_b200 import seqio, synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+META = json.load(open(os.path.join(HERE, "golden", "lambda_golden.json")))
+GOLD = np.load(os.path.join(HERE, "golden", "lambda_golden.npz"))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_fixture_is_the_reference_fixture(lambda_reads):
+    # RavenTest/data/ERA476754.fastq.gz: 236 reads, 1,674,628 bases
+    assert lambda_reads.n == 236
+    assert lambda_reads.bases == 1674628
+    assert int(lambda_reads.lens.min()) == 443 and int(lambda_reads.lens.max()) == 11968
+
+
+@pytest.mark.parametrize("minhash", [False, True])
+def test_sketch_golden(oracle, lambda_reads, minhash):
+    eng = oracle.engine(15, 5)
+    sk = oracle.sketch(eng, oracle.reads(lambda_reads), 0, lambda_reads.n, minhash)
+    tag = "micro" if minhash else "full"
+    assert sk["value"].size == META[f"sketch_{tag}_n"]
+    assert sha(sk["value"]) == META[f"sketch_{tag}_value_sha256"]
+    assert sha(sk["origin"]) == META[f"sketch_{tag}_origin_sha256"]
+    assert sha(sk["offsets"]) == META[f"sketch_{tag}_offsets_sha256"]
+
+
+def test_survey_anchors(oracle, lambda_reads):
+    """Counts measured independently by the survey."""
+    eng = oracle.engine(15, 5, threads=4)
+    reads = oracle.reads(lambda_reads)
+    oracle.minimize(eng, reads, 0, lambda_reads.n, False)
+    keys = oracle.keys(eng)
+    assert keys["totals"].tolist() == [467532, 568395]
+    assert int((keys["counts"] == 1).sum()) == 436140
+    assert int(keys["counts"].max()) == 25
+    assert oracle.filter(eng, 0.001) == 15
+    m = oracle.map(eng, reads, 0, lambda_reads.n, True, True, True, True)
+    assert m["match_group"].size == 68597 and m["overlaps"].shape[0] == 2407
+    assert sha(m["overlaps"]) == META["map_micro_overlaps_sha256"]
+    m = oracle.map(eng, reads, 0, lambda_reads.n, True, True, False, True)
+    assert m["match_group"].size == 326834 and m["overlaps"].shape[0] == 3890
+    assert sha(m["overlaps"]) == META["map_full_overlaps_sha256"]
+    assert sha(m["filtered"]) == META["map_full_filtered_sha256"]
+
+
+def test_filter_rejects_bad_frequency(oracle, lambda_reads):
+    eng = oracle.engine(15, 5)
+    oracle.minimize(eng, oracle.reads(lambda_reads), 0, 10, False)
+    for f in (-0.1, 1.5, float("nan")):
+        with pytest.raises(ValueError):
+            oracle.filter(eng, f)
+    assert oracle.filter(eng, 0) == 0xFFFFFFFF
+
+
+@pytest.mark.parametrize("minhash", [False, True])
+def test_stage1_golden(oracle, lambda_reads, minhash):
+    tag = "minhash" if minhash else "plain"
+    st = oracle.stage1(oracle.engine(15, 5, threads=4), oracle.reads(lambda_reads),
+                       0.001, 32, minhash)
+    for k in ("overlaps", "ovl_off", "pile", "pile_off"):
+        assert np.array_equal(st[k], GOLD[f"stage1_{tag}_{k}"]), k
+    assert int(st["num_mapped"][0]) == META[f"stage1_{tag}_num_mapped"]
+
+
+@pytest.mark.parametrize("minhash", [False, True])
+def test_stage1_port_equals_compiled_reference(oracle, reference, lambda_reads, minhash):
+    """construct.cc / pile.cc / overlap_utils.cc compiled in place vs the port."""
+    a = oracle.stage1(oracle.engine(15, 5, threads=4), oracle.reads(lambda_reads),
+                      0.001, 32, minhash)
+    b = reference.stage1(reference.reads(lambda_reads), 15, 5, 0.001, 32, minhash, 4)
+    for k in ("overlaps", "ovl_off", "pile", "pile_off", "occurrences"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_stage1_port_equals_compiled_reference_synthetic(oracle, reference):
+    rs = synth.make_reads(40_000, 150, 3000, seed=11)
+    for kmax in (4, 32):
+        a = oracle.stage1(oracle.engine(15, 5, threads=4), oracle.reads(rs), 0.001,
+                          kmax, False)
+        b = reference.stage1(reference.reads(rs), 15, 5, 0.001, kmax, False, 4)
+        for k in ("overlaps", "ovl_off", "pile", "pile_off"):
+            assert np.array_equal(a[k], b[k]), (kmax, k)
+
+
+def test_add_layers_equals_reference_pile(oracle, reference):
+    rng = np.random.default_rng(3)
+    length = 5000
+    ovl = []
+    for _ in range(300):
+        b = int(rng.integers(0, length - 200))
+        e = int(rng.integers(b + 100, min(length, b + 3000) + 1))
+        side = rng.random() < 0.5
+        rec = [7, b, e, 9, 16, 200, 100, 1] if side else [9, 16, 200, 7, b, e, 100, 0]
+        ovl.append(rec)
+    ovl = np.array(ovl, dtype=np.uint32)
+    want = reference.pile_add_layers(7, length, ovl, rounds=2)
+    got = np.zeros(length >> 4, np.uint16)
+    got = oracle.pile_add_layers(7, got, ovl)
+    got = oracle.pile_add_layers(7, got, ovl)
+    assert np.array_equal(got, want)
+    # saturation at 65535
+    want = reference.pile_add_layers(7, length, ovl, rounds=700)
+    got = np.zeros(length >> 4, np.uint16)
+    for _ in range(700):
+        got = oracle.pile_add_layers(7, got, ovl)
+    assert np.array_equal(got, want) and got.max() == 65535
+
+
+def test_multi_batch_schedule_is_exercised(oracle):
+    """Small thresholds drive >1 index batch and >1 flush; the result must
+    differ from the single-batch run only through the documented schedule."""
+    rs = synth.make_reads(30_000, 100, 3000, seed=5)
+    eng = oracle.engine(15, 5, threads=4)
+    one = oracle.stage1(eng, oracle.reads(rs), 0.001, 8, False)
+    many = oracle.stage1(oracle.engine(15, 5, threads=4), oracle.reads(rs), 0.001, 8,
+                         False, index_batch_bases=100_000, query_batch_bases=40_000)
+    assert len(many["occurrences"]) > 1
+    assert np.array_equal(one["pile_off"], many["pile_off"])
+    assert (np.diff(many["ovl_off"].astype(np.int64)) <= 8).all()
+
+
+def _numpy_minimizers(codes, k, w):
+    """Independent restatement: hash every k-mer, then the window rule."""
+    n = len(codes)
+    if n < k:
+        return []
+    mask = (1 << (2 * k)) - 1
+
+    def h(key):
+        key = (~key + (key << 21)) & mask
+        key ^= key >> 24
+        key = (key + (key << 3) + (key << 8)) & mask
+        key ^= key >> 14
+        key = (key + (key << 2) + (key << 4)) & mask
+        key ^= key >> 28
+        key = (key + (key << 31)) & mask
+        return key
+
+    vals, strands = [], []
+    for p in range(n - k + 1):
+        fw = rv = 0
+        for i in range(k):
+            fw = (fw << 2) | int(codes[p + i])
+            rv |= (3 - int(codes[p + i])) << (2 * i)
+        if fw < rv:
+            vals.append(h(fw)); strands.append(0)
+        elif fw > rv:
+            vals.append(h(rv)); strands.append(1)
+        else:
+            vals.append(None); strands.append(0)
+    L = len(vals)
+    out = set()
+    for s in range(0, L - w + 1):
+        win = [(vals[q], q) for q in range(s, s + w) if vals[q] is not None]
+        if not win:
+            continue
+        m = min(v for v, _ in win)
+        out.update(q for v, q in win if v == m)
+    return [(vals[q], (q << 1) | strands[q]) for q in sorted(out)]
+
+
+def test_sketch_matches_naive_definition(oracle):
+    rng = np.random.default_rng(9)
+    seqs = [rng.integers(0, 4, n, dtype=np.uint8) for n in (14, 15, 18, 19, 20, 64, 300)]
+    seqs.append(np.zeros(100, np.uint8))                      # homopolymer
+    seqs.append(np.tile(np.array([0, 3], np.uint8), 60))      # ATAT.. (palindromes)
+    seqs.append(np.tile(np.array([0, 1, 2, 3], np.uint8), 40))
+    rs = seqio.pack_codes(seqs)
+    for k, w in ((15, 5), (5, 3), (4, 1), (19, 10)):
+        eng = oracle.engine(k, w)
+        sk = oracle.sketch(eng, oracle.reads(rs), 0, rs.n, False)
+        for i, s in enumerate(seqs):
+            a, b = int(sk["offsets"][i]), int(sk["offsets"][i + 1])
+            want = _numpy_minimizers(s, k, w)
+            got = list(zip(sk["value"][a:b].tolist(),
+                           (sk["origin"][a:b] & 0xFFFFFFFF).tolist()))
+            assert got == want, (k, w, i)
+            assert ((sk["origin"][a:b] >> 32) == i).all()
+
+
+def test_edit_distance_oracle(oracle):
+    assert oracle.edit_distance(b"kitten", b"sitting") == 3
+    assert oracle.edit_distance(b"", b"ACGT") == 4
+    assert oracle.edit_distance(b"ACGT", b"ACGT") == 0
