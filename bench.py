@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — overlaps/s of the stage-1 all-vs-all overlap path on B200.
+
+One "step" = one pass of raven::FindOverlapsAndCreatePiles (sketch, index,
+filter, map/chain, pile coverage, truncation) over one synthetic read set.
+Workload at N=1 = BASELINE.json configs[1]: 200k synthetic ONT reads ~10 kb
+(~2 Gbp), k=15 w=5 f=0.001, overlap-only (-p 0).
+
+  value   overlaps/s with the packed reads already resident in HBM
+  e2e     the same through the C-ABI with HOST buffers: H2D of the packed
+          reads and D2H of overlaps + piles inside the timed region
+  --impl reference   the reference's own CPU code for the path (oracle/_ref:
+          construct.cc/pile.cc/overlap_utils.cc compiled in place, over the
+          restated ram engine) on a bounded sample, all host threads.
+
+N>1 (torchrun): every rank runs the same-size workload on its own, seeded
+shard ("weak", no data-path collective); value = sum of overlaps / max time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SEED = 20260924
+K, W, FREQ, KMAX = 15, 5, 0.001, 32
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=200_000)
+    ap.add_argument("--genome", type=int, default=50_000_000)
+    ap.add_argument("--mean-len", type=int, default=10_000)
+    ap.add_argument("--cpu-sample-reads", type=int, default=20_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"C2: {a.reads} synthetic ONT reads ~{a.mean_len // 1000} kb over a "
+            f"{a.genome / 1e6:.0f} Mbp genome (40x, 10% error), k={K} w={W} f={FREQ} "
+            f"kMaxNumOverlaps={KMAX}, stage-1 all-vs-all "
+            "(FindOverlapsAndCreatePiles), -p 0")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.p = None
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        self.t.join(timeout=2)
+        sm = sorted(int(r[1]) for r in self.rows if len(r) > 8 and r[1].isdigit())
+        mx = max([int(r[2]) for r in self.rows if len(r) > 8 and r[2].isdigit()] or [0])
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(a):
+    """Bounded sample of the same workload for the CPU legs: same read model and
+    coverage (40x) over a proportionally smaller genome."""
+    from bench import synth
+    n = min(a.cpu_sample_reads, a.reads)
+    g = max(int(a.genome * n / max(a.reads, 1)), 4 * a.mean_len)
+    return synth.make_reads(SEED + 1, g, n, a.mean_len), n, g
+
+
+def run_cpu(a, kind_pref="reference", threads=None):
+    """One stage-1 pass of the CPU path on the bounded sample."""
+    import oracle_lib
+    threads = threads or os.cpu_count() or 1
+    rs, n, g = cpu_sample(a)
+    sample = (f"{n} reads / {g / 1e6:.1f} Mbp genome of the same 40x model "
+              f"({rs.bases / 1e9:.3f} Gbp), one stage-1 pass")
+    if kind_pref == "reference" and oracle_lib.Reference.available():
+        R = oracle_lib.Reference()
+        reads = R.reads(rs)
+
+        def step():
+            t = time.perf_counter()
+            # stderr phase lines of the reference are silenced for the bench
+            fd = os.dup(2)
+            devnull = os.open(os.devnull, os.O_WRONLY)
+            os.dup2(devnull, 2)
+            try:
+                res = R.stage1(reads, K, W, FREQ, KMAX, False, threads)
+            finally:
+                os.dup2(fd, 2)
+                os.close(fd)
+                os.close(devnull)
+            dt = time.perf_counter() - t
+            # overlaps returned by all Map calls = half the incidences before
+            # truncation; the reference library does not expose it, so count
+            # via the port's counter on the first call only
+            return dt, res
+        kind = "reference"
+    else:
+        O = oracle_lib.Oracle()
+        reads = O.reads(rs)
+
+        def step():
+            t = time.perf_counter()
+            res = O.stage1(O.engine(K, W, threads=threads), reads, FREQ, KMAX, False)
+            return time.perf_counter() - t, res
+        kind = "port"
+    # number of mapped overlaps of the sample (identical for port and reference)
+    O = oracle_lib.Oracle()
+    n_mapped = int(O.stage1(O.engine(K, W, threads=threads), O.reads(rs), FREQ, KMAX,
+                            False)["num_mapped"][0])
+    return step, n_mapped, kind, threads, sample
+
+
+def main_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, n_mapped, kind, threads, sample = run_cpu(a, "reference")
+    for _ in range(min(a.warmup, 1)):
+        step()
+    ts = [step()[0] for _ in range(a.steps)]
+    dt = sum(ts)
+    v = n_mapped * a.steps / dt
+    out = {
+        "impl": "reference", "metric": "overlaps/s", "value": v, "unit": "overlaps/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1),
+        "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "measured_on": sample,
+                   "reference": "RavenLib construct.cc/pile.cc/overlap_utils.cc compiled "
+                                "in place over the restated ram engine (ram is not "
+                                "vendored upstream)" if kind == "reference" else
+                                "oracle port (oracle/_ref absent)"},
+        "cpu_baseline": {"value": v, "unit": "overlaps/s", "cores": threads, "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": v, "unit": "overlaps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from bench import synth
+    from raven_b200 import engine
+
+    rs = synth.make_reads(SEED + 1000 * rank, a.genome, a.reads, a.mean_len)
+    # pinned host copies: the e2e leg uploads from these every step
+    words = torch.from_numpy(rs.words.view(np.int64)).pin_memory()
+    woff = torch.from_numpy(rs.word_off.view(np.int64)).pin_memory()
+    lens = torch.from_numpy(rs.lens.view(np.int32)).pin_memory()
+
+    class Pinned:
+        pass
+
+    prs = Pinned()
+    prs.words = words.numpy().view(np.uint64)
+    prs.word_off = woff.numpy().view(np.uint64)
+    prs.lens = lens.numpy().view(np.uint32)
+    prs.n = rs.n
+
+    stream = torch.cuda.current_stream()
+    eng = engine.Engine(device=local, stream=stream.cuda_stream)
+    eng.configure(K, W)
+    eng.upload(prs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        eng.find_overlaps_and_create_piles(FREQ, KMAX, False, fetch=False)
+
+    def step_e2e():
+        eng.upload(prs)
+        eng.find_overlaps_and_create_piles(FREQ, KMAX, False, fetch=False)
+        # results are host-resident after the call (D2H inside the step)
+
+    def timed(fn, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(steps):
+            fn()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        barrier()
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(a.warmup):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    eng.set_option("reset_stats", 1)
+    ms_total = timed(step_resident, a.steps)
+    st = eng.stats()          # counters of the LAST step
+    phases = eng.timings()    # device ms per phase of the LAST step
+    launches_step = st["kernel_launches"]
+    n_mapped = st["overlaps"]
+    clocks = sampler.stop() if sampler else None
+
+    for _ in range(1):
+        step_e2e()
+    ms_e2e = timed(step_e2e, a.steps)
+
+    tot = torch.tensor([float(n_mapped)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    total_mapped = float(tot.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        # ---- roofline of the dominant kernel (by device time of the last step) ----
+        own = {k: v for k, v in phases.items()}
+        dom = max(own, key=own.get)
+        alg = algorithmic_bytes(st)
+        dom_bytes = alg.get(dom, 0.0)
+        dom_ms = own[dom]
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(prof):
+            traffic = json.load(open(prof)).get(dom)
+        h2d = int(prs.words.nbytes + prs.word_off.nbytes + prs.lens.nbytes)
+        res = eng.find_overlaps_and_create_piles(FREQ, KMAX, False, fetch=True)
+        d2h = int(res["overlaps"].nbytes + res["ovl_off"].nbytes + res["pile"].nbytes
+                  + n_mapped * 32)
+        out = {
+            "metric": "overlaps/s", "value": total_mapped * a.steps / (ms_total * 1e-3),
+            "unit": "overlaps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "reads_per_gpu": rs.n,
+                       "bases_per_gpu": int(rs.bases), "overlaps_per_step_per_gpu": n_mapped,
+                       "l2": "inputs (0.5 GB packed reads, 10.7 GB minimizer records) "
+                             "exceed the 126 MB L2; no explicit flush",
+                       "parallelism": f"{world} independent shard(s), no collective"},
+            "clocks": clocks,
+            "e2e": {"value": total_mapped * a.steps / (ms_e2e * 1e-3), "unit": "overlaps/s",
+                    "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches_step) * a.steps,
+            "phases_ms": {k: round(v, 3) for k, v in sorted(phases.items())},
+            "query_mbases_per_s": st["query_bases"] / 1e6 / (ms_total / a.steps * 1e-3),
+            "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"
+                         if peaks else "fallback 6650 GB/s (of fallback)",
+                         "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
+                         "traffic": traffic},
+            "path_roofline": {"algorithmic_bytes": sum(alg.values()),
+                              "achieved": sum(alg.values()) / (ms_total / a.steps * 1e-3) / 1e9,
+                              "frac": sum(alg.values()) / (ms_total / a.steps * 1e-3) / 1e9 / peak},
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            step, n_map_cpu, kind, threads, sample = run_cpu(a, "reference")
+            dt, _ = step()
+            out["cpu_baseline"] = {"value": n_map_cpu / dt, "unit": "overlaps/s",
+                                   "cores": threads, "kind": kind, "sample": sample,
+                                   "seconds": dt}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def algorithmic_bytes(st):
+    """SURVEY.md §8(d) / DESIGN.md: bytes each phase must move at minimum."""
+    nb, nm, nk = st["index_bases"], st["index_records"], st["index_keys"]
+    qb, qm, nh, no = st["query_bases"], st["query_records"], st["hits"], st["overlaps"]
+    return {
+        "sketch": 0.25 * nb + 16.0 * nm,
+        "micromize": 16.0 * nm + 16.0 * qm,
+        "index_sort": 2 * 16.0 * nm,
+        "index_table": 8.0 * nm + 4.0 * nk,
+        "filter": 4.0 * nk,
+        "probe": 16.0 * qm + 16.0 * qm,
+        "expand": 8.0 * nh + 16.0 * nh,
+        "chain": 16.0 * nh + 32.0 * no,
+        "pile": 2 * 2.0 * st["pile_bins"],
+    }
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_ours(args)

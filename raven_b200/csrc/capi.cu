@@ -87,6 +87,9 @@ void Stage1(Ctx& c, double freq, uint64_t kmax, bool minhash, uint64_t ib,
         "[ram::MinimizerEngine::Filter] error: invalid frequency");
   }
   c.st_valid = false;
+  // a stage-1 pass owns its intermediates: nothing is carried over from an
+  // earlier call (sketches, micromizers and the index are rebuilt)
+  c.s_valid = c.q_valid = c.i_valid = c.r_valid = false;
   TimerReset(c);
   std::memset(&c.stats, 0, sizeof(c.stats));
   const uint64_t launches0 = c.launches;

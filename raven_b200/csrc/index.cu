@@ -56,16 +56,32 @@ __global__ void ScatterRunStarts(const uint32_t* __restrict__ flag,
 
 constexpr uint32_t kHistBins = 1u << 16;
 
-// histogram of run lengths; lengths >= kHistBins-1 land in the last bin
-__global__ void RunLengthHistogram(const uint32_t* __restrict__ run_start,
-                                   uint64_t n_keys, uint64_t n,
-                                   unsigned long long* __restrict__ hist) {
-  const uint64_t j = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (j >= n_keys) return;
-  const uint64_t end = j + 1 < n_keys ? run_start[j + 1] : n;
-  uint64_t len = end - run_start[j];
-  if (len > kHistBins - 1) len = kHistBins - 1;
-  atomicAdd(&hist[len], 1ULL);
+// histogram of run lengths; lengths >= kHistBins-1 land in the last bin.
+// Nearly every run has length 1..3, so short lengths are counted in a
+// shared-memory histogram per CTA (one global atomic per bin per CTA).
+constexpr uint32_t kSmemBins = 1024;
+__global__ void __launch_bounds__(kThreads)
+RunLengthHistogram(const uint32_t* __restrict__ run_start, uint64_t n_keys,
+                   uint64_t n, unsigned long long* __restrict__ hist) {
+  __shared__ uint32_t sh[kSmemBins];
+  for (uint32_t i = threadIdx.x; i < kSmemBins; i += kThreads) sh[i] = 0;
+  __syncthreads();
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kThreads;
+  for (uint64_t j = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+       j < n_keys; j += stride) {
+    const uint64_t end = j + 1 < n_keys ? run_start[j + 1] : n;
+    uint64_t len = end - run_start[j];
+    if (len > kHistBins - 1) len = kHistBins - 1;
+    if (len < kSmemBins) {
+      atomicAdd(&sh[len], 1u);
+    } else {
+      atomicAdd(&hist[len], 1ULL);
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < kSmemBins; i += kThreads) {
+    if (sh[i]) atomicAdd(&hist[i], static_cast<unsigned long long>(sh[i]));
+  }
 }
 
 __global__ void CollectLongRuns(const uint32_t* __restrict__ run_start,
@@ -190,7 +206,8 @@ uint32_t FilterIndex(Ctx& c, double frequency) {
   static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
   uint64_t* hist = c.m_counter.reserve(kHistBins + 8);
   RVN_CUDA(cudaMemsetAsync(hist, 0, (kHistBins + 8) * sizeof(uint64_t), c.stream));
-  RunLengthHistogram<<<CeilDiv(c.i_keys, kThreads), kThreads, 0, c.stream>>>(
+  RunLengthHistogram<<<std::min<unsigned>(CeilDiv(c.i_keys, kThreads), 148 * 16),
+                       kThreads, 0, c.stream>>>(
       c.i_run_start.get(), c.i_keys, c.i_n,
       reinterpret_cast<unsigned long long*>(hist));
   RVN_LAUNCH_CHECK();
