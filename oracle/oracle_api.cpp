@@ -215,3 +215,11 @@ ORC_EXPORT std::uint64_t orc_truncate(std::uint32_t* ovl, std::uint64_t n,
   });
   return max_overlaps;
 }
+
+// the real std::sort on u64 elements compared by their high 32 bits,
+// descending - the checker for raven_b200/csrc/introsort.cuh
+ORC_EXPORT void orc_std_sort_hi32_desc(std::uint64_t* data, std::uint64_t n) {
+  std::sort(data, data + n, [](std::uint64_t a, std::uint64_t b) {
+    return (a >> 32) > (b >> 32);
+  });
+}

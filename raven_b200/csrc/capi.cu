@@ -3,7 +3,6 @@
 // (RavenLib/src/construct.cc:14-121).
 #include <algorithm>
 #include <cstring>
-#include <thread>
 
 #include "engine.cuh"
 
@@ -47,37 +46,9 @@ void CheckRange(const Ctx& c, uint32_t first, uint32_t last) {
   }
 }
 
-inline rvn_overlap Reverse(const rvn_overlap& o) {  // overlap_utils.cc:5-8
-  return rvn_overlap{o.rhs_id, o.rhs_begin, o.rhs_end, o.lhs_id,
-                     o.lhs_begin, o.lhs_end, o.score, o.strand};
-}
-
-inline uint32_t Length(const rvn_overlap& o) {  // overlap_utils.cc:10-12
-  return std::max(o.rhs_end - o.rhs_begin, o.lhs_end - o.lhs_begin);
-}
-
-template <typename F>
-void ParallelFor(size_t n, F&& f) {
-  unsigned t = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
-  if (n < 4096 || t == 1) {
-    for (size_t i = 0; i < n; ++i) f(i);
-    return;
-  }
-  std::vector<std::thread> th;
-  const size_t chunk = (n + t - 1) / t;
-  for (unsigned k = 0; k < t; ++k) {
-    const size_t b = k * chunk, e = std::min(n, b + chunk);
-    if (b >= e) break;
-    th.emplace_back([b, e, &f] {
-      for (size_t i = b; i < e; ++i) f(i);
-    });
-  }
-  for (auto& x : th) x.join();
-}
-
 // raven::FindOverlapsAndCreatePiles, same batch / flush schedule as the
-// reference; GPU for Minimize, Filter, Map and AddLayers, host for the serial
-// gather and the (libstdc++ std::sort) truncation rule.
+// reference; every step runs on the GPU (Minimize, Filter, Map, AddLayers,
+// gather, truncation); the host only drives the schedule.
 void Stage1(Ctx& c, double freq, uint64_t kmax, bool minhash, uint64_t ib,
             uint64_t qb) {
   if (ib == 0) ib = 1ULL << 32;
@@ -107,9 +78,7 @@ void Stage1(Ctx& c, double freq, uint64_t kmax, bool minhash, uint64_t ib,
   RVN_CUDA(cudaMemcpyAsync(d_poff, c.st_pile_off.data(), (n + 1ULL) * 8,
                            cudaMemcpyHostToDevice, c.stream));
 
-  std::vector<std::vector<rvn_overlap>> lists(n);
-  std::vector<uint8_t> touched(n, 0);
-  std::vector<uint32_t> touched_ids;
+  GatherReset(c);
   c.st_mapped = 0;
 
   uint64_t bases = 0;
@@ -121,55 +90,25 @@ void Stage1(Ctx& c, double freq, uint64_t kmax, bool minhash, uint64_t ib,
     BuildIndex(c, j, i + 1, minhash);
     FilterIndex(c, freq);
 
+    // every read up to the end of this index batch is a query, flushed per
+    // >= qb bases exactly like the reference (the truncation rule makes the
+    // flush boundaries observable)
     for (uint32_t k = 0, k0 = 0; k < i + 1; ++k) {
       bases += c.h_len[k];
       if (k != i && bases < qb) continue;
       bases = 0;
 
-      MapRange(c, k0, k + 1, true, true, true, false);
+      MapRange(c, k0, k + 1, true, true, true, false, /*fetch=*/false);
       PileAddLayersDevice(c, d_pile, d_poff, c.st_pile_off.data(), n,
                           c.m_ovl.get(), c.r_n_ovl);
-
-      // serial gather in query order: forward record, then mirrored record
-      touched_ids.clear();
-      const rvn_overlap* o = c.r_ovl.get();
-      for (uint64_t e = 0; e < c.r_n_ovl; ++e) {
-        lists[o[e].lhs_id].push_back(o[e]);
-        lists[o[e].rhs_id].push_back(Reverse(o[e]));
-        if (!touched[o[e].lhs_id]) {
-          touched[o[e].lhs_id] = 1;
-          touched_ids.push_back(o[e].lhs_id);
-        }
-        if (!touched[o[e].rhs_id]) {
-          touched[o[e].rhs_id] = 1;
-          touched_ids.push_back(o[e].rhs_id);
-        }
-      }
+      GatherFlush(c, k0, k + 1, kmax);
       c.st_mapped += c.r_n_ovl;
-      // keep the kmax longest of every list that grew (construct.cc:92-107)
-      ParallelFor(touched_ids.size(), [&](size_t t) {
-        auto& l = lists[touched_ids[t]];
-        touched[touched_ids[t]] = 0;
-        if (l.size() < kmax) return;
-        std::sort(l.begin(), l.end(),
-                  [](const rvn_overlap& a, const rvn_overlap& b) {
-                    return Length(a) > Length(b);
-                  });
-        l.resize(kmax);
-      });
       k0 = k + 1;
     }
     j = i + 1;
   }
 
-  c.st_ovl_off.assign(n + 1ULL, 0);
-  for (uint32_t i = 0; i < n; ++i) {
-    c.st_ovl_off[i + 1] = c.st_ovl_off[i] + lists[i].size();
-  }
-  c.st_ovl.resize(c.st_ovl_off[n]);
-  ParallelFor(n, [&](size_t i) {
-    std::copy(lists[i].begin(), lists[i].end(), c.st_ovl.begin() + c.st_ovl_off[i]);
-  });
+  GatherFetch(c);
   c.st_pile.resize(total_bins);
   RVN_CUDA(cudaMemcpyAsync(c.st_pile.data(), d_pile, total_bins * sizeof(uint16_t),
                            cudaMemcpyDeviceToHost, c.stream));

@@ -119,6 +119,14 @@ struct Ctx {
   DevBuf<uint64_t> p_off;
   DevBuf<rvn_overlap> p_ovl;
 
+  // ---- per-read overlap lists (gather.cu) ----
+  int g_cur = 0;
+  uint64_t g_total = 0;
+  DevBuf<rvn_overlap> g_list[2], g_stage;
+  DevBuf<uint64_t> g_off, g_off_alt, g_rhs_off, g_t_off, g_pairs;
+  DevBuf<uint32_t> g_cnt, g_kept, g_key, g_idx, g_key2, g_idx2, g_rhs_cnt,
+      g_total_cnt;
+
   // ---- stage-1 results ----
   std::vector<rvn_overlap> st_ovl;
   std::vector<uint64_t> st_ovl_off;
@@ -157,8 +165,16 @@ void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash);
 uint32_t FilterIndex(Ctx& c, double frequency);
 
 // ---- map.cu ----
+// fetch = copy the ordered overlaps to the host (rvn_map); stage 1 keeps them
+// on the device (c.m_ovl, c.m_ovl_off, c.r_n_ovl)
 void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
-              bool avoid_symmetric, bool minhash, bool want_filtered);
+              bool avoid_symmetric, bool minhash, bool want_filtered,
+              bool fetch = true);
+
+// ---- gather.cu ----
+void GatherReset(Ctx& c);
+void GatherFlush(Ctx& c, uint32_t k0, uint32_t k1, uint64_t kmax);
+void GatherFetch(Ctx& c);
 
 // ---- pile.cu ----
 // data: device u16 bins, off: device u64 offsets (n_piles + 1)

@@ -621,7 +621,8 @@ __global__ void ReorderOverlaps(const rvn_overlap* __restrict__ raw,
 }  // namespace
 
 void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
-              bool avoid_symmetric, bool minhash, bool want_filtered) {
+              bool avoid_symmetric, bool minhash, bool want_filtered,
+              bool fetch) {
   if (!c.i_valid) throw StateError("Map before Minimize");
   c.r_valid = false;
   const uint32_t nr = last - first;
@@ -827,18 +828,20 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
   TimerEnd(c);
 
   // ---- results to the host ----
-  rvn_overlap* ho = c.r_ovl.reserve(n_ovl + 1);
-  uint64_t* hoff = c.r_ovl_off.reserve(nr + 2ULL);
-  RVN_CUDA(cudaMemcpyAsync(ho, ordered, n_ovl * sizeof(rvn_overlap),
-                           cudaMemcpyDeviceToHost, c.stream));
-  RVN_CUDA(cudaMemcpyAsync(hoff, ooff, (nr + 1ULL) * sizeof(uint64_t),
-                           cudaMemcpyDeviceToHost, c.stream));
-  RVN_CUDA(cudaStreamSynchronize(c.stream));
+  if (fetch) {
+    rvn_overlap* ho = c.r_ovl.reserve(n_ovl + 1);
+    uint64_t* hoff = c.r_ovl_off.reserve(nr + 2ULL);
+    RVN_CUDA(cudaMemcpyAsync(ho, ordered, n_ovl * sizeof(rvn_overlap),
+                             cudaMemcpyDeviceToHost, c.stream));
+    RVN_CUDA(cudaMemcpyAsync(hoff, ooff, (nr + 1ULL) * sizeof(uint64_t),
+                             cudaMemcpyDeviceToHost, c.stream));
+    RVN_CUDA(cudaStreamSynchronize(c.stream));
+  }
   c.r_n_ovl = n_ovl;
   c.m_hits = n_hits;
   c.m_first_read = first;
   c.m_last_read = last;
-  c.r_valid = true;
+  c.r_valid = fetch;
 
   uint64_t qbases = 0;
   for (uint32_t r = first; r < last; ++r) qbases += c.h_len[r];
