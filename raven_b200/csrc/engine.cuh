@@ -89,7 +89,7 @@ struct Ctx {
   DevBuf<uint64_t> h_grp, h_pos;
   DevBuf<uint64_t> m_read_hit_off;  // per query read (+1)
   DevBuf<uint64_t> m_scratch64;     // oversize chain scratch
-  DevBuf<uint32_t> m_scratch32;
+  DevBuf<uint32_t> m_scratch32, m_fallback;
   DevBuf<rvn_overlap> m_ovl_raw, m_ovl;
   DevBuf<uint64_t> m_ovl_loc;  // per read: base<<24 | count  (raw placement)
   DevBuf<uint64_t> m_ovl_off;

@@ -496,63 +496,383 @@ __device__ uint32_t ChainRead(const ChainWork<IdxT>& wk, uint32_t n,
   return total;
 }
 
-constexpr uint32_t kChainSmemCap = 4095;  // hits per read on the smem path
+constexpr uint32_t kChainSmemCap = 8191;  // hits per read on the smem path
+constexpr uint32_t kChainMaxGroup = 1024;  // larger (rhs, strand) groups -> generic path
 
-// shared-memory path: one CTA per query read
-__global__ void __launch_bounds__(kThreads)
-ChainKernelSmem(const uint64_t* __restrict__ h_grp,
-                const uint64_t* __restrict__ h_pos,
-                const uint64_t* __restrict__ read_hit_off, uint32_t first_read,
-                uint32_t n_reads, ChainParams cp,
-                rvn_overlap* __restrict__ ovl_raw,
-                unsigned long long* __restrict__ ovl_counter, uint64_t ovl_cap,
-                uint64_t* __restrict__ ovl_loc) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ uint32_t sm32[34];
-  const uint32_t r = blockIdx.x;
-  if (r >= n_reads) return;
-  const uint64_t hb = read_hit_off[r];
-  const uint64_t n64 = read_hit_off[r + 1] - hb;
-  if (n64 < 4 || n64 > kChainSmemCap) {
-    // < 4 hits cannot form a band; oversize reads belong to the other kernel
-    if (threadIdx.x == 0 && n64 < 4) ovl_loc[r] = 0;
-    return;
-  }
-  const uint32_t n = static_cast<uint32_t>(n64);
-  uint32_t npad = 8;
-  while (npad < n + 1) npad <<= 1;  // room for the stop dummy at G[n]
+// ---------------------------------------------------------------------------
+// Fast path: one CTA per query read, everything in shared memory.
+//
+// Bands never span two (rhs_id, strand) pairs (group keys of different pairs
+// differ by >= 2^30 > bandwidth), so the reference's global sort by group is
+// not needed: hits are first split by pair with a shared-memory hash table
+// (pairs with < 4 hits can never form a band and are dropped on the spot),
+// then ONE THREAD PER PAIR orders its few dozen hits by (diagonal, positions)
+// with an insertion sort, walks the reference's window loop, and for every
+// closed band sorts by positions, runs the patience/LIS recurrence, splits at
+// gaps and tests covered bases — all without a barrier. Overlaps are staged
+// in the (by then dead) hash table and written out ordered by (pair, band,
+// walk) = the reference's emission order.
+// ---------------------------------------------------------------------------
+struct FastLayout {
+  uint32_t n, hs, ngmax;
+  size_t p2, d2, hk, hc, gl, goff, gcnt, bytes;
+};
 
-  ChainWork<uint16_t> wk;
-  wk.G = reinterpret_cast<uint64_t*>(smem);
-  wk.P = wk.G + npad;
-  wk.LB = reinterpret_cast<uint16_t*>(wk.P + npad);
-  const uint32_t nbmax = n / 4 + 1;
-  wk.PD = wk.LB + (n + nbmax + 2);
-  wk.IB = wk.PD + (n + 1);
-  wk.IE = wk.IB + nbmax;
-  wk.CNT = reinterpret_cast<uint32_t*>(
-      (reinterpret_cast<uintptr_t>(wk.IE + nbmax) + 3) & ~uintptr_t(3));
-
-  for (uint32_t i = threadIdx.x; i < npad; i += kThreads) {
-    wk.G[i] = i < n ? h_grp[hb + i] : ~0ULL;
-    wk.P[i] = i < n ? h_pos[hb + i] : ~0ULL;
-  }
-  __syncthreads();
-  uint64_t base = 0;
-  const uint32_t total = ChainRead<uint16_t, kThreads>(
-      wk, n, npad, first_read + r, cp, sm32, ovl_raw, ovl_counter, ovl_cap,
-      &base);
-  if (threadIdx.x == 0) ovl_loc[r] = total ? (base << 24) | total : 0;
+__host__ __device__ inline FastLayout MakeFastLayout(uint32_t n) {
+  FastLayout L;
+  L.n = n;
+  uint32_t hs = 8;
+  while (hs < n + 1) hs <<= 1;
+  L.hs = hs;
+  L.ngmax = n / 4 + 1;
+  size_t o = 0;
+  L.p2 = o;   o += 8ULL * n;                 // positions, grouped
+  L.d2 = o;   o += 4ULL * n;                 // diagonals, grouped (later LIS scratch)
+  o = (o + 15) & ~size_t(15);                // staging is read as uint4
+  L.hk = o;   o += 4ULL * hs;                // hash keys      } later: overlap staging
+  L.hc = o;   o += 4ULL * hs;                // hash counters  }   (8*hs bytes)
+  uint32_t gpad = 2;
+  while (gpad < L.ngmax) gpad <<= 1;
+  L.gl = o;   o += 8ULL * gpad;              // (gid << 32 | slot), later staging keys
+  L.goff = o; o += 2ULL * L.ngmax;
+  L.gcnt = o; o += 2ULL * L.ngmax;
+  L.bytes = (o + 15) & ~size_t(15);
+  return L;
 }
 
-size_t ChainSmemBytes(uint32_t n) {
-  uint32_t npad = 8;
-  while (npad < n + 1) npad <<= 1;
-  const uint32_t nbmax = n / 4 + 1;
-  size_t b = 2ULL * npad * 8;
-  b += 2ULL * ((n + nbmax + 2) + (n + 1) + 2 * nbmax);
-  b += 4 + 4ULL * nbmax;
-  return b + 16;
+__device__ __forceinline__ uint32_t HashGid(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352dU;
+  x ^= x >> 15;
+  x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
+}
+
+// one band [jb, ie) of a pair: sort by positions, LIS, gap split, emit
+__device__ __forceinline__ void FastBand(uint64_t* P, uint32_t* D, uint32_t jb,
+                                         uint32_t ie, bool strand, uint32_t lhs_id,
+                                         uint32_t rhs_id, const ChainParams& cp,
+                                         uint32_t q, uint32_t* seq,
+                                         rvn_overlap* stage, uint32_t* stage_key,
+                                         uint32_t* stage_cnt) {
+  const uint32_t len = ie - jb;
+  if (len < cp.chain) return;
+  uint64_t* Pb = P + jb;
+  for (uint32_t a = 1; a < len; ++a) {  // insertion sort by positions
+    const uint64_t p = Pb[a];
+    uint32_t b = a;
+    while (b > 0 && Pb[b - 1] > p) {
+      Pb[b] = Pb[b - 1];
+      --b;
+    }
+    Pb[b] = p;
+  }
+  // the band's diagonals are dead: their storage holds minimal[1..len] and
+  // predecessor[0..len) as u16 (minimal[0] is always 0)
+  uint16_t* mini = reinterpret_cast<uint16_t*>(D + jb);  // mini[x-1] = minimal[x]
+  uint16_t* pred = mini + len;
+  uint32_t longest = 0;
+  for (uint32_t t = 0; t < len; ++t) {
+    const uint32_t cl = static_cast<uint32_t>(Pb[t] >> 32);
+    const uint32_t cr = static_cast<uint32_t>(Pb[t]);
+    uint32_t lo = 1, hi = longest;
+    while (lo <= hi) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      const uint64_t tail = Pb[mini[mid - 1]];
+      const uint32_t tl = static_cast<uint32_t>(tail >> 32);
+      const uint32_t tr = static_cast<uint32_t>(tail);
+      if (tl < cl && (strand ? tr < cr : tr > cr)) {
+        lo = mid + 1;
+      } else {
+        hi = mid - 1;
+      }
+    }
+    pred[t] = lo > 1 ? mini[lo - 2] : 0;
+    mini[lo - 1] = static_cast<uint16_t>(t);
+    longest = max(longest, lo);
+  }
+  if (longest < cp.chain) return;
+  {
+    uint32_t j = mini[longest - 1];
+    for (uint32_t i = 0; i < longest; ++i) {
+      const uint32_t pj = pred[j];
+      mini[longest - 1 - i] = static_cast<uint16_t>(j);
+      j = pj;
+    }
+  }
+  const uint16_t* idx = mini;
+  for (uint32_t kk = 1, l = 0; kk <= longest; ++kk) {
+    const uint32_t prev = static_cast<uint32_t>(Pb[idx[kk - 1]] >> 32);
+    const uint32_t cur =
+        kk < longest ? static_cast<uint32_t>(Pb[idx[kk]] >> 32) : 0xFFFFFFFFu;
+    if (cur - prev > cp.gap) {
+      if (kk - l >= cp.chain) {
+        uint32_t lm = 0, lb_ = 0, le = 0, rm = 0, rb_ = 0, re = 0;
+        for (uint32_t m = l; m < kk; ++m) {
+          const uint64_t pp = Pb[idx[m]];
+          const uint32_t lp = static_cast<uint32_t>(pp >> 32);
+          if (lp > le) {
+            lm += le - lb_;
+            lb_ = lp;
+          }
+          le = lp + cp.k;
+          uint32_t rp = static_cast<uint32_t>(pp);
+          rp = strand ? rp : (1U << 31) - (rp + cp.k - 1);
+          if (rp > re) {
+            rm += re - rb_;
+            rb_ = rp;
+          }
+          re = rp + cp.k;
+        }
+        lm += le - lb_;
+        rm += re - rb_;
+        if (min(lm, rm) >= cp.matches) {
+          const uint64_t pf = Pb[idx[l]], pl = Pb[idx[kk - 1]];
+          rvn_overlap o;
+          o.lhs_id = lhs_id;
+          o.lhs_begin = static_cast<uint32_t>(pf >> 32);
+          o.lhs_end = cp.k + static_cast<uint32_t>(pl >> 32);
+          o.rhs_id = rhs_id;
+          o.rhs_begin = strand ? static_cast<uint32_t>(pf) : static_cast<uint32_t>(pl);
+          o.rhs_end = cp.k + (strand ? static_cast<uint32_t>(pl)
+                                     : static_cast<uint32_t>(pf));
+          o.score = min(lm, rm);
+          o.strand = strand;
+          const uint32_t slot = atomicAdd(stage_cnt, 1u);
+          stage[slot] = o;
+          stage_key[slot] = (q << 16) | (*seq)++;
+        }
+      }
+      l = kk;
+    }
+  }
+}
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+ChainKernelFast(const uint64_t* __restrict__ h_grp,
+                const uint64_t* __restrict__ h_pos,
+                const uint64_t* __restrict__ read_hit_off, uint32_t first_read,
+                const uint32_t* __restrict__ read_list, ChainParams cp,
+                rvn_overlap* __restrict__ ovl_raw,
+                unsigned long long* __restrict__ ovl_counter, uint64_t ovl_cap,
+                uint64_t* __restrict__ ovl_loc,
+                uint32_t* __restrict__ fallback_list,
+                unsigned int* __restrict__ fallback_cnt) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ uint32_t sm32[34];
+  __shared__ uint32_t sh_stage_cnt, sh_bail;
+  __shared__ unsigned long long sh_base;
+  const uint32_t r = read_list[blockIdx.x];
+  const uint64_t hb = read_hit_off[r];
+  const uint32_t n = static_cast<uint32_t>(read_hit_off[r + 1] - hb);
+  const FastLayout L = MakeFastLayout(n);
+  uint64_t* P2 = reinterpret_cast<uint64_t*>(smem + L.p2);
+  uint32_t* D2 = reinterpret_cast<uint32_t*>(smem + L.d2);
+  uint32_t* HK = reinterpret_cast<uint32_t*>(smem + L.hk);
+  uint32_t* HC = reinterpret_cast<uint32_t*>(smem + L.hc);
+  uint64_t* GL = reinterpret_cast<uint64_t*>(smem + L.gl);
+  uint16_t* GOFF = reinterpret_cast<uint16_t*>(smem + L.goff);
+  uint16_t* GCNT = reinterpret_cast<uint16_t*>(smem + L.gcnt);
+  const uint32_t hmask = L.hs - 1;
+  const uint64_t* hg = h_grp + hb;
+  const uint64_t* hp = h_pos + hb;
+
+  // ---- 1a. hash table of (rhs_id, strand) pairs with their hit counts ----
+  for (uint32_t i = threadIdx.x; i < L.hs; i += THREADS) {
+    HK[i] = 0xFFFFFFFFu;
+    HC[i] = 0;
+  }
+  if (threadIdx.x == 0) {
+    sh_stage_cnt = 0;
+    sh_bail = 0;
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
+    const uint32_t gid = static_cast<uint32_t>(hg[i] >> 32);
+    uint32_t s = HashGid(gid) & hmask;
+    while (true) {
+      const uint32_t prev = atomicCAS(&HK[s], 0xFFFFFFFFu, gid);
+      if (prev == 0xFFFFFFFFu || prev == gid) break;
+      s = (s + 1) & hmask;
+    }
+    atomicAdd(&HC[s], 1u);
+  }
+  __syncthreads();
+
+  // ---- 1b. pairs with >= 4 hits: list + grouped offsets ----
+  uint32_t carry = 0;  // low 16: pairs so far, high 16: hits so far
+  for (uint32_t b = 0; b < L.hs; b += THREADS) {
+    const uint32_t s = b + threadIdx.x;
+    const uint32_t cnt = s < L.hs ? HC[s] : 0;
+    const uint32_t keep = cnt >= 4;
+    if (cnt > kChainMaxGroup) sh_bail = 1;
+    uint32_t tot;
+    const uint32_t ex = BlockExclusiveSum<uint32_t, THREADS>(
+        keep ? ((cnt << 16) | 1u) : 0u, sm32, &tot);
+    if (s < L.hs) {
+      if (keep) {
+        const uint32_t at = carry + ex;
+        GL[at & 0xFFFF] = (static_cast<uint64_t>(HK[s]) << 32) | s;
+        HC[s] = (cnt << 16) | (at >> 16);  // (count, offset)
+      } else {
+        HC[s] = 0xFFFFFFFFu;  // dropped
+      }
+    }
+    carry += tot;
+  }
+  const uint32_t ng = carry & 0xFFFF;
+  __syncthreads();
+  if (sh_bail) {  // a very large pair: the generic kernel takes this read
+    if (threadIdx.x == 0) fallback_list[atomicAdd(fallback_cnt, 1u)] = r;
+    return;
+  }
+  if (ng == 0) {
+    if (threadIdx.x == 0) ovl_loc[r] = 0;
+    return;
+  }
+
+  // ---- 1c. pairs in ascending key order (= the reference's emission order) ----
+  uint32_t gpad = 2;
+  while (gpad < ng) gpad <<= 1;
+  for (uint32_t i = ng + threadIdx.x; i < gpad; i += THREADS) GL[i] = ~0ULL;
+  __syncthreads();
+  for (uint32_t size = 2; size <= gpad; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t t = threadIdx.x; t < (gpad >> 1); t += THREADS) {
+        const uint32_t i = 2 * t - (t & (stride - 1));
+        const uint32_t j = i + stride;
+        const uint64_t a = GL[i], c2 = GL[j];
+        if ((a > c2) == ((i & size) == 0)) {
+          GL[i] = c2;
+          GL[j] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (uint32_t q = threadIdx.x; q < ng; q += THREADS) {
+    const uint32_t s = static_cast<uint32_t>(GL[q]);
+    const uint32_t v = HC[s];
+    GOFF[q] = static_cast<uint16_t>(v & 0xFFFF);
+    GCNT[q] = static_cast<uint16_t>(v >> 16);
+    HC[s] = v & 0xFFFF;  // fill cursor
+  }
+  __syncthreads();
+
+  // ---- 1d. scatter the hits of kept pairs (order inside a pair is free) ----
+  for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
+    const uint64_t g = hg[i];
+    const uint32_t gid = static_cast<uint32_t>(g >> 32);
+    uint32_t s = HashGid(gid) & hmask;
+    while (HK[s] != gid) s = (s + 1) & hmask;
+    if (HC[s] == 0xFFFFFFFFu) continue;
+    const uint32_t at = atomicAdd(&HC[s], 1u);
+    D2[at] = static_cast<uint32_t>(g);
+    P2[at] = hp[i];
+  }
+  __syncthreads();
+
+  // ---- 2. one thread per pair ----
+  rvn_overlap* stage = reinterpret_cast<rvn_overlap*>(smem + L.hk);
+  uint32_t* stage_key = reinterpret_cast<uint32_t*>(smem + L.gl);
+  // GL is dead once every thread has its (gid, offset, count) in registers
+  uint32_t my_gid[(kChainSmemCap / 4 + THREADS) / THREADS];
+  {
+    uint32_t t = 0;
+    for (uint32_t q = threadIdx.x; q < ng; q += THREADS) my_gid[t++] = GL[q] >> 32;
+  }
+  __syncthreads();
+  {
+    uint32_t t = 0;
+    for (uint32_t q = threadIdx.x; q < ng; q += THREADS, ++t) {
+      const uint32_t gid = my_gid[t];
+      const uint32_t off = GOFF[q], m = GCNT[q];
+      uint32_t* D = D2 + off;
+      uint64_t* P = P2 + off;
+      for (uint32_t a = 1; a < m; ++a) {  // insertion sort by (diagonal, positions)
+        const uint32_t d = D[a];
+        const uint64_t p = P[a];
+        uint32_t b = a;
+        while (b > 0 && (D[b - 1] > d || (D[b - 1] == d && P[b - 1] > p))) {
+          D[b] = D[b - 1];
+          P[b] = P[b - 1];
+          --b;
+        }
+        D[b] = d;
+        P[b] = p;
+      }
+      // the reference's window loop; index m plays the stop dummy
+      const bool strand = gid & 1;
+      const uint32_t rhs_id = gid >> 1;
+      uint32_t seq = 0;
+      bool open = false;
+      uint32_t ob = 0, oe = 0;
+      for (uint32_t i = 1, j = 0; i <= m; ++i) {
+        if (i == m || D[i] - D[j] > cp.bandwidth) {
+          if (i - j >= 4) {
+            if (open && oe > j) {
+              oe = i;
+            } else {
+              if (open) {
+                FastBand(P, D, ob, oe, strand, first_read + r, rhs_id, cp, q, &seq,
+                         stage, stage_key, &sh_stage_cnt);
+              }
+              ob = j;
+              oe = i;
+              open = true;
+            }
+          }
+          ++j;
+          while (j < i && (i == m || D[i] - D[j] > cp.bandwidth)) ++j;
+        }
+      }
+      if (open) {
+        FastBand(P, D, ob, oe, strand, first_read + r, rhs_id, cp, q, &seq, stage,
+                 stage_key, &sh_stage_cnt);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 3. emission order, reserved slab, write ----
+  const uint32_t total = sh_stage_cnt;
+  if (threadIdx.x == 0) {
+    sh_base = total ? atomicAdd(ovl_counter, static_cast<unsigned long long>(total))
+                    : 0ULL;
+    ovl_loc[r] = total ? (static_cast<uint64_t>(sh_base) << 24) | total : 0;
+  }
+  if (total == 0) return;
+  uint64_t* order = P2;  // dead: (key << 32 | staging slot)
+  uint32_t opad = 2;
+  while (opad < total) opad <<= 1;
+  for (uint32_t i = threadIdx.x; i < opad; i += THREADS) {
+    order[i] = i < total ? (static_cast<uint64_t>(stage_key[i]) << 32) | i : ~0ULL;
+  }
+  __syncthreads();
+  for (uint32_t size = 2; size <= opad; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t t = threadIdx.x; t < (opad >> 1); t += THREADS) {
+        const uint32_t i = 2 * t - (t & (stride - 1));
+        const uint32_t j = i + stride;
+        const uint64_t a = order[i], c2 = order[j];
+        if ((a > c2) == ((i & size) == 0)) {
+          order[i] = c2;
+          order[j] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const uint64_t base = sh_base;
+  if (base + total > ovl_cap) return;  // host reports the overflow
+  const uint4* src = reinterpret_cast<const uint4*>(stage);
+  uint4* dst = reinterpret_cast<uint4*>(ovl_raw + base);
+  for (uint32_t i = threadIdx.x; i < total * 2; i += THREADS) {
+    const uint32_t from = static_cast<uint32_t>(order[i >> 1]);
+    dst[i] = src[from * 2 + (i & 1)];
+  }
 }
 
 // global-memory path for reads with more hits than shared memory holds: one
@@ -751,26 +1071,80 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
   RVN_CUDA(cudaMemsetAsync(counter, 0, sizeof(uint64_t), c.stream));
   RVN_CUDA(cudaMemsetAsync(loc, 0, (nr + 1ULL) * sizeof(uint64_t), c.stream));
 
-  uint64_t max_small = 0;
+  // size classes by hit count (n + 1 <= 256 << k), then the generic path
+  constexpr int kClasses = 6;
+  std::vector<uint32_t> cls[kClasses];
   std::vector<uint32_t> big;
+  const bool fast_ok = c.prm.chain >= 4;  // staging capacity argument (n / 4)
   for (uint32_t i = 0; i < nr; ++i) {
     const uint64_t n = h_rho[i + 1] - h_rho[i];
-    if (n > kChainSmemCap) {
+    if (n < 4) continue;  // cannot form a band; ovl_loc stays 0
+    if (n > kChainSmemCap || !fast_ok) {
       big.push_back(i);
-    } else if (n > max_small) {
-      max_small = n;
+      continue;
     }
+    int k = 0;
+    while ((256u << k) < n + 1) ++k;
+    cls[k].push_back(i);
   }
-  if (nr > 0 && max_small >= 4) {
-    const size_t smem = ChainSmemBytes(static_cast<uint32_t>(max_small));
-    RVN_CUDA(cudaFuncSetAttribute(ChainKernelSmem,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(ChainSmemBytes(kChainSmemCap))));
-    ChainKernelSmem<<<nr, kThreads, smem, c.stream>>>(
-        hg, hp, read_hit_off, first, nr, cp, raw,
-        reinterpret_cast<unsigned long long*>(counter), ovl_cap, loc);
-    RVN_LAUNCH_CHECK();
-    ++c.launches;
+  {
+    size_t total = 0;
+    for (auto& v : cls) total += v.size();
+    uint32_t* d_list = c.m_first.reserve(std::max<size_t>(total, n_q) + 1);
+    uint32_t* d_fb = c.m_fallback.reserve(nr + 4ULL);
+    RVN_CUDA(cudaMemsetAsync(d_fb, 0, 2 * sizeof(uint32_t), c.stream));
+    std::vector<uint32_t> flat;
+    flat.reserve(total);
+    for (int k = kClasses - 1; k >= 0; --k) {
+      flat.insert(flat.end(), cls[k].begin(), cls[k].end());
+    }
+    if (total) {
+      RVN_CUDA(cudaMemcpyAsync(d_list, flat.data(), total * sizeof(uint32_t),
+                               cudaMemcpyHostToDevice, c.stream));
+      RVN_CUDA(cudaStreamSynchronize(c.stream));  // flat goes out of scope
+    }
+    size_t off = 0;
+    auto* ctr = reinterpret_cast<unsigned long long*>(counter);
+    for (int k = kClasses - 1; k >= 0; --k) {  // largest class first
+      const unsigned cnt = static_cast<unsigned>(cls[k].size());
+      if (cnt == 0) continue;
+      const size_t smem = MakeFastLayout((256u << k) - 1).bytes;
+      const uint32_t* lst = d_list + off;
+      off += cnt;
+      if (k >= 3) {
+        auto kern = ChainKernelFast<256, 2>;
+        RVN_CUDA(cudaFuncSetAttribute(
+            kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            static_cast<int>(MakeFastLayout(kChainSmemCap).bytes)));
+        kern<<<cnt, 256, smem, c.stream>>>(hg, hp, read_hit_off, first, lst, cp,
+                                           raw, ctr, ovl_cap, loc, d_fb + 2, d_fb);
+      } else {
+        auto kern = ChainKernelFast<128, 8>;
+        RVN_CUDA(cudaFuncSetAttribute(
+            kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            static_cast<int>(MakeFastLayout(2047).bytes)));
+        kern<<<cnt, 128, smem, c.stream>>>(hg, hp, read_hit_off, first, lst, cp,
+                                           raw, ctr, ovl_cap, loc, d_fb + 2, d_fb);
+      }
+      RVN_LAUNCH_CHECK();
+      ++c.launches;
+    }
+    if (total) {
+      // reads the fast kernel handed back (a pair with > kChainMaxGroup hits)
+      std::vector<uint32_t> fb(1);
+      RVN_CUDA(cudaMemcpyAsync(fb.data(), d_fb, sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, c.stream));
+      RVN_CUDA(cudaStreamSynchronize(c.stream));
+      const uint32_t nfb = fb[0];
+      if (nfb) {
+        fb.resize(nfb);
+        RVN_CUDA(cudaMemcpyAsync(fb.data(), d_fb + 2, nfb * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, c.stream));
+        RVN_CUDA(cudaStreamSynchronize(c.stream));
+        std::sort(fb.begin(), fb.end());
+        big.insert(big.end(), fb.begin(), fb.end());
+      }
+    }
   }
   if (!big.empty()) {
     std::vector<uint64_t> off64(big.size() + 1, 0), off32(big.size() + 1, 0);
