@@ -9,7 +9,8 @@
  *   rvn_reads_upload       biosoup::NucleicAcid fields RavenLib/include/raven/graph/graph.h:13-18
  *   rvn_minimize           MinimizerEngine::Minimize   RavenLib/src/construct.cc:42-43,363
  *   rvn_filter             MinimizerEngine::Filter     RavenLib/src/construct.cc:44,372
- *   rvn_map                MinimizerEngine::Map        RavenLib/src/construct.cc:59-64,377-381
+ *   rvn_map / rvn_map_external
+ *                          MinimizerEngine::Map        RavenLib/src/construct.cc:59-64,377-381
  *   rvn_pile_add_layers    raven::Pile::AddLayers      RavenLib/src/pile.cc:33-62
  *   rvn_find_overlaps_and_create_piles
  *                          raven::FindOverlapsAndCreatePiles
@@ -91,6 +92,13 @@ int rvn_reads_upload(rvn_ctx* ctx, const uint64_t* words,
                      const uint64_t* word_off, const uint32_t* lens,
                      uint32_t n_reads);
 
+/* Same, with explicit sequence ids (biosoup::NucleicAcid::id): origins and
+ * overlap ids carry ids[i] instead of i. raven re-sorts its sequence vector
+ * before stage 2 (construct.cc:324-349), so id != position there. */
+int rvn_reads_upload_ids(rvn_ctx* ctx, const uint64_t* words,
+                         const uint64_t* word_off, const uint32_t* lens,
+                         const uint32_t* ids, uint32_t n_reads);
+
 /* Minimize(reads[first..last), minhash): sketch and index. */
 int rvn_minimize(rvn_ctx* ctx, uint32_t first, uint32_t last, int minhash);
 
@@ -105,6 +113,12 @@ int rvn_filter(rvn_ctx* ctx, double frequency, uint32_t* occurrence);
  * positions of over-frequent query minimizers (only if want_filtered). */
 int rvn_map(rvn_ctx* ctx, uint32_t first, uint32_t last, int avoid_equal,
             int avoid_symmetric, int minhash, int want_filtered);
+/* Map one read that is NOT in the uploaded set (e.g. a query of an earlier
+ * index batch, construct.cc:59; plasmids vs unitigs, assemble.cc:757,780).
+ * Results through rvn_map_results with a single query. */
+int rvn_map_external(rvn_ctx* ctx, const uint64_t* words, uint32_t len,
+                     uint32_t id, int avoid_equal, int avoid_symmetric,
+                     int minhash, int want_filtered);
 int rvn_map_results(rvn_ctx* ctx, const rvn_overlap** overlaps,
                     const uint64_t** ovl_off, uint64_t* n_overlaps,
                     const uint32_t** filtered, const uint64_t** filt_off);

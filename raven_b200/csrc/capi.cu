@@ -57,6 +57,9 @@ void Stage1(Ctx& c, double freq, uint64_t kmax, bool minhash, uint64_t ib,
     throw InvalidArgument(
         "[ram::MinimizerEngine::Filter] error: invalid frequency");
   }
+  if (!c.ids_identity) {
+    throw StateError("stage 1 needs read ids equal to their index");
+  }
   c.st_valid = false;
   // a stage-1 pass owns its intermediates: nothing is carried over from an
   // earlier call (sketches, micromizers and the index are rebuilt)
@@ -190,39 +193,119 @@ RVN_API int rvn_engine_configure(rvn_ctx* ctx, uint32_t k, uint32_t w,
   });
 }
 
+static void UploadReads(Ctx& c, const uint64_t* words, const uint64_t* word_off,
+                        const uint32_t* lens, const uint32_t* ids,
+                        uint32_t n_reads) {
+  if (n_reads && (!word_off || !lens)) throw InvalidArgument("null read set");
+  if (n_reads == 0xFFFFFFFFu) throw LimitError("too many reads");
+  c.s_valid = c.q_valid = c.i_valid = c.r_valid = c.st_valid = false;
+  c.tiles_k = 0;
+  c.n_reads = n_reads;
+  c.h_woff.assign(1, 0);
+  if (n_reads) c.h_woff.assign(word_off, word_off + n_reads + 1);
+  c.h_len.assign(lens, lens + n_reads);
+  c.h_ids.resize(n_reads);
+  c.ids_identity = true;
+  for (uint32_t i = 0; i < n_reads; ++i) {
+    const uint64_t have = c.h_woff[i + 1] - c.h_woff[i];
+    if (have < ((static_cast<uint64_t>(lens[i]) + 31) >> 5)) {
+      throw InvalidArgument("read shorter than its declared length");
+    }
+    if (lens[i] >= (1u << 31)) throw LimitError("read of 2^31 or more bases");
+    c.h_ids[i] = ids ? ids[i] : i;
+    if (c.h_ids[i] != i) c.ids_identity = false;
+  }
+  c.n_words = c.h_woff[n_reads];
+  // one spare slot everywhere: an external query read rides at index n_reads
+  uint64_t* dw = c.d_words.reserve(c.n_words + 2);
+  uint64_t* dwo = c.d_woff.reserve(n_reads + 2ULL);
+  uint32_t* dl = c.d_len.reserve(n_reads + 2ULL);
+  uint32_t* di = c.d_ids.reserve(n_reads + 2ULL);
+  if (c.n_words) {
+    RVN_CUDA(cudaMemcpyAsync(dw, words, c.n_words * 8, cudaMemcpyHostToDevice,
+                             c.stream));
+  }
+  RVN_CUDA(cudaMemcpyAsync(dwo, c.h_woff.data(), (n_reads + 1ULL) * 8,
+                           cudaMemcpyHostToDevice, c.stream));
+  if (n_reads) {
+    RVN_CUDA(cudaMemcpyAsync(dl, c.h_len.data(), n_reads * 4ULL,
+                             cudaMemcpyHostToDevice, c.stream));
+    RVN_CUDA(cudaMemcpyAsync(di, c.h_ids.data(), n_reads * 4ULL,
+                             cudaMemcpyHostToDevice, c.stream));
+  }
+  RVN_CUDA(cudaStreamSynchronize(c.stream));
+}
+
 RVN_API int rvn_reads_upload(rvn_ctx* ctx, const uint64_t* words,
                              const uint64_t* word_off, const uint32_t* lens,
                              uint32_t n_reads) {
   return Guard(ctx, [&](Ctx& c) {
-    if (n_reads && (!word_off || !lens)) throw InvalidArgument("null read set");
-    c.s_valid = c.q_valid = c.i_valid = c.r_valid = c.st_valid = false;
-    c.tiles_k = 0;
-    c.n_reads = n_reads;
-    c.h_woff.assign(word_off, word_off + n_reads + (n_reads ? 1 : 0));
-    if (!n_reads) c.h_woff.assign(1, 0);
-    c.h_len.assign(lens, lens + n_reads);
-    for (uint32_t i = 0; i < n_reads; ++i) {
-      const uint64_t have = c.h_woff[i + 1] - c.h_woff[i];
-      if (have < ((static_cast<uint64_t>(lens[i]) + 31) >> 5)) {
-        throw InvalidArgument("read shorter than its declared length");
-      }
-      if (lens[i] >= (1u << 31)) throw LimitError("read of 2^31 or more bases");
-    }
-    c.n_words = c.h_woff[n_reads];
-    uint64_t* dw = c.d_words.reserve(c.n_words + 2);
-    uint64_t* dwo = c.d_woff.reserve(n_reads + 1ULL);
-    uint32_t* dl = c.d_len.reserve(n_reads + 1ULL);
-    if (c.n_words) {
-      RVN_CUDA(cudaMemcpyAsync(dw, words, c.n_words * 8, cudaMemcpyHostToDevice,
-                               c.stream));
-    }
-    RVN_CUDA(cudaMemcpyAsync(dwo, c.h_woff.data(), (n_reads + 1ULL) * 8,
-                             cudaMemcpyHostToDevice, c.stream));
-    if (n_reads) {
-      RVN_CUDA(cudaMemcpyAsync(dl, c.h_len.data(), n_reads * 4ULL,
+    UploadReads(c, words, word_off, lens, nullptr, n_reads);
+  });
+}
+
+RVN_API int rvn_reads_upload_ids(rvn_ctx* ctx, const uint64_t* words,
+                                 const uint64_t* word_off, const uint32_t* lens,
+                                 const uint32_t* ids, uint32_t n_reads) {
+  return Guard(ctx, [&](Ctx& c) {
+    UploadReads(c, words, word_off, lens, ids, n_reads);
+  });
+}
+
+// Map one read that is not part of the uploaded set (it rides in the spare
+// slot behind the set for the duration of the call)
+RVN_API int rvn_map_external(rvn_ctx* ctx, const uint64_t* words, uint32_t len,
+                             uint32_t id, int avoid_equal, int avoid_symmetric,
+                             int minhash, int want_filtered) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (!c.i_valid) throw StateError("Map before Minimize");
+    if (len >= (1u << 31)) throw LimitError("read of 2^31 or more bases");
+    const uint32_t n = c.n_reads;
+    const uint64_t nw = (static_cast<uint64_t>(len) + 31) >> 5;
+    if (nw && !words) throw InvalidArgument("null read");
+    uint64_t* dw = c.d_words.reserve_keep(c.n_words + nw + 2, c.n_words, c.stream);
+    if (nw) {
+      RVN_CUDA(cudaMemcpyAsync(dw + c.n_words, words, nw * 8,
                                cudaMemcpyHostToDevice, c.stream));
     }
+    EnsureTiles(c);
+    // extend the host/device tables by the spare slot
+    const uint64_t woff_tail[2] = {c.n_words, c.n_words + nw};
+    uint64_t tiles = 0;
+    if (len >= c.prm.k && len - c.prm.k + 1 >= c.prm.w) {
+      tiles = (len - c.prm.k + 1 + kSketchTile - 1) / kSketchTile;
+    }
+    const uint64_t tile_tail[2] = {c.h_tile_off[n], c.h_tile_off[n] + tiles};
+    RVN_CUDA(cudaMemcpyAsync(c.d_woff.get() + n, woff_tail, 16,
+                             cudaMemcpyHostToDevice, c.stream));
+    RVN_CUDA(cudaMemcpyAsync(c.d_tile_off.get() + n, tile_tail, 16,
+                             cudaMemcpyHostToDevice, c.stream));
+    RVN_CUDA(cudaMemcpyAsync(c.d_len.get() + n, &len, 4, cudaMemcpyHostToDevice,
+                             c.stream));
+    RVN_CUDA(cudaMemcpyAsync(c.d_ids.get() + n, &id, 4, cudaMemcpyHostToDevice,
+                             c.stream));
     RVN_CUDA(cudaStreamSynchronize(c.stream));
+    c.h_woff.push_back(c.n_words + nw);
+    c.h_len.push_back(len);
+    c.h_ids.push_back(id);
+    c.h_tile_off.push_back(tile_tail[1]);
+    c.n_reads = n + 1;
+    c.s_valid = c.q_valid = false;
+    try {
+      MapRange(c, n, n + 1, avoid_equal != 0, avoid_symmetric != 0, minhash != 0,
+               want_filtered != 0);
+    } catch (...) {
+      c.n_reads = n;
+      c.h_woff.pop_back(); c.h_len.pop_back(); c.h_ids.pop_back();
+      c.h_tile_off.pop_back();
+      c.s_valid = c.q_valid = false;
+      throw;
+    }
+    c.n_reads = n;
+    c.h_woff.pop_back(); c.h_len.pop_back(); c.h_ids.pop_back();
+    c.h_tile_off.pop_back();
+    c.s_valid = c.q_valid = false;
+    TimerCollect(c);
   });
 }
 

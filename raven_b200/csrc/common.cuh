@@ -62,6 +62,23 @@ struct DevBuf {
     }
     return p;
   }
+  // growth keeps the first `keep` elements
+  T* reserve_keep(std::size_t n, std::size_t keep, cudaStream_t stream) {
+    if (n > cap) {
+      std::size_t want = n + n / 16 + 64;
+      T* np = nullptr;
+      RVN_CUDA(cudaMalloc(&np, want * sizeof(T)));
+      if (p && keep) {
+        RVN_CUDA(cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice,
+                                 stream));
+        RVN_CUDA(cudaStreamSynchronize(stream));
+      }
+      if (p) cudaFree(p);
+      p = np;
+      cap = want;
+    }
+    return p;
+  }
   T* get() const { return p; }
 };
 

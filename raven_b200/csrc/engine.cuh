@@ -47,9 +47,10 @@ struct Ctx {
   uint32_t n_reads = 0;
   uint64_t n_words = 0;
   DevBuf<uint64_t> d_words, d_woff;
-  DevBuf<uint32_t> d_len;
+  DevBuf<uint32_t> d_len, d_ids;
   std::vector<uint64_t> h_woff;
-  std::vector<uint32_t> h_len;
+  std::vector<uint32_t> h_len, h_ids;
+  bool ids_identity = true;  // id == index (needed by the device-side gather)
   // sketch tiles: tile_off[r] = first tile of read r (depends on k)
   std::vector<uint64_t> h_tile_off;
   DevBuf<uint64_t> d_tile_off;

@@ -653,7 +653,8 @@ template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 ChainKernelFast(const uint64_t* __restrict__ h_grp,
                 const uint64_t* __restrict__ h_pos,
-                const uint64_t* __restrict__ read_hit_off, uint32_t first_read,
+                const uint64_t* __restrict__ read_hit_off,
+                const uint32_t* __restrict__ lhs_ids,
                 const uint32_t* __restrict__ read_list, ChainParams cp,
                 rvn_overlap* __restrict__ ovl_raw,
                 unsigned long long* __restrict__ ovl_counter, uint64_t ovl_cap,
@@ -816,7 +817,7 @@ ChainKernelFast(const uint64_t* __restrict__ h_grp,
               oe = i;
             } else {
               if (open) {
-                FastBand(P, D, ob, oe, strand, first_read + r, rhs_id, cp, q, &seq,
+                FastBand(P, D, ob, oe, strand, lhs_ids[r], rhs_id, cp, q, &seq,
                          stage, stage_key, &sh_stage_cnt);
               }
               ob = j;
@@ -829,7 +830,7 @@ ChainKernelFast(const uint64_t* __restrict__ h_grp,
         }
       }
       if (open) {
-        FastBand(P, D, ob, oe, strand, first_read + r, rhs_id, cp, q, &seq, stage,
+        FastBand(P, D, ob, oe, strand, lhs_ids[r], rhs_id, cp, q, &seq, stage,
                  stage_key, &sh_stage_cnt);
       }
     }
@@ -881,7 +882,8 @@ __global__ void __launch_bounds__(kThreads)
 ChainKernelGlobal(const uint64_t* __restrict__ h_grp,
                   const uint64_t* __restrict__ h_pos,
                   const uint64_t* __restrict__ read_hit_off,
-                  uint32_t first_read, const uint32_t* __restrict__ big_reads,
+                  const uint32_t* __restrict__ lhs_ids,
+                  const uint32_t* __restrict__ big_reads,
                   const uint64_t* __restrict__ slab64_off,
                   const uint64_t* __restrict__ slab32_off,
                   uint64_t* __restrict__ slab64, uint32_t* __restrict__ slab32,
@@ -912,7 +914,7 @@ ChainKernelGlobal(const uint64_t* __restrict__ h_grp,
   __syncthreads();
   uint64_t base = 0;
   const uint32_t total = ChainRead<uint32_t, kThreads>(
-      wk, n, npad, first_read + r, cp, sm32, ovl_raw, ovl_counter, ovl_cap,
+      wk, n, npad, lhs_ids[r], cp, sm32, ovl_raw, ovl_counter, ovl_cap,
       &base);
   if (threadIdx.x == 0) ovl_loc[r] = total ? (base << 24) | total : 0;
 }
@@ -1064,6 +1066,7 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
   // ---- chain ----
   TimerBegin(c, "chain");
   ChainParams cp{c.prm.k, c.prm.bandwidth, c.prm.chain, c.prm.matches, c.prm.gap};
+  const uint32_t* lhs_ids = c.d_ids.get() + first;
   const uint64_t ovl_cap = n_hits / std::max(1u, std::min(c.prm.chain, 4u)) + 16;
   rvn_overlap* raw = c.m_ovl_raw.reserve(ovl_cap);
   uint64_t* loc = c.m_ovl_loc.reserve(nr + 1ULL);
@@ -1116,14 +1119,14 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
         RVN_CUDA(cudaFuncSetAttribute(
             kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
             static_cast<int>(MakeFastLayout(kChainSmemCap).bytes)));
-        kern<<<cnt, 256, smem, c.stream>>>(hg, hp, read_hit_off, first, lst, cp,
+        kern<<<cnt, 256, smem, c.stream>>>(hg, hp, read_hit_off, lhs_ids, lst, cp,
                                            raw, ctr, ovl_cap, loc, d_fb + 2, d_fb);
       } else {
         auto kern = ChainKernelFast<128, 8>;
         RVN_CUDA(cudaFuncSetAttribute(
             kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
             static_cast<int>(MakeFastLayout(2047).bytes)));
-        kern<<<cnt, 128, smem, c.stream>>>(hg, hp, read_hit_off, first, lst, cp,
+        kern<<<cnt, 128, smem, c.stream>>>(hg, hp, read_hit_off, lhs_ids, lst, cp,
                                            raw, ctr, ovl_cap, loc, d_fb + 2, d_fb);
       }
       RVN_LAUNCH_CHECK();
@@ -1171,7 +1174,7 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
                              cudaMemcpyHostToDevice, c.stream));
     ChainKernelGlobal<<<static_cast<unsigned>(big.size()), kThreads, 0,
                         c.stream>>>(
-        hg, hp, read_hit_off, first, d_big, d_off64, d_off32, slab64, slab32, cp,
+        hg, hp, read_hit_off, lhs_ids, d_big, d_off64, d_off32, slab64, slab32, cp,
         raw, reinterpret_cast<unsigned long long*>(counter), ovl_cap, loc);
     RVN_LAUNCH_CHECK();
     ++c.launches;

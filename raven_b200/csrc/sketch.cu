@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(kSketchThreads)
 SketchKernel(const uint64_t* __restrict__ words,
              const uint64_t* __restrict__ woff,
              const uint32_t* __restrict__ lens,
+             const uint32_t* __restrict__ ids,
              const uint64_t* __restrict__ tile_off, uint32_t first_read,
              uint32_t last_read, uint32_t k, uint32_t w,
              uint32_t* __restrict__ tile_cnt,
@@ -155,7 +156,7 @@ SketchKernel(const uint64_t* __restrict__ words,
     return;
   }
   uint64_t dst = tile_out[blockIdx.x] + ex;
-  const uint64_t id = static_cast<uint64_t>(r) << 32;
+  const uint64_t id = static_cast<uint64_t>(ids[r]) << 32;
   while (flags) {
     const uint32_t i = __ffs(flags) - 1;
     flags &= flags - 1;
@@ -291,7 +292,8 @@ void EnsureTiles(Ctx& c) {
     }
     c.h_tile_off[r + 1] = c.h_tile_off[r] + tiles;
   }
-  uint64_t* d = c.d_tile_off.reserve(c.n_reads + 1ULL);
+  // one spare slot: an external query read rides at index n_reads
+  uint64_t* d = c.d_tile_off.reserve(c.n_reads + 2ULL);
   RVN_CUDA(cudaMemcpyAsync(d, c.h_tile_off.data(),
                            (c.n_reads + 1ULL) * sizeof(uint64_t),
                            cudaMemcpyHostToDevice, c.stream));
@@ -319,7 +321,8 @@ void EnsureSketch(Ctx& c, uint32_t first, uint32_t last) {
     uint64_t* tout = c.tile_out.reserve(n_tiles + 1);
     SketchKernel<false><<<static_cast<unsigned>(n_tiles), kSketchThreads, smem,
                           c.stream>>>(c.d_words.get(), c.d_woff.get(),
-                                      c.d_len.get(), c.d_tile_off.get(), first,
+                                      c.d_len.get(), c.d_ids.get(),
+                                      c.d_tile_off.get(), first,
                                       last, c.prm.k, c.prm.w, tcnt, nullptr,
                                       nullptr, nullptr);
     RVN_LAUNCH_CHECK();
@@ -330,7 +333,8 @@ void EnsureSketch(Ctx& c, uint32_t first, uint32_t last) {
     uint64_t* org = c.s_org.reserve(total);
     SketchKernel<true><<<static_cast<unsigned>(n_tiles), kSketchThreads, smem,
                          c.stream>>>(c.d_words.get(), c.d_woff.get(),
-                                     c.d_len.get(), c.d_tile_off.get(), first,
+                                     c.d_len.get(), c.d_ids.get(),
+                                     c.d_tile_off.get(), first,
                                      last, c.prm.k, c.prm.w, nullptr, tout, val,
                                      org);
     RVN_LAUNCH_CHECK();
