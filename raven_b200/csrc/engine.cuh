@@ -91,7 +91,12 @@ struct Ctx {
   DevBuf<uint64_t> m_read_hit_off;  // per query read (+1)
   DevBuf<uint64_t> m_scratch64;     // oversize chain scratch
   DevBuf<uint32_t> m_scratch32, m_fallback;
-  DevBuf<rvn_overlap> m_ovl_raw, m_ovl;
+  // split chain path: pair descriptors, pair-contiguous hits, overlap keys
+  DevBuf<uint32_t> m_desc, m_desc_cnt, m_desc_idx, m_desc_cnt2, m_desc_idx2, m_gdiag,
+      m_oidx, m_oidx2;
+  DevBuf<uint64_t> m_gpos, m_group_loc, m_okey, m_okey2, m_starts;
+  DevBuf<uint32_t> m_bounds;
+  DevBuf<rvn_overlap> m_ovl_raw, m_ovl, m_ovl_tmp;
   DevBuf<uint64_t> m_ovl_loc;  // per read: base<<24 | count  (raw placement)
   DevBuf<uint64_t> m_ovl_off;
   DevBuf<uint64_t> m_counter;

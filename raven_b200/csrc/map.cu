@@ -21,6 +21,8 @@
 // The chain result is a pure function of the MULTISET of hits of a query
 // (both reference sorts are total orders here: equal (group, positions)
 // pairs cannot occur), so hit generation order is free.
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 
 #include "engine.cuh"
@@ -496,46 +498,54 @@ __device__ uint32_t ChainRead(const ChainWork<IdxT>& wk, uint32_t n,
   return total;
 }
 
-constexpr uint32_t kChainSmemCap = 8191;  // hits per read on the smem path
-constexpr uint32_t kChainMaxGroup = 1024;  // larger (rhs, strand) groups -> generic path
+constexpr uint32_t kChainSmemCap = 8191;   // hits per read on the split path
+constexpr uint32_t kChainMaxGroup = 2048;  // larger (rhs, strand) pairs -> generic path
 
 // ---------------------------------------------------------------------------
-// Fast path: one CTA per query read, everything in shared memory.
+// Fast path, two kernels.
 //
 // Bands never span two (rhs_id, strand) pairs (group keys of different pairs
-// differ by >= 2^30 > bandwidth), so the reference's global sort by group is
-// not needed: hits are first split by pair with a shared-memory hash table
-// (pairs with < 4 hits can never form a band and are dropped on the spot),
-// then ONE THREAD PER PAIR orders its few dozen hits by (diagonal, positions)
-// with an insertion sort, walks the reference's window loop, and for every
-// closed band sorts by positions, runs the patience/LIS recurrence, splits at
-// gaps and tests covered bases — all without a barrier. Overlaps are staged
-// in the (by then dead) hash table and written out ordered by (pair, band,
-// walk) = the reference's emission order.
+// differ by >= 2^30 > bandwidth), so the reference's per-query sort by group is
+// not needed.
+//  SplitKernel  one CTA per query read: the read's hits are split by pair with
+//               a shared-memory hash table; pairs with < 4 hits (about half of
+//               all hits: spurious key matches) are dropped on the spot; the
+//               rest is written pair-contiguous to HBM with one descriptor per
+//               pair, pairs of a read in ascending key order (= the reference's
+//               emission order).
+//  GroupChainKernel  ONE THREAD PER PAIR over all pairs of all reads, largest
+//               pairs first (size-sorted, so the lanes of a warp carry similar
+//               work and nothing waits at a barrier): (diagonal, positions)
+//               order by binary insertion, the reference's window loop, per
+//               band the position order, ram's patience/LIS recurrence with
+//               its exact probe sequence, gap split, covered bases. Overlaps go
+//               to a global list keyed (pair index, sequence number) and are
+//               put back in emission order by a radix sort of the keys.
 // ---------------------------------------------------------------------------
-struct FastLayout {
-  uint32_t n, hs, ngmax;
-  size_t p2, d2, hk, hc, gl, goff, gcnt, bytes;
+struct GroupDesc {
+  uint32_t hit_off, cnt, gid, lhs_id;
 };
 
-__host__ __device__ inline FastLayout MakeFastLayout(uint32_t n) {
-  FastLayout L;
-  L.n = n;
-  uint32_t hs = 8;
+struct SplitLayout {
+  uint32_t hs, gpad;
+  size_t hk, hc, gl, bytes;
+};
+
+__host__ __device__ inline SplitLayout MakeSplitLayout(uint32_t n) {
+  SplitLayout L;
+  // open addressing, never full: distinct pairs <= n < hs. (A smaller table
+  // does fill up: a random key match drags in every read covering that locus,
+  // so single-hit pairs are about as many as half the hits.)
+  uint32_t hs = 64;
   while (hs < n + 1) hs <<= 1;
   L.hs = hs;
-  L.ngmax = n / 4 + 1;
-  size_t o = 0;
-  L.p2 = o;   o += 8ULL * n;                 // positions, grouped
-  L.d2 = o;   o += 4ULL * n;                 // diagonals, grouped (later LIS scratch)
-  o = (o + 15) & ~size_t(15);                // staging is read as uint4
-  L.hk = o;   o += 4ULL * hs;                // hash keys      } later: overlap staging
-  L.hc = o;   o += 4ULL * hs;                // hash counters  }   (8*hs bytes)
   uint32_t gpad = 2;
-  while (gpad < L.ngmax) gpad <<= 1;
-  L.gl = o;   o += 8ULL * gpad;              // (gid << 32 | slot), later staging keys
-  L.goff = o; o += 2ULL * L.ngmax;
-  L.gcnt = o; o += 2ULL * L.ngmax;
+  while (gpad < n / 4 + 1) gpad <<= 1;
+  L.gpad = gpad;
+  size_t o = 0;
+  L.hk = o; o += 4ULL * hs;
+  L.hc = o; o += 4ULL * hs;
+  L.gl = o; o += 8ULL * gpad;
   L.bytes = (o + 15) & ~size_t(15);
   return L;
 }
@@ -549,146 +559,39 @@ __device__ __forceinline__ uint32_t HashGid(uint32_t x) {
   return x;
 }
 
-// one band [jb, ie) of a pair: sort by positions, LIS, gap split, emit
-__device__ __forceinline__ void FastBand(uint64_t* P, uint32_t* D, uint32_t jb,
-                                         uint32_t ie, bool strand, uint32_t lhs_id,
-                                         uint32_t rhs_id, const ChainParams& cp,
-                                         uint32_t q, uint32_t* seq,
-                                         rvn_overlap* stage, uint32_t* stage_key,
-                                         uint32_t* stage_cnt) {
-  const uint32_t len = ie - jb;
-  if (len < cp.chain) return;
-  uint64_t* Pb = P + jb;
-  for (uint32_t a = 1; a < len; ++a) {  // insertion sort by positions
-    const uint64_t p = Pb[a];
-    uint32_t b = a;
-    while (b > 0 && Pb[b - 1] > p) {
-      Pb[b] = Pb[b - 1];
-      --b;
-    }
-    Pb[b] = p;
-  }
-  // the band's diagonals are dead: their storage holds minimal[1..len] and
-  // predecessor[0..len) as u16 (minimal[0] is always 0)
-  uint16_t* mini = reinterpret_cast<uint16_t*>(D + jb);  // mini[x-1] = minimal[x]
-  uint16_t* pred = mini + len;
-  uint32_t longest = 0;
-  for (uint32_t t = 0; t < len; ++t) {
-    const uint32_t cl = static_cast<uint32_t>(Pb[t] >> 32);
-    const uint32_t cr = static_cast<uint32_t>(Pb[t]);
-    uint32_t lo = 1, hi = longest;
-    while (lo <= hi) {
-      const uint32_t mid = lo + (hi - lo) / 2;
-      const uint64_t tail = Pb[mini[mid - 1]];
-      const uint32_t tl = static_cast<uint32_t>(tail >> 32);
-      const uint32_t tr = static_cast<uint32_t>(tail);
-      if (tl < cl && (strand ? tr < cr : tr > cr)) {
-        lo = mid + 1;
-      } else {
-        hi = mid - 1;
-      }
-    }
-    pred[t] = lo > 1 ? mini[lo - 2] : 0;
-    mini[lo - 1] = static_cast<uint16_t>(t);
-    longest = max(longest, lo);
-  }
-  if (longest < cp.chain) return;
-  {
-    uint32_t j = mini[longest - 1];
-    for (uint32_t i = 0; i < longest; ++i) {
-      const uint32_t pj = pred[j];
-      mini[longest - 1 - i] = static_cast<uint16_t>(j);
-      j = pj;
-    }
-  }
-  const uint16_t* idx = mini;
-  for (uint32_t kk = 1, l = 0; kk <= longest; ++kk) {
-    const uint32_t prev = static_cast<uint32_t>(Pb[idx[kk - 1]] >> 32);
-    const uint32_t cur =
-        kk < longest ? static_cast<uint32_t>(Pb[idx[kk]] >> 32) : 0xFFFFFFFFu;
-    if (cur - prev > cp.gap) {
-      if (kk - l >= cp.chain) {
-        uint32_t lm = 0, lb_ = 0, le = 0, rm = 0, rb_ = 0, re = 0;
-        for (uint32_t m = l; m < kk; ++m) {
-          const uint64_t pp = Pb[idx[m]];
-          const uint32_t lp = static_cast<uint32_t>(pp >> 32);
-          if (lp > le) {
-            lm += le - lb_;
-            lb_ = lp;
-          }
-          le = lp + cp.k;
-          uint32_t rp = static_cast<uint32_t>(pp);
-          rp = strand ? rp : (1U << 31) - (rp + cp.k - 1);
-          if (rp > re) {
-            rm += re - rb_;
-            rb_ = rp;
-          }
-          re = rp + cp.k;
-        }
-        lm += le - lb_;
-        rm += re - rb_;
-        if (min(lm, rm) >= cp.matches) {
-          const uint64_t pf = Pb[idx[l]], pl = Pb[idx[kk - 1]];
-          rvn_overlap o;
-          o.lhs_id = lhs_id;
-          o.lhs_begin = static_cast<uint32_t>(pf >> 32);
-          o.lhs_end = cp.k + static_cast<uint32_t>(pl >> 32);
-          o.rhs_id = rhs_id;
-          o.rhs_begin = strand ? static_cast<uint32_t>(pf) : static_cast<uint32_t>(pl);
-          o.rhs_end = cp.k + (strand ? static_cast<uint32_t>(pl)
-                                     : static_cast<uint32_t>(pf));
-          o.score = min(lm, rm);
-          o.strand = strand;
-          const uint32_t slot = atomicAdd(stage_cnt, 1u);
-          stage[slot] = o;
-          stage_key[slot] = (q << 16) | (*seq)++;
-        }
-      }
-      l = kk;
-    }
-  }
-}
-
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
-ChainKernelFast(const uint64_t* __restrict__ h_grp,
-                const uint64_t* __restrict__ h_pos,
-                const uint64_t* __restrict__ read_hit_off,
-                const uint32_t* __restrict__ lhs_ids,
-                const uint32_t* __restrict__ read_list, ChainParams cp,
-                rvn_overlap* __restrict__ ovl_raw,
-                unsigned long long* __restrict__ ovl_counter, uint64_t ovl_cap,
-                uint64_t* __restrict__ ovl_loc,
-                uint32_t* __restrict__ fallback_list,
-                unsigned int* __restrict__ fallback_cnt) {
+SplitKernel(const uint64_t* __restrict__ h_grp, const uint64_t* __restrict__ h_pos,
+            const uint64_t* __restrict__ read_hit_off,
+            const uint32_t* __restrict__ lhs_ids,
+            const uint32_t* __restrict__ read_list,
+            unsigned long long* __restrict__ totals,  // [0] pairs, [1] kept hits
+            GroupDesc* __restrict__ desc, uint32_t* __restrict__ desc_cnt,
+            uint32_t* __restrict__ desc_idx, uint32_t* __restrict__ g_diag,
+            uint64_t* __restrict__ g_pos, uint64_t* __restrict__ group_loc,
+            uint32_t* __restrict__ fallback_list,
+            unsigned int* __restrict__ fallback_cnt) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ uint32_t sm32[34];
-  __shared__ uint32_t sh_stage_cnt, sh_bail;
-  __shared__ unsigned long long sh_base;
+  __shared__ uint32_t sh_bail;
+  __shared__ unsigned long long sh_gbase, sh_hbase;
   const uint32_t r = read_list[blockIdx.x];
   const uint64_t hb = read_hit_off[r];
   const uint32_t n = static_cast<uint32_t>(read_hit_off[r + 1] - hb);
-  const FastLayout L = MakeFastLayout(n);
-  uint64_t* P2 = reinterpret_cast<uint64_t*>(smem + L.p2);
-  uint32_t* D2 = reinterpret_cast<uint32_t*>(smem + L.d2);
+  const SplitLayout L = MakeSplitLayout(n);
   uint32_t* HK = reinterpret_cast<uint32_t*>(smem + L.hk);
   uint32_t* HC = reinterpret_cast<uint32_t*>(smem + L.hc);
   uint64_t* GL = reinterpret_cast<uint64_t*>(smem + L.gl);
-  uint16_t* GOFF = reinterpret_cast<uint16_t*>(smem + L.goff);
-  uint16_t* GCNT = reinterpret_cast<uint16_t*>(smem + L.gcnt);
   const uint32_t hmask = L.hs - 1;
   const uint64_t* hg = h_grp + hb;
   const uint64_t* hp = h_pos + hb;
 
-  // ---- 1a. hash table of (rhs_id, strand) pairs with their hit counts ----
+  // ---- hash table of (rhs_id, strand) pairs with their hit counts ----
   for (uint32_t i = threadIdx.x; i < L.hs; i += THREADS) {
     HK[i] = 0xFFFFFFFFu;
     HC[i] = 0;
   }
-  if (threadIdx.x == 0) {
-    sh_stage_cnt = 0;
-    sh_bail = 0;
-  }
+  if (threadIdx.x == 0) sh_bail = 0;
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
     const uint32_t gid = static_cast<uint32_t>(hg[i] >> 32);
@@ -702,8 +605,8 @@ ChainKernelFast(const uint64_t* __restrict__ h_grp,
   }
   __syncthreads();
 
-  // ---- 1b. pairs with >= 4 hits: list + grouped offsets ----
-  uint32_t carry = 0;  // low 16: pairs so far, high 16: hits so far
+  // ---- pairs with >= 4 hits: list + offsets inside the read's kept hits ----
+  uint32_t carry = 0;  // low 16: pairs so far, high 16: kept hits so far
   for (uint32_t b = 0; b < L.hs; b += THREADS) {
     const uint32_t s = b + threadIdx.x;
     const uint32_t cnt = s < L.hs ? HC[s] : 0;
@@ -723,21 +626,25 @@ ChainKernelFast(const uint64_t* __restrict__ h_grp,
     }
     carry += tot;
   }
-  const uint32_t ng = carry & 0xFFFF;
+  const uint32_t ng = carry & 0xFFFF, nh = carry >> 16;
   __syncthreads();
   if (sh_bail) {  // a very large pair: the generic kernel takes this read
     if (threadIdx.x == 0) fallback_list[atomicAdd(fallback_cnt, 1u)] = r;
     return;
   }
   if (ng == 0) {
-    if (threadIdx.x == 0) ovl_loc[r] = 0;
+    if (threadIdx.x == 0) group_loc[r] = 0;
     return;
   }
 
-  // ---- 1c. pairs in ascending key order (= the reference's emission order) ----
+  // ---- pairs in ascending key order; reserve descriptor and hit space ----
   uint32_t gpad = 2;
   while (gpad < ng) gpad <<= 1;
   for (uint32_t i = ng + threadIdx.x; i < gpad; i += THREADS) GL[i] = ~0ULL;
+  if (threadIdx.x == 0) {
+    sh_gbase = atomicAdd(&totals[0], static_cast<unsigned long long>(ng));
+    sh_hbase = atomicAdd(&totals[1], static_cast<unsigned long long>(nh));
+  }
   __syncthreads();
   for (uint32_t size = 2; size <= gpad; size <<= 1) {
     for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
@@ -753,127 +660,306 @@ ChainKernelFast(const uint64_t* __restrict__ h_grp,
       __syncthreads();
     }
   }
+  const uint64_t gbase = sh_gbase, hbase = sh_hbase;
+  const uint32_t lhs_id = lhs_ids[r];
   for (uint32_t q = threadIdx.x; q < ng; q += THREADS) {
-    const uint32_t s = static_cast<uint32_t>(GL[q]);
+    const uint64_t e = GL[q];
+    const uint32_t s = static_cast<uint32_t>(e);
     const uint32_t v = HC[s];
-    GOFF[q] = static_cast<uint16_t>(v & 0xFFFF);
-    GCNT[q] = static_cast<uint16_t>(v >> 16);
+    GroupDesc d;
+    d.hit_off = static_cast<uint32_t>(hbase) + (v & 0xFFFF);
+    d.cnt = v >> 16;
+    d.gid = static_cast<uint32_t>(e >> 32);
+    d.lhs_id = lhs_id;
+    desc[gbase + q] = d;
+    desc_cnt[gbase + q] = d.cnt;
+    desc_idx[gbase + q] = static_cast<uint32_t>(gbase + q);
     HC[s] = v & 0xFFFF;  // fill cursor
   }
+  if (threadIdx.x == 0) group_loc[r] = (gbase << 24) | ng;
   __syncthreads();
 
-  // ---- 1d. scatter the hits of kept pairs (order inside a pair is free) ----
+  // ---- scatter the hits of kept pairs (order inside a pair is free) ----
   for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
     const uint64_t g = hg[i];
     const uint32_t gid = static_cast<uint32_t>(g >> 32);
     uint32_t s = HashGid(gid) & hmask;
     while (HK[s] != gid) s = (s + 1) & hmask;
     if (HC[s] == 0xFFFFFFFFu) continue;
-    const uint32_t at = atomicAdd(&HC[s], 1u);
-    D2[at] = static_cast<uint32_t>(g);
-    P2[at] = hp[i];
+    const uint64_t at = hbase + atomicAdd(&HC[s], 1u);
+    g_diag[at] = static_cast<uint32_t>(g);
+    g_pos[at] = hp[i];
   }
-  __syncthreads();
+}
 
-  // ---- 2. one thread per pair ----
-  rvn_overlap* stage = reinterpret_cast<rvn_overlap*>(smem + L.hk);
-  uint32_t* stage_key = reinterpret_cast<uint32_t*>(smem + L.gl);
-  // GL is dead once every thread has its (gid, offset, count) in registers
-  uint32_t my_gid[(kChainSmemCap / 4 + THREADS) / THREADS];
-  {
-    uint32_t t = 0;
-    for (uint32_t q = threadIdx.x; q < ng; q += THREADS) my_gid[t++] = GL[q] >> 32;
-  }
-  __syncthreads();
-  {
-    uint32_t t = 0;
-    for (uint32_t q = threadIdx.x; q < ng; q += THREADS, ++t) {
-      const uint32_t gid = my_gid[t];
-      const uint32_t off = GOFF[q], m = GCNT[q];
-      uint32_t* D = D2 + off;
-      uint64_t* P = P2 + off;
-      for (uint32_t a = 1; a < m; ++a) {  // insertion sort by (diagonal, positions)
-        const uint32_t d = D[a];
-        const uint64_t p = P[a];
-        uint32_t b = a;
-        while (b > 0 && (D[b - 1] > d || (D[b - 1] == d && P[b - 1] > p))) {
-          D[b] = D[b - 1];
-          P[b] = P[b - 1];
-          --b;
-        }
-        D[b] = d;
-        P[b] = p;
+// A pair's hits live in shared memory, interleaved across the CTA's threads
+// (element i of thread t at [i * T + t]): every thread walks its own column,
+// same-index accesses of a warp are conflict-free, and no barrier is needed.
+struct Column {
+  uint64_t* P;  // positions column (already offset by the thread index)
+  uint32_t* D;  // diagonal column; per band re-used as (minimal, predecessor) u16 pairs
+  uint32_t T;   // column stride = threads per CTA
+  __device__ __forceinline__ uint64_t& p(uint32_t i) const { return P[i * T]; }
+  __device__ __forceinline__ uint32_t& d(uint32_t i) const { return D[i * T]; }
+};
+
+// one band [jb, ie) of a pair: position order, LIS, gap split, emit
+__device__ __forceinline__ void BandChain(const Column& c, uint32_t jb, uint32_t ie,
+                                          bool strand, uint32_t lhs_id,
+                                          uint32_t rhs_id, const ChainParams& cp,
+                                          uint64_t key_hi, uint32_t* seq,
+                                          rvn_overlap* __restrict__ out,
+                                          uint64_t* __restrict__ out_key,
+                                          unsigned long long* __restrict__ out_cnt,
+                                          uint64_t out_cap) {
+  const uint32_t len = ie - jb;
+  if (len < cp.chain) return;
+  for (uint32_t a = 1; a < len; ++a) {  // binary insertion sort by positions
+    const uint64_t pv = c.p(jb + a);
+    if (c.p(jb + a - 1) <= pv) continue;
+    uint32_t lo = 0, hi = a - 1;  // first element > pv lies in [lo, hi]
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (c.p(jb + mid) > pv) {
+        hi = mid;
+      } else {
+        lo = mid + 1;
       }
-      // the reference's window loop; index m plays the stop dummy
-      const bool strand = gid & 1;
-      const uint32_t rhs_id = gid >> 1;
-      uint32_t seq = 0;
-      bool open = false;
-      uint32_t ob = 0, oe = 0;
-      for (uint32_t i = 1, j = 0; i <= m; ++i) {
-        if (i == m || D[i] - D[j] > cp.bandwidth) {
-          if (i - j >= 4) {
-            if (open && oe > j) {
-              oe = i;
-            } else {
-              if (open) {
-                FastBand(P, D, ob, oe, strand, lhs_ids[r], rhs_id, cp, q, &seq,
-                         stage, stage_key, &sh_stage_cnt);
-              }
-              ob = j;
-              oe = i;
-              open = true;
-            }
+    }
+    for (uint32_t b = a; b > lo; --b) c.p(jb + b) = c.p(jb + b - 1);
+    c.p(jb + lo) = pv;
+  }
+  // the band's diagonals are dead: word x of the band now holds
+  // minimal[x + 1] (low half) and predecessor[x] (high half); minimal[0] = 0
+  auto mini_get = [&](uint32_t x) -> uint32_t { return c.d(jb + x) & 0xFFFFu; };
+  auto mini_set = [&](uint32_t x, uint32_t v) {
+    c.d(jb + x) = (c.d(jb + x) & 0xFFFF0000u) | v;
+  };
+  auto pred_get = [&](uint32_t x) -> uint32_t { return c.d(jb + x) >> 16; };
+  auto pred_set = [&](uint32_t x, uint32_t v) {
+    c.d(jb + x) = (c.d(jb + x) & 0xFFFFu) | (v << 16);
+  };
+  uint32_t longest = 0;
+  for (uint32_t t = 0; t < len; ++t) {
+    const uint64_t cur = c.p(jb + t);
+    const uint32_t cl = static_cast<uint32_t>(cur >> 32);
+    const uint32_t cr = static_cast<uint32_t>(cur);
+    uint32_t lo = 1, hi = longest;
+    while (lo <= hi) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      const uint64_t tail = c.p(jb + mini_get(mid - 1));
+      const uint32_t tl = static_cast<uint32_t>(tail >> 32);
+      const uint32_t tr = static_cast<uint32_t>(tail);
+      if (tl < cl && (strand ? tr < cr : tr > cr)) {
+        lo = mid + 1;
+      } else {
+        hi = mid - 1;
+      }
+    }
+    pred_set(t, lo > 1 ? mini_get(lo - 2) : 0u);
+    mini_set(lo - 1, t);
+    longest = max(longest, lo);
+  }
+  if (longest < cp.chain) return;
+  {
+    uint32_t j = mini_get(longest - 1);
+    for (uint32_t i = 0; i < longest; ++i) {
+      const uint32_t pj = pred_get(j);
+      mini_set(longest - 1 - i, j);
+      j = pj;
+    }
+  }
+  for (uint32_t kk = 1, l = 0; kk <= longest; ++kk) {
+    const uint32_t prev = static_cast<uint32_t>(c.p(jb + mini_get(kk - 1)) >> 32);
+    const uint32_t cur = kk < longest
+                             ? static_cast<uint32_t>(c.p(jb + mini_get(kk)) >> 32)
+                             : 0xFFFFFFFFu;
+    if (cur - prev > cp.gap) {
+      if (kk - l >= cp.chain) {
+        uint32_t lm = 0, lb_ = 0, le = 0, rm = 0, rb_ = 0, re = 0;
+        for (uint32_t m = l; m < kk; ++m) {
+          const uint64_t pp = c.p(jb + mini_get(m));
+          const uint32_t lp = static_cast<uint32_t>(pp >> 32);
+          if (lp > le) {
+            lm += le - lb_;
+            lb_ = lp;
           }
-          ++j;
-          while (j < i && (i == m || D[i] - D[j] > cp.bandwidth)) ++j;
+          le = lp + cp.k;
+          uint32_t rp = static_cast<uint32_t>(pp);
+          rp = strand ? rp : (1U << 31) - (rp + cp.k - 1);
+          if (rp > re) {
+            rm += re - rb_;
+            rb_ = rp;
+          }
+          re = rp + cp.k;
+        }
+        lm += le - lb_;
+        rm += re - rb_;
+        if (min(lm, rm) >= cp.matches) {
+          const uint64_t pf = c.p(jb + mini_get(l)), pl = c.p(jb + mini_get(kk - 1));
+          rvn_overlap o;
+          o.lhs_id = lhs_id;
+          o.lhs_begin = static_cast<uint32_t>(pf >> 32);
+          o.lhs_end = cp.k + static_cast<uint32_t>(pl >> 32);
+          o.rhs_id = rhs_id;
+          o.rhs_begin = strand ? static_cast<uint32_t>(pf) : static_cast<uint32_t>(pl);
+          o.rhs_end = cp.k + (strand ? static_cast<uint32_t>(pl)
+                                     : static_cast<uint32_t>(pf));
+          o.score = min(lm, rm);
+          o.strand = strand;
+          const unsigned long long slot = atomicAdd(out_cnt, 1ULL);
+          if (slot < out_cap) {
+            out[slot] = o;
+            out_key[slot] = key_hi | (*seq)++;
+          }
         }
       }
-      if (open) {
-        FastBand(P, D, ob, oe, strand, lhs_ids[r], rhs_id, cp, q, &seq, stage,
-                 stage_key, &sh_stage_cnt);
-      }
+      l = kk;
     }
   }
-  __syncthreads();
+}
 
-  // ---- 3. emission order, reserved slab, write ----
-  const uint32_t total = sh_stage_cnt;
-  if (threadIdx.x == 0) {
-    sh_base = total ? atomicAdd(ovl_counter, static_cast<unsigned long long>(total))
-                    : 0ULL;
-    ovl_loc[r] = total ? (static_cast<uint64_t>(sh_base) << 24) | total : 0;
+// thread t of the launch handles pair order[first + t]; every pair of this
+// launch has at most m_cap hits (the launch is one size class)
+__global__ void GroupChainKernel(const GroupDesc* __restrict__ desc,
+                                 const uint32_t* __restrict__ order, uint64_t first,
+                                 uint64_t last, uint32_t m_cap,
+                                 const uint32_t* __restrict__ g_diag,
+                                 const uint64_t* __restrict__ g_pos, ChainParams cp,
+                                 rvn_overlap* __restrict__ out,
+                                 uint64_t* __restrict__ out_key,
+                                 unsigned long long* __restrict__ out_cnt,
+                                 uint64_t out_cap) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const uint32_t T = blockDim.x;
+  const uint64_t t = first + static_cast<uint64_t>(blockIdx.x) * T + threadIdx.x;
+  if (t >= last) return;
+  Column c;
+  c.P = reinterpret_cast<uint64_t*>(smem) + threadIdx.x;
+  c.D = reinterpret_cast<uint32_t*>(smem + 8ULL * m_cap * T) + threadIdx.x;
+  c.T = T;
+  const uint32_t g = order[t];
+  const GroupDesc d = desc[g];
+  const uint32_t m = d.cnt;
+  for (uint32_t i = 0; i < m; ++i) {
+    c.p(i) = g_pos[d.hit_off + i];
+    c.d(i) = g_diag[d.hit_off + i];
   }
-  if (total == 0) return;
-  uint64_t* order = P2;  // dead: (key << 32 | staging slot)
-  uint32_t opad = 2;
-  while (opad < total) opad <<= 1;
-  for (uint32_t i = threadIdx.x; i < opad; i += THREADS) {
-    order[i] = i < total ? (static_cast<uint64_t>(stage_key[i]) << 32) | i : ~0ULL;
+  for (uint32_t a = 1; a < m; ++a) {  // binary insertion by (diagonal, positions)
+    const uint32_t dv = c.d(a);
+    const uint64_t pv = c.p(a);
+    uint32_t lo = 0, hi = a;  // first element > (dv, pv) lies in [lo, hi]
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      const uint32_t dm = c.d(mid);
+      if (dm > dv || (dm == dv && c.p(mid) > pv)) {
+        hi = mid;
+      } else {
+        lo = mid + 1;
+      }
+    }
+    for (uint32_t b = a; b > lo; --b) {
+      c.d(b) = c.d(b - 1);
+      c.p(b) = c.p(b - 1);
+    }
+    c.d(lo) = dv;
+    c.p(lo) = pv;
   }
-  __syncthreads();
-  for (uint32_t size = 2; size <= opad; size <<= 1) {
-    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-      for (uint32_t t = threadIdx.x; t < (opad >> 1); t += THREADS) {
-        const uint32_t i = 2 * t - (t & (stride - 1));
-        const uint32_t j = i + stride;
-        const uint64_t a = order[i], c2 = order[j];
-        if ((a > c2) == ((i & size) == 0)) {
-          order[i] = c2;
-          order[j] = a;
+  // the reference's window loop; index m plays the stop dummy
+  const bool strand = d.gid & 1;
+  const uint32_t rhs_id = d.gid >> 1;
+  const uint64_t key_hi = static_cast<uint64_t>(g) << 16;
+  uint32_t seq = 0;
+  bool open = false;
+  uint32_t ob = 0, oe = 0;
+  for (uint32_t i = 1, j = 0; i <= m; ++i) {
+    if (i == m || c.d(i) - c.d(j) > cp.bandwidth) {
+      if (i - j >= 4) {
+        if (open && oe > j) {
+          oe = i;
+        } else {
+          if (open) {
+            BandChain(c, ob, oe, strand, d.lhs_id, rhs_id, cp, key_hi, &seq, out,
+                      out_key, out_cnt, out_cap);
+          }
+          ob = j;
+          oe = i;
+          open = true;
         }
       }
-      __syncthreads();
+      ++j;
+      while (j < i && (i == m || c.d(i) - c.d(j) > cp.bandwidth)) ++j;
     }
   }
-  const uint64_t base = sh_base;
-  if (base + total > ovl_cap) return;  // host reports the overflow
-  const uint4* src = reinterpret_cast<const uint4*>(stage);
-  uint4* dst = reinterpret_cast<uint4*>(ovl_raw + base);
-  for (uint32_t i = threadIdx.x; i < total * 2; i += THREADS) {
-    const uint32_t from = static_cast<uint32_t>(order[i >> 1]);
-    dst[i] = src[from * 2 + (i & 1)];
+  if (open) {
+    BandChain(c, ob, oe, strand, d.lhs_id, rhs_id, cp, key_hi, &seq, out, out_key,
+              out_cnt, out_cap);
   }
+}
+
+// first index of a descending-sorted count array with count <= bound[i]
+__global__ void SizeClassStarts(const uint32_t* __restrict__ sorted_cnt, uint64_t n,
+                                const uint32_t* __restrict__ bound, uint32_t n_bounds,
+                                uint64_t* __restrict__ start) {
+  const uint32_t i = threadIdx.x;
+  if (i >= n_bounds) return;
+  const uint32_t bnd = bound[i];
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint64_t mid = lo + (hi - lo) / 2;
+    if (sorted_cnt[mid] > bnd) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+    }
+  }
+  start[i] = lo;
+}
+
+__global__ void IotaU32(uint32_t* __restrict__ out, uint64_t n) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = static_cast<uint32_t>(i);
+}
+
+__global__ void GatherOverlapsByIndex(const rvn_overlap* __restrict__ src,
+                                      const uint32_t* __restrict__ idx, uint64_t n,
+                                      rvn_overlap* __restrict__ dst) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n * 2) return;
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  reinterpret_cast<uint4*>(dst)[i] = s[static_cast<uint64_t>(idx[i >> 1]) * 2 + (i & 1)];
+}
+
+// per listed read: where its overlaps sit in the key-sorted list
+__global__ void LocateReadOverlaps(const uint64_t* __restrict__ sorted_key,
+                                   uint64_t n_keys,
+                                   const uint32_t* __restrict__ read_list,
+                                   uint32_t n_list,
+                                   const uint64_t* __restrict__ group_loc,
+                                   uint64_t base0, uint64_t* __restrict__ ovl_loc) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_list) return;
+  const uint32_t r = read_list[i];
+  const uint64_t gl = group_loc[r];
+  const uint64_t gbase = gl >> 24, ng = gl & 0xFFFFFF;
+  if (ng == 0) {
+    ovl_loc[r] = 0;
+    return;
+  }
+  auto lower = [&](uint64_t key) {
+    uint64_t lo = 0, hi = n_keys;
+    while (lo < hi) {
+      const uint64_t mid = lo + (hi - lo) / 2;
+      if (sorted_key[mid] < key) {
+        lo = mid + 1;
+      } else {
+        hi = mid;
+      }
+    }
+    return lo;
+  };
+  const uint64_t a = lower(gbase << 16), b = lower((gbase + ng) << 16);
+  ovl_loc[r] = b > a ? ((base0 + a) << 24) | (b - a) : 0;
 }
 
 // global-memory path for reads with more hits than shared memory holds: one
@@ -1074,11 +1160,12 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
   RVN_CUDA(cudaMemsetAsync(counter, 0, sizeof(uint64_t), c.stream));
   RVN_CUDA(cudaMemsetAsync(loc, 0, (nr + 1ULL) * sizeof(uint64_t), c.stream));
 
-  // size classes by hit count (n + 1 <= 256 << k), then the generic path
-  constexpr int kClasses = 6;
+  // ---- fast path: split by (rhs, strand) pair, then one thread per pair ----
+  static const uint32_t kBounds[] = {256, 512, 1024, 2048, 4096, 8192};
+  constexpr int kClasses = sizeof(kBounds) / sizeof(kBounds[0]);
   std::vector<uint32_t> cls[kClasses];
   std::vector<uint32_t> big;
-  const bool fast_ok = c.prm.chain >= 4;  // staging capacity argument (n / 4)
+  const bool fast_ok = c.prm.chain >= 1;
   for (uint32_t i = 0; i < nr; ++i) {
     const uint64_t n = h_rho[i + 1] - h_rho[i];
     if (n < 4) continue;  // cannot form a band; ovl_loc stays 0
@@ -1087,9 +1174,10 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
       continue;
     }
     int k = 0;
-    while ((256u << k) < n + 1) ++k;
+    while (kBounds[k] < n + 1) ++k;
     cls[k].push_back(i);
   }
+  uint64_t n_fast_ovl = 0;
   {
     size_t total = 0;
     for (auto& v : cls) total += v.size();
@@ -1105,39 +1193,55 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
       RVN_CUDA(cudaMemcpyAsync(d_list, flat.data(), total * sizeof(uint32_t),
                                cudaMemcpyHostToDevice, c.stream));
       RVN_CUDA(cudaStreamSynchronize(c.stream));  // flat goes out of scope
-    }
-    size_t off = 0;
-    auto* ctr = reinterpret_cast<unsigned long long*>(counter);
-    for (int k = kClasses - 1; k >= 0; --k) {  // largest class first
-      const unsigned cnt = static_cast<unsigned>(cls[k].size());
-      if (cnt == 0) continue;
-      const size_t smem = MakeFastLayout((256u << k) - 1).bytes;
-      const uint32_t* lst = d_list + off;
-      off += cnt;
-      if (k >= 3) {
-        auto kern = ChainKernelFast<256, 2>;
-        RVN_CUDA(cudaFuncSetAttribute(
-            kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            static_cast<int>(MakeFastLayout(kChainSmemCap).bytes)));
-        kern<<<cnt, 256, smem, c.stream>>>(hg, hp, read_hit_off, lhs_ids, lst, cp,
-                                           raw, ctr, ovl_cap, loc, d_fb + 2, d_fb);
-      } else {
-        auto kern = ChainKernelFast<128, 8>;
-        RVN_CUDA(cudaFuncSetAttribute(
-            kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            static_cast<int>(MakeFastLayout(2047).bytes)));
-        kern<<<cnt, 128, smem, c.stream>>>(hg, hp, read_hit_off, lhs_ids, lst, cp,
-                                           raw, ctr, ovl_cap, loc, d_fb + 2, d_fb);
+
+      const uint64_t max_groups = n_hits / 4 + 1;
+      GroupDesc* desc = reinterpret_cast<GroupDesc*>(
+          c.m_desc.reserve(max_groups * (sizeof(GroupDesc) / 4)));
+      uint32_t* dcnt = c.m_desc_cnt.reserve(max_groups);
+      uint32_t* didx = c.m_desc_idx.reserve(max_groups);
+      uint32_t* dcnt2 = c.m_desc_cnt2.reserve(max_groups);
+      uint32_t* didx2 = c.m_desc_idx2.reserve(max_groups);
+      uint32_t* g_diag = c.m_gdiag.reserve(n_hits + 1);
+      uint64_t* g_pos = c.m_gpos.reserve(n_hits + 1);
+      uint64_t* group_loc = c.m_group_loc.reserve(nr + 1ULL);
+      // counters: [0] overlaps (generic path), [1] pairs, [2] kept hits,
+      // [3] overlaps of the fast path
+      RVN_CUDA(cudaMemsetAsync(counter, 0, 4 * sizeof(uint64_t), c.stream));
+      auto* ctr = reinterpret_cast<unsigned long long*>(counter);
+
+      size_t off = 0;
+      for (int k = kClasses - 1; k >= 0; --k) {  // largest class first
+        const unsigned cnt = static_cast<unsigned>(cls[k].size());
+        if (cnt == 0) continue;
+        const size_t smem = MakeSplitLayout(kBounds[k] - 1).bytes;
+        const uint32_t* lst = d_list + off;
+        off += cnt;
+        if (kBounds[k] > 2048) {
+          auto kern = SplitKernel<256, 2>;
+          RVN_CUDA(cudaFuncSetAttribute(
+              kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+              static_cast<int>(MakeSplitLayout(kChainSmemCap).bytes)));
+          kern<<<cnt, 256, smem, c.stream>>>(hg, hp, read_hit_off, lhs_ids, lst,
+                                             ctr + 1, desc, dcnt, didx, g_diag, g_pos,
+                                             group_loc, d_fb + 2, d_fb);
+        } else {
+          auto kern = SplitKernel<128, 8>;
+          kern<<<cnt, 128, smem, c.stream>>>(hg, hp, read_hit_off, lhs_ids, lst,
+                                             ctr + 1, desc, dcnt, didx, g_diag, g_pos,
+                                             group_loc, d_fb + 2, d_fb);
+        }
+        RVN_LAUNCH_CHECK();
+        ++c.launches;
       }
-      RVN_LAUNCH_CHECK();
-      ++c.launches;
-    }
-    if (total) {
-      // reads the fast kernel handed back (a pair with > kChainMaxGroup hits)
-      std::vector<uint32_t> fb(1);
-      RVN_CUDA(cudaMemcpyAsync(fb.data(), d_fb, sizeof(uint32_t),
+      // pair count, reads handed back (a pair with > kChainMaxGroup hits)
+      uint64_t* hpin = c.pin64.reserve(8);
+      RVN_CUDA(cudaMemcpyAsync(hpin, counter, 4 * sizeof(uint64_t),
+                               cudaMemcpyDeviceToHost, c.stream));
+      std::vector<uint32_t> fb(2);
+      RVN_CUDA(cudaMemcpyAsync(fb.data(), d_fb, 2 * sizeof(uint32_t),
                                cudaMemcpyDeviceToHost, c.stream));
       RVN_CUDA(cudaStreamSynchronize(c.stream));
+      const uint64_t n_groups = hpin[1];
       const uint32_t nfb = fb[0];
       if (nfb) {
         fb.resize(nfb);
@@ -1147,6 +1251,82 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
         std::sort(fb.begin(), fb.end());
         big.insert(big.end(), fb.begin(), fb.end());
       }
+      if (n_groups >= 0xFFFFFFFFULL) throw LimitError("2^32 or more seed pairs");
+
+      if (n_groups) {
+        // largest pairs first: lanes of a warp get pairs of similar size
+        cub::DoubleBuffer<uint32_t> kk(dcnt, dcnt2), vv(didx, didx2);
+        size_t tmp_bytes = 0;
+        RVN_CUDA(cub::DeviceRadixSort::SortPairsDescending(
+            nullptr, tmp_bytes, kk, vv, n_groups, 0, 12, c.stream));
+        void* tmp = c.sort_tmp.reserve(tmp_bytes + 16);
+        RVN_CUDA(cub::DeviceRadixSort::SortPairsDescending(
+            tmp, tmp_bytes, kk, vv, n_groups, 0, 12, c.stream));
+        rvn_overlap* tmp_ovl = c.m_ovl_tmp.reserve(ovl_cap);
+        uint64_t* key = c.m_okey.reserve(ovl_cap);
+        uint64_t* key2 = c.m_okey2.reserve(ovl_cap);
+        uint32_t* oidx = c.m_oidx.reserve(ovl_cap);
+        uint32_t* oidx2 = c.m_oidx2.reserve(ovl_cap);
+        // one launch per size class of the (descending) pair order: shared
+        // memory per CTA = threads x class bound x 12 B
+        static const uint32_t kGB[] = {2048, 1024, 512, 256, 128, 96, 64, 48, 32, 24, 16, 8};
+        constexpr uint32_t kNB = sizeof(kGB) / sizeof(kGB[0]);
+        uint32_t* d_bounds = c.m_bounds.reserve(kNB);
+        uint64_t* d_starts = c.m_starts.reserve(kNB + 1);
+        RVN_CUDA(cudaMemcpyAsync(d_bounds, kGB, sizeof(kGB), cudaMemcpyHostToDevice,
+                                 c.stream));
+        SizeClassStarts<<<1, 32, 0, c.stream>>>(kk.Current(), n_groups, d_bounds, kNB,
+                                                d_starts);
+        uint64_t h_starts[kNB + 1];
+        RVN_CUDA(cudaMemcpyAsync(h_starts, d_starts, kNB * sizeof(uint64_t),
+                                 cudaMemcpyDeviceToHost, c.stream));
+        RVN_CUDA(cudaStreamSynchronize(c.stream));
+        h_starts[kNB] = n_groups;
+        RVN_CUDA(cudaFuncSetAttribute(GroupChainKernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      200 * 1024));
+        for (uint32_t b = 0; b < kNB; ++b) {
+          // pairs with bound[b+1] < count <= bound[b]  (class 0 starts at index 0)
+          const uint64_t lo = b == 0 ? 0 : h_starts[b], hi = h_starts[b + 1];
+          if (hi <= lo) continue;
+          uint32_t threads = 128;
+          while (threads > 8 && 12ULL * kGB[b] * threads > 196 * 1024) threads >>= 1;
+          const size_t smem = 12ULL * kGB[b] * threads;
+          GroupChainKernel<<<CeilDiv(hi - lo, threads), threads, smem, c.stream>>>(
+              desc, vv.Current(), lo, hi, kGB[b], g_diag, g_pos, cp, tmp_ovl, key,
+              ctr + 3, ovl_cap);
+          RVN_LAUNCH_CHECK();
+          ++c.launches;
+        }
+        n_fast_ovl = ReadU64(c, counter + 3);
+        if (n_fast_ovl > ovl_cap) throw LimitError("overlap slab overflow");
+        if (n_fast_ovl >= 0xFFFFFFFFULL) throw LimitError("2^32 or more overlaps");
+        if (n_fast_ovl) {
+          // emission order = (pair index, sequence number)
+          IotaU32<<<CeilDiv(n_fast_ovl, kThreads), kThreads, 0, c.stream>>>(
+              oidx, n_fast_ovl);
+          int key_bits = 17;
+          while (key_bits < 64 && (1ULL << (key_bits - 16)) < n_groups) ++key_bits;
+          cub::DoubleBuffer<uint64_t> ok(key, key2);
+          cub::DoubleBuffer<uint32_t> ov(oidx, oidx2);
+          RVN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ok, ov,
+                                                   n_fast_ovl, 0, key_bits, c.stream));
+          tmp = c.sort_tmp.reserve(tmp_bytes + 16);
+          RVN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, ok, ov, n_fast_ovl,
+                                                   0, key_bits, c.stream));
+          GatherOverlapsByIndex<<<CeilDiv(n_fast_ovl * 2, kThreads), kThreads, 0,
+                                  c.stream>>>(tmp_ovl, ov.Current(), n_fast_ovl, raw);
+          LocateReadOverlaps<<<CeilDiv(total, kThreads), kThreads, 0, c.stream>>>(
+              ok.Current(), n_fast_ovl, d_list, static_cast<uint32_t>(total),
+              group_loc, 0, loc);
+          RVN_LAUNCH_CHECK();
+          c.launches += 3;
+        }
+      }
+      // the generic kernel appends behind the fast path's overlaps
+      RVN_CUDA(cudaMemcpyAsync(counter, &n_fast_ovl, sizeof(uint64_t),
+                               cudaMemcpyHostToDevice, c.stream));
+      RVN_CUDA(cudaStreamSynchronize(c.stream));
     }
   }
   if (!big.empty()) {
