@@ -63,7 +63,7 @@ struct Ctx {
   DevBuf<uint64_t> s_val, s_org, s_off;  // s_off: (s_last-s_first)+1
   std::vector<uint64_t> h_s_off;
   DevBuf<uint32_t> tile_cnt;
-  DevBuf<uint64_t> tile_out;
+  DevBuf<uint64_t> tile_out, tile_status;
 
   // ---- current micromizer set (of reads [q_first, q_last)) ----
   bool q_valid = false;

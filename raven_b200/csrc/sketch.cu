@@ -16,6 +16,8 @@
 // One CTA sketches kSketchTile positions of one read (+ w-1 halo each side).
 // Pass 1 counts, a device scan places tiles, pass 2 writes (value, origin)
 // records in (read, position) order — the order the index build relies on.
+#include <algorithm>
+
 #include "engine.cuh"
 
 namespace rvn {
@@ -56,7 +58,34 @@ __device__ __forceinline__ uint32_t FindRead(const uint64_t* __restrict__ tile_o
   return lo;
 }
 
-template <bool WRITE>
+__device__ __forceinline__ uint32_t MixHash32(uint32_t key, uint32_t mask) {
+  // the same mix on 32-bit registers; exact for 2k <= 30 bits because every
+  // step is masked to 2k bits and wrap-around above bit 31 never reaches them
+  key = ((~key) + (key << 21)) & mask;
+  key = key ^ (key >> 24);
+  key = ((key + (key << 3)) + (key << 8)) & mask;
+  key = key ^ (key >> 14);
+  key = ((key + (key << 2)) + (key << 4)) & mask;
+  key = key ^ (key >> 28);
+  // (key << 31) has no bit below 31: the last step is the identity here
+  return key & mask;
+}
+
+__device__ __forceinline__ uint32_t ReverseGroups32(uint32_t x) {
+  x = __brev(x);
+  return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+}
+
+// decoupled look-back status word: state in the top two bits
+constexpr uint64_t kStAggregate = 1ULL << 62;
+constexpr uint64_t kStPrefix = 2ULL << 62;
+constexpr uint64_t kStMask = 3ULL << 62;
+
+// Single pass: every CTA takes the next tile (ticket), selects its minimizers
+// and obtains its output offset from the running prefix of the tiles before it
+// (decoupled look-back on a status array), so records land in (read,
+// position) order without a counting pass. HashT = u32 when 2k <= 30.
+template <typename HashT>
 __global__ void __launch_bounds__(kSketchThreads)
 SketchKernel(const uint64_t* __restrict__ words,
              const uint64_t* __restrict__ woff,
@@ -64,33 +93,37 @@ SketchKernel(const uint64_t* __restrict__ words,
              const uint32_t* __restrict__ ids,
              const uint64_t* __restrict__ tile_off, uint32_t first_read,
              uint32_t last_read, uint32_t k, uint32_t w,
-             uint32_t* __restrict__ tile_cnt,
-             const uint64_t* __restrict__ tile_out,
+             unsigned int* __restrict__ ticket, uint64_t* __restrict__ status,
+             uint64_t* __restrict__ tile_out, uint64_t n_tiles, uint64_t out_cap,
              uint64_t* __restrict__ out_val, uint64_t* __restrict__ out_org) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: hash values | strand bytes | packed words | scan scratch
+  constexpr HashT kBad = static_cast<HashT>(~static_cast<HashT>(0));
   const uint32_t halo = w - 1;
   const uint32_t span = kSketchTile + 2 * halo;
-  uint64_t* sh_hash = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* sh_words = sh_hash + span;
+  // layout: packed words | hash values | scan scratch | strand bytes
   const uint32_t max_words = (span + 31 + 31) / 32 + 2;
-  uint32_t* sh_scan = reinterpret_cast<uint32_t*>(sh_words + max_words);
+  uint64_t* sh_words = reinterpret_cast<uint64_t*>(smem_raw);
+  HashT* sh_hash = reinterpret_cast<HashT*>(sh_words + max_words);
+  uint32_t* sh_scan = reinterpret_cast<uint32_t*>(
+      (reinterpret_cast<uintptr_t>(sh_hash + span) + 3) & ~uintptr_t(3));
   unsigned char* sh_strand = reinterpret_cast<unsigned char*>(sh_scan + 34);
-  __shared__ uint32_t sh_read;
+  __shared__ uint32_t sh_read, sh_tile;
+  __shared__ uint64_t sh_excl;
 
-  const uint64_t tile0 = tile_off[first_read];
-  const uint64_t t = tile0 + blockIdx.x;
   if (threadIdx.x == 0) {
-    sh_read = FindRead(tile_off, first_read, last_read, t);
+    const uint32_t tk = atomicAdd(ticket, 1u);
+    sh_tile = tk;
+    sh_read = FindRead(tile_off, first_read, last_read, tile_off[first_read] + tk);
   }
   __syncthreads();
+  const uint32_t tile = sh_tile;
+  const uint64_t t = tile_off[first_read] + tile;
   const uint32_t r = sh_read;
   const uint32_t len = lens[r];
   const uint32_t L = len - k + 1;  // k-mer positions (tiles exist only if L >= w)
   const uint32_t q0 = static_cast<uint32_t>(t - tile_off[r]) * kSketchTile;
   const uint32_t q1 = min(q0 + kSketchTile, L);
-  // hashed range incl. halo
-  const uint32_t hs = q0 >= halo ? q0 - halo : 0;
+  const uint32_t hs = q0 >= halo ? q0 - halo : 0;  // hashed range incl. halo
   const uint32_t he = min(q1 + halo, L);
 
   // ---- stage the packed words this tile touches ----
@@ -104,22 +137,35 @@ SketchKernel(const uint64_t* __restrict__ words,
   __syncthreads();
 
   // ---- canonical k-mer hash of every position in [hs, he) ----
-  const uint64_t mask = (1ULL << (2 * k)) - 1;
   for (uint32_t p = hs + threadIdx.x; p < he; p += kSketchThreads) {
     const uint32_t wi = (p >> 5) - w_lo;
     const uint32_t sh = (p & 31) << 1;
     uint64_t lo = sh_words[wi] >> sh;
     if (sh) lo |= sh_words[wi + 1] << (64 - sh);
-    lo &= mask;
-    const uint64_t rv = (~lo) & mask;
-    const uint64_t fw = ReverseGroups(lo) >> (64 - 2 * k);
-    uint64_t h = kInvalid;  // palindromic k-mers never enter a window
+    HashT h = kBad;  // palindromic k-mers never enter a window
     unsigned char strand = 0;
-    if (fw < rv) {
-      h = MixHash(fw, mask);
-    } else if (fw > rv) {
-      h = MixHash(rv, mask);
-      strand = 1;
+    if (sizeof(HashT) == 4) {
+      const uint32_t mask = (1u << (2 * k)) - 1;
+      const uint32_t l32 = static_cast<uint32_t>(lo) & mask;
+      const uint32_t rv = (~l32) & mask;
+      const uint32_t fw = ReverseGroups32(l32) >> (32 - 2 * k);
+      if (fw < rv) {
+        h = static_cast<HashT>(MixHash32(fw, mask));
+      } else if (fw > rv) {
+        h = static_cast<HashT>(MixHash32(rv, mask));
+        strand = 1;
+      }
+    } else {
+      const uint64_t mask = (1ULL << (2 * k)) - 1;
+      lo &= mask;
+      const uint64_t rv = (~lo) & mask;
+      const uint64_t fw = ReverseGroups(lo) >> (64 - 2 * k);
+      if (fw < rv) {
+        h = static_cast<HashT>(MixHash(fw, mask));
+      } else if (fw > rv) {
+        h = static_cast<HashT>(MixHash(rv, mask));
+        strand = 1;
+      }
     }
     sh_hash[p - hs] = h;
     sh_strand[p - hs] = strand;
@@ -134,8 +180,8 @@ SketchKernel(const uint64_t* __restrict__ words,
   for (uint32_t i = 0; i < ITEMS; ++i) {
     const uint32_t q = qa + i;
     if (q >= q1) break;
-    const uint64_t h = sh_hash[q - hs];
-    if (h == kInvalid) continue;
+    const HashT h = sh_hash[q - hs];
+    if (h == kBad) continue;
     // consecutive left neighbours with hash >= h (capped)
     const uint32_t lcap = min(halo, q);
     uint32_t ra = 0;
@@ -151,18 +197,41 @@ SketchKernel(const uint64_t* __restrict__ words,
   uint32_t total;
   const uint32_t ex = BlockExclusiveSum<uint32_t, kSketchThreads>(
       __popc(flags), sh_scan, &total);
-  if (!WRITE) {
-    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
-    return;
+
+  // ---- output offset: running prefix of the tiles before this one ----
+  if (threadIdx.x == 0) {
+    uint64_t excl = 0;
+    volatile uint64_t* st = status;
+    if (tile > 0) {
+      st[tile] = kStAggregate | total;
+      __threadfence();
+      uint64_t idx = tile;
+      while (idx > 0) {
+        --idx;
+        uint64_t v;
+        do {
+          v = st[idx];
+        } while ((v & kStMask) == 0);
+        excl += v & ~kStMask;
+        if ((v & kStMask) == kStPrefix) break;
+      }
+    }
+    st[tile] = kStPrefix | (excl + total);
+    tile_out[tile] = excl;
+    if (tile + 1 == n_tiles) tile_out[n_tiles] = excl + total;
+    sh_excl = excl;
   }
-  uint64_t dst = tile_out[blockIdx.x] + ex;
+  __syncthreads();
+  uint64_t dst = sh_excl + ex;
   const uint64_t id = static_cast<uint64_t>(ids[r]) << 32;
   while (flags) {
     const uint32_t i = __ffs(flags) - 1;
     flags &= flags - 1;
     const uint32_t q = qa + i;
-    out_val[dst] = sh_hash[q - hs];
-    out_org[dst] = id | (static_cast<uint64_t>(q) << 1) | sh_strand[q - hs];
+    if (dst < out_cap) {
+      out_val[dst] = static_cast<uint64_t>(sh_hash[q - hs]);
+      out_org[dst] = id | (static_cast<uint64_t>(q) << 1) | sh_strand[q - hs];
+    }
     ++dst;
   }
 }
@@ -271,11 +340,11 @@ MicromizeKernel(const uint64_t* __restrict__ s_val,
   }
 }
 
-size_t SketchSmemBytes(uint32_t w) {
+size_t SketchSmemBytes(uint32_t w, size_t hash_bytes) {
   const uint32_t halo = w - 1;
   const uint32_t span = kSketchTile + 2 * halo;
   const uint32_t max_words = (span + 31 + 31) / 32 + 2;
-  return span * 8 + max_words * 8 + 34 * 4 + span + 16;
+  return max_words * 8 + span * hash_bytes + 4 + 34 * 4 + span + 16;
 }
 
 }  // namespace
@@ -316,29 +385,45 @@ void EnsureSketch(Ctx& c, uint32_t first, uint32_t last) {
   uint64_t total = 0;
   if (n_tiles > 0) {
     TimerBegin(c, "sketch");
-    const size_t smem = SketchSmemBytes(c.prm.w);
-    uint32_t* tcnt = c.tile_cnt.reserve(n_tiles);
+    const bool k32 = 2 * c.prm.k <= 30;
+    const size_t smem = SketchSmemBytes(c.prm.w, k32 ? 4 : 8);
+    // status words + ticket; output capacity from the expected density (all
+    // ties of a window minimum are emitted, so a repetitive read can exceed it:
+    // the kernel then only counts and the pass is repeated with the exact size)
+    uint64_t positions = 0;
+    for (uint32_t r = first; r < last; ++r) {
+      if (c.h_len[r] >= c.prm.k) positions += c.h_len[r] - c.prm.k + 1;
+    }
+    uint64_t cap = static_cast<uint64_t>(
+                       static_cast<double>(positions) *
+                       std::min(1.0, 2.2 / (c.prm.w + 1.0))) + 4096;
+    cap = std::max<uint64_t>(cap, std::min<uint64_t>(c.s_val.cap, c.s_org.cap));
     uint64_t* tout = c.tile_out.reserve(n_tiles + 1);
-    SketchKernel<false><<<static_cast<unsigned>(n_tiles), kSketchThreads, smem,
-                          c.stream>>>(c.d_words.get(), c.d_woff.get(),
-                                      c.d_len.get(), c.d_ids.get(),
-                                      c.d_tile_off.get(), first,
-                                      last, c.prm.k, c.prm.w, tcnt, nullptr,
-                                      nullptr, nullptr);
-    RVN_LAUNCH_CHECK();
-    ++c.launches;
-    ExclusiveScanU32(c, tcnt, tout, n_tiles);
-    total = ReadU64(c, tout + n_tiles);
-    uint64_t* val = c.s_val.reserve(total);
-    uint64_t* org = c.s_org.reserve(total);
-    SketchKernel<true><<<static_cast<unsigned>(n_tiles), kSketchThreads, smem,
-                         c.stream>>>(c.d_words.get(), c.d_woff.get(),
-                                     c.d_len.get(), c.d_ids.get(),
-                                     c.d_tile_off.get(), first,
-                                     last, c.prm.k, c.prm.w, nullptr, tout, val,
-                                     org);
-    RVN_LAUNCH_CHECK();
-    ++c.launches;
+    uint64_t* status = c.tile_status.reserve(n_tiles + 2);
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(status + n_tiles);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      uint64_t* val = c.s_val.reserve(cap);
+      uint64_t* org = c.s_org.reserve(cap);
+      RVN_CUDA(cudaMemsetAsync(status, 0, (n_tiles + 2) * sizeof(uint64_t), c.stream));
+      if (k32) {
+        SketchKernel<uint32_t><<<static_cast<unsigned>(n_tiles), kSketchThreads, smem,
+                                 c.stream>>>(
+            c.d_words.get(), c.d_woff.get(), c.d_len.get(), c.d_ids.get(),
+            c.d_tile_off.get(), first, last, c.prm.k, c.prm.w, ticket, status, tout,
+            n_tiles, cap, val, org);
+      } else {
+        SketchKernel<uint64_t><<<static_cast<unsigned>(n_tiles), kSketchThreads, smem,
+                                 c.stream>>>(
+            c.d_words.get(), c.d_woff.get(), c.d_len.get(), c.d_ids.get(),
+            c.d_tile_off.get(), first, last, c.prm.k, c.prm.w, ticket, status, tout,
+            n_tiles, cap, val, org);
+      }
+      RVN_LAUNCH_CHECK();
+      ++c.launches;
+      total = ReadU64(c, tout + n_tiles);
+      if (total <= cap) break;
+      cap = total;  // denser than expected: once more with the exact size
+    }
     GatherReadOffsets<<<CeilDiv(nr + 1ULL, 256), 256, 0, c.stream>>>(
         c.d_tile_off.get(), tout, first, nr, read_off);
     RVN_LAUNCH_CHECK();
