@@ -12,6 +12,7 @@
  *   rvn_map / rvn_map_external
  *                          MinimizerEngine::Map        RavenLib/src/construct.cc:59-64,377-381
  *   rvn_pile_add_layers    raven::Pile::AddLayers      RavenLib/src/pile.cc:33-62
+ *   rvn_kmer_complexity    raven::Pile::AddKmers       RavenLib/src/pile.cc:64-120
  *   rvn_find_overlaps_and_create_piles
  *                          raven::FindOverlapsAndCreatePiles
  *                                                      RavenLib/src/construct.cc:14-121
@@ -130,6 +131,14 @@ int rvn_map_results(rvn_ctx* ctx, const rvn_overlap** overlaps,
 int rvn_pile_add_layers(rvn_ctx* ctx, uint16_t* data, const uint64_t* bin_off,
                         uint32_t n_piles, const rvn_overlap* overlaps,
                         uint64_t n_overlaps);
+
+/* The low-complexity test of Pile::AddKmers (RavenLib/src/pile.cc:64-120) for
+ * n (read index, position) pairs - the positions rvn_map reports as filtered
+ * (construct.cc:377-383): keep[i] = 1 iff the k-mer at positions[i] survives
+ * the three compressions, i.e. iff the reference sets kmers_[position >> 4]. */
+int rvn_kmer_complexity(rvn_ctx* ctx, const uint32_t* read_index,
+                        const uint32_t* positions, uint64_t n, uint32_t kmer_len,
+                        uint8_t* keep);
 
 /* raven::FindOverlapsAndCreatePiles over the uploaded read set: index batches
  * of >= index_batch_bases (reference: 1<<32), query flushes of >=

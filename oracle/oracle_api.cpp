@@ -223,3 +223,42 @@ ORC_EXPORT void orc_std_sort_hi32_desc(std::uint64_t* data, std::uint64_t n) {
     return (a >> 32) > (b >> 32);
   });
 }
+
+// Pile::AddKmers' low-complexity test (pile.cc:64-120), restated with plain
+// strings: keep[i] = 1 iff the reference would set kmers_[pos >> 4]
+ORC_EXPORT void orc_kmer_complexity(orc_reads* r, const std::uint32_t* read_index,
+                                    const std::uint32_t* pos, std::uint64_t n,
+                                    std::uint32_t k, std::uint8_t* keep) {
+  auto unique_concat = [](const std::vector<std::string>& tok) {
+    std::string out;
+    for (std::size_t i = 0; i < tok.size(); ++i) {
+      if (i == 0 || tok[i] != tok[i - 1]) out += tok[i];
+    }
+    return out;
+  };
+  for (std::uint64_t t = 0; t < n; ++t) {
+    std::string kmer = r->seqs[read_index[t]]->InflateData(pos[t], k);
+    keep[t] = 0;
+    std::vector<std::string> tok;
+    for (char c : kmer) tok.emplace_back(1, c);
+    kmer = unique_concat(tok);
+    if (kmer.size() < k / 2 + 1) continue;
+    tok.clear();
+    for (std::size_t i = 0; i < kmer.size(); ++i) {
+      if (i % 2 == 1) tok.back() += kmer[i]; else tok.emplace_back(1, kmer[i]);
+    }
+    kmer = unique_concat(tok);
+    if (kmer.size() < k / 2 + 1) continue;
+    tok.clear();
+    for (std::size_t i = 0; i < kmer.size(); ++i) {
+      if (!tok.empty() && i % 2 == 0) tok.back() += kmer[i]; else tok.emplace_back(1, kmer[i]);
+    }
+    kmer = unique_concat(tok);
+    if (kmer.size() < k / 2 + 1) continue;
+    keep[t] = 1;
+  }
+}
+
+ORC_EXPORT void orc_reads_set_ids(orc_reads* r, const std::uint32_t* ids) {
+  for (std::size_t i = 0; i < r->seqs.size(); ++i) r->seqs[i]->id = ids[i];
+}

@@ -34,6 +34,16 @@ namespace {
 
 // Pile keeps its histogram private; the only door the reference leaves open is
 // `friend cereal::access` + serialize(). This archive just captures fields.
+struct KmerProbe {
+  bool any = false;
+  template <typename... Ts>
+  void operator()(std::uint32_t&, std::uint32_t&, std::uint32_t&, std::uint16_t&,
+                  bool&, bool&, bool&, bool&, std::vector<std::uint16_t>&,
+                  std::vector<bool>& kmers, Ts&...) {
+    for (bool b : kmers) any = any || b;
+  }
+};
+
 struct PileProbe {
   std::vector<std::uint16_t> data;
   template <typename... Ts>
@@ -105,6 +115,21 @@ ORC_EXPORT orc_bag* ref_pile_add_layers(std::uint32_t id, std::uint32_t len,
   auto* bag = new orc_bag();
   bag->Put("pile", probe.data);
   return bag;
+}
+
+// raven::Pile::AddKmers on a fresh pile of read `index`: which positions mark
+// their bin (one position at a time, so keep[] is per position)
+ORC_EXPORT void ref_kmer_complexity(orc_reads* r, const std::uint32_t* read_index,
+                                    const std::uint32_t* pos, std::uint64_t n,
+                                    std::uint32_t k, std::uint8_t* keep) {
+  for (std::uint64_t t = 0; t < n; ++t) {
+    const auto& seq = r->seqs[read_index[t]];
+    raven::Pile p(seq->id, seq->inflated_len);
+    p.AddKmers(std::vector<std::uint32_t>{pos[t]}, k, seq);
+    KmerProbe probe;
+    cereal::access::member_serialize(probe, p);
+    keep[t] = probe.any;
+  }
 }
 
 ORC_EXPORT std::uint32_t ref_overlap_length(const std::uint32_t* o) {

@@ -372,6 +372,19 @@ RVN_API int rvn_pile_add_layers(rvn_ctx* ctx, uint16_t* data,
   });
 }
 
+RVN_API int rvn_kmer_complexity(rvn_ctx* ctx, const uint32_t* read_index,
+                                const uint32_t* positions, uint64_t n,
+                                uint32_t kmer_len, uint8_t* keep) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (n && (!read_index || !positions || !keep)) throw InvalidArgument("null argument");
+    if (kmer_len == 0 || kmer_len > 31) throw InvalidArgument("k-mer length outside [1, 31]");
+    for (uint64_t i = 0; i < n; ++i) {
+      if (read_index[i] >= c.n_reads) throw InvalidArgument("read index out of bounds");
+    }
+    KmerComplexity(c, read_index, positions, n, kmer_len, keep);
+  });
+}
+
 RVN_API int rvn_find_overlaps_and_create_piles(rvn_ctx* ctx, double frequency,
                                                uint64_t max_overlaps,
                                                int minhash,

@@ -188,4 +188,8 @@ void PileAddLayersDevice(Ctx& c, uint16_t* d_data, const uint64_t* d_off,
                          const uint64_t* h_off, uint32_t n_piles,
                          const rvn_overlap* d_ovl, uint64_t n_ovl);
 
+// Pile::AddKmers low-complexity test for (read index, position) pairs
+void KmerComplexity(Ctx& c, const uint32_t* h_read_idx, const uint32_t* h_pos,
+                    uint64_t n, uint32_t k, uint8_t* h_keep);
+
 }  // namespace rvn

@@ -95,3 +95,100 @@ void PileAddLayersDevice(Ctx& c, uint16_t* d_data, const uint64_t* d_off,
 }
 
 }  // namespace rvn
+
+// ---------------------------------------------------------------------------
+// raven::Pile::AddKmers (RavenLib/src/pile.cc:64-120): a position of an
+// over-frequent minimizer marks its pile bin unless the k-mer is of low
+// complexity. Three successive compressions, each must leave >= k/2 + 1
+// characters: (1) homopolymer runs, (2) equal neighbouring 2-mers taken at even
+// offsets, (3) equal neighbouring 2-mers taken at odd offsets. A pure function
+// of <= 31 bases: one thread per position.
+// ---------------------------------------------------------------------------
+namespace rvn {
+
+namespace {
+
+__device__ __forceinline__ uint32_t BaseAt(const uint64_t* __restrict__ w, uint32_t i) {
+  return static_cast<uint32_t>(w[i >> 5] >> ((i & 31) << 1)) & 3u;
+}
+
+// unique-consecutive over `n` tokens; tokens are (value, width) packed as
+// value | width << 8; returns the number of characters kept and rewrites c[]
+__device__ uint32_t CompressPairs(uint8_t* c, uint32_t n, uint32_t first_single) {
+  // tokenise: an optional leading single, then 2-mers, a trailing single if odd
+  uint8_t out[32];
+  uint32_t m = 0;
+  uint32_t i = 0;
+  uint32_t last_tok = 0xFFFFFFFFu;
+  auto emit = [&](uint32_t a, uint32_t b, uint32_t width) {
+    const uint32_t tok = a | (b << 2) | (width << 4);
+    if (tok != last_tok) {
+      out[m++] = static_cast<uint8_t>(a);
+      if (width == 2) out[m++] = static_cast<uint8_t>(b);
+    }
+    last_tok = tok;
+  };
+  if (first_single && n > 0) {
+    emit(c[0], 0, 1);
+    i = 1;
+  }
+  for (; i + 1 < n; i += 2) emit(c[i], c[i + 1], 2);
+  if (i < n) emit(c[i], 0, 1);
+  for (uint32_t j = 0; j < m; ++j) c[j] = out[j];
+  return m;
+}
+
+__global__ void KmerComplexityKernel(const uint64_t* __restrict__ words,
+                                     const uint64_t* __restrict__ woff,
+                                     const uint32_t* __restrict__ lens,
+                                     const uint32_t* __restrict__ read_idx,
+                                     const uint32_t* __restrict__ pos, uint64_t n,
+                                     uint32_t k, uint8_t* __restrict__ keep) {
+  const uint64_t t = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint32_t r = read_idx[t];
+  const uint32_t p = pos[t];
+  const uint32_t len = lens[r];
+  const uint64_t* w = words + woff[r];
+  uint8_t c[32];
+  uint32_t m = 0;
+  // InflateData(p, k) clamps at the read end
+  for (uint32_t i = 0; i < k && p + i < len; ++i) c[m++] = static_cast<uint8_t>(BaseAt(w, p + i));
+  const uint32_t need = k / 2 + 1;
+  // (1) homopolymer compression
+  uint32_t q = 0;
+  for (uint32_t i = 0; i < m; ++i) {
+    if (i == 0 || c[i] != c[i - 1]) c[q++] = c[i];
+  }
+  m = q;
+  bool ok = m >= need;
+  if (ok) {  // (2) 2-mers at even offsets
+    m = CompressPairs(c, m, 0);
+    ok = m >= need;
+  }
+  if (ok) {  // (3) 2-mers at odd offsets
+    m = CompressPairs(c, m, 1);
+    ok = m >= need;
+  }
+  keep[t] = ok ? 1 : 0;
+}
+
+}  // namespace
+
+void KmerComplexity(Ctx& c, const uint32_t* h_read_idx, const uint32_t* h_pos,
+                    uint64_t n, uint32_t k, uint8_t* h_keep) {
+  if (n == 0) return;
+  uint32_t* d_idx = c.m_cnt.reserve(n);
+  uint32_t* d_pos = c.m_first.reserve(n);
+  uint8_t* d_keep = c.m_filt.reserve(n);
+  RVN_CUDA(cudaMemcpyAsync(d_idx, h_read_idx, n * 4, cudaMemcpyHostToDevice, c.stream));
+  RVN_CUDA(cudaMemcpyAsync(d_pos, h_pos, n * 4, cudaMemcpyHostToDevice, c.stream));
+  KmerComplexityKernel<<<CeilDiv(n, 256), 256, 0, c.stream>>>(
+      c.d_words.get(), c.d_woff.get(), c.d_len.get(), d_idx, d_pos, n, k, d_keep);
+  RVN_LAUNCH_CHECK();
+  ++c.launches;
+  RVN_CUDA(cudaMemcpyAsync(h_keep, d_keep, n, cudaMemcpyDeviceToHost, c.stream));
+  RVN_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+}  // namespace rvn

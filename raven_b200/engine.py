@@ -133,6 +133,16 @@ class Engine:
             C.cast(o.ctypes.data, OVLP), o.shape[0]))
         return d
 
+    def kmer_complexity(self, read_index, positions, kmer_len):
+        """Pile::AddKmers' low-complexity test (pile.cc:64-120): 1 = bin gets marked."""
+        ri = np.ascontiguousarray(read_index, dtype=np.uint32)
+        po = np.ascontiguousarray(positions, dtype=np.uint32)
+        keep = np.zeros(ri.size, dtype=np.uint8)
+        self._check(self.lib.rvn_kmer_complexity(
+            self.h, ri.ctypes.data_as(U32P), po.ctypes.data_as(U32P), ri.size, kmer_len,
+            keep.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return keep
+
     # ---- raven::FindOverlapsAndCreatePiles ----
     def find_overlaps_and_create_piles(self, freq=0.001, max_overlaps=32,
                                        use_minhash=False, index_batch_bases=0,

@@ -178,6 +178,16 @@ class Oracle(_Flat):
         n = self.lib.orc_truncate(_ptr(o, _U32P), o.shape[0], max_overlaps)
         return o[:n]
 
+    def kmer_complexity(self, reads, read_index, positions, k):
+        ri = np.ascontiguousarray(read_index, dtype=np.uint32)
+        po = np.ascontiguousarray(positions, dtype=np.uint32)
+        keep = np.zeros(ri.size, dtype=np.uint8)
+        self.lib.orc_kmer_complexity.argtypes = [C.c_void_p, _U32P, _U32P, C.c_uint64,
+                                                 C.c_uint32, _U8P]
+        self.lib.orc_kmer_complexity(reads.h, _ptr(ri, _U32P), _ptr(po, _U32P), ri.size, k,
+                                     _ptr(keep, _U8P))
+        return keep
+
     def edit_distance(self, a: bytes, b: bytes) -> int:
         return self.lib.orc_edit_distance(a, len(a), b, len(b))
 
@@ -208,6 +218,16 @@ class Reference(_Flat):
         r = self.unbag(bag, _STAGE1)
         r["overlaps"] = r["overlaps"].reshape(-1, 8)
         return r
+
+    def kmer_complexity(self, reads, read_index, positions, k):
+        ri = np.ascontiguousarray(read_index, dtype=np.uint32)
+        po = np.ascontiguousarray(positions, dtype=np.uint32)
+        keep = np.zeros(ri.size, dtype=np.uint8)
+        self.lib.ref_kmer_complexity.argtypes = [C.c_void_p, _U32P, _U32P, C.c_uint64,
+                                                 C.c_uint32, _U8P]
+        self.lib.ref_kmer_complexity(reads.h, _ptr(ri, _U32P), _ptr(po, _U32P), ri.size, k,
+                                     _ptr(keep, _U8P))
+        return keep
 
     def pile_add_layers(self, read_id, length, overlaps, rounds=1):
         o = np.ascontiguousarray(overlaps, dtype=np.uint32).reshape(-1, 8)

@@ -237,3 +237,62 @@ def test_stage1_hifi_params(gpu_engine, oracle):
     want = oracle.stage1(oracle.engine(19, 10, threads=4), oracle.reads(rs), 0.001, 32, False)
     for k in ("overlaps", "ovl_off", "pile", "pile_off"):
         assert np.array_equal(got[k], want[k]), k
+
+
+def test_kmer_complexity(gpu_engine, oracle):
+    """Pile::AddKmers' low-complexity rule on the positions Map reports as filtered."""
+    from test_oracle import _lowcomplexity_reads
+    rs = _lowcomplexity_reads()
+    gpu_engine.configure(15, 5)
+    gpu_engine.upload(rs)
+    idx, pos = [], []
+    for r in range(rs.n):
+        for p in range(0, int(rs.lens[r])):
+            idx.append(r); pos.append(p)
+    for k in (15, 19, 31, 9, 4, 1):
+        got = gpu_engine.kmer_complexity(idx, pos, k)
+        want = oracle.kmer_complexity(oracle.reads(rs), idx, pos, k)
+        assert np.array_equal(got, want), k
+    with pytest.raises(ValueError):
+        gpu_engine.kmer_complexity([0], [0], 32)
+    with pytest.raises(ValueError):
+        gpu_engine.kmer_complexity([99], [0], 15)
+
+
+def test_stage2_map_filtered_feeds_add_kmers(gpu_engine, oracle, lambda_reads):
+    """Stage-2 semantics (construct.cc:363-383): full sketches, filtered positions,
+    explicit ids after raven's re-sort of the sequences."""
+    n = lambda_reads.n
+    order = np.r_[np.arange(0, n, 2), np.arange(1, n, 2)]     # ids no longer == positions
+    rs = lambda_reads.subset(order)
+    lib = gpu_engine.lib
+    import ctypes as C
+    words = np.ascontiguousarray(rs.words); woff = np.ascontiguousarray(rs.word_off)
+    lens = np.ascontiguousarray(rs.lens); ids = np.ascontiguousarray(order.astype(np.uint32))
+    from raven_b200._lib import U64P, U32P
+    gpu_engine.configure(15, 5)
+    gpu_engine._check(lib.rvn_reads_upload_ids(gpu_engine.h, words.ctypes.data_as(U64P),
+                                               woff.ctypes.data_as(U64P),
+                                               lens.ctypes.data_as(U32P),
+                                               ids.ctypes.data_as(U32P), rs.n))
+    gpu_engine.n_reads = rs.n
+    gpu_engine.minimize(0, 150, False)
+    occ = gpu_engine.filter(0.001)
+    got = gpu_engine.map(0, 150, True, True, False, want_filtered=True)
+    # the oracle sees the same permuted set with the same ids
+    eng = oracle.engine(15, 5, threads=4)
+    reads = oracle.reads(rs)
+    import oracle_lib
+    # give the oracle's sequences the permuted ids
+    oracle.lib.orc_reads_set_ids.argtypes = [C.c_void_p, oracle_lib._U32P]
+    oracle.lib.orc_reads_set_ids(reads.h, ids.ctypes.data_as(oracle_lib._U32P))
+    oracle.minimize(eng, reads, 0, 150, False)
+    assert occ == oracle.filter(eng, 0.001)
+    want = oracle.map(eng, reads, 0, 150, True, True, False)
+    assert np.array_equal(got["overlaps"], want["overlaps"])
+    assert np.array_equal(got["filtered"], want["filtered"])
+    assert np.array_equal(got["filt_off"], want["filt_off"])
+    # filtered positions -> AddKmers rule
+    ri = np.repeat(np.arange(150), np.diff(got["filt_off"].astype(np.int64)))
+    keep = gpu_engine.kmer_complexity(ri, got["filtered"], 15)
+    assert np.array_equal(keep, oracle.kmer_complexity(reads, ri, got["filtered"], 15))

@@ -195,3 +195,29 @@ def test_edit_distance_oracle(oracle):
     assert oracle.edit_distance(b"kitten", b"sitting") == 3
     assert oracle.edit_distance(b"", b"ACGT") == 4
     assert oracle.edit_distance(b"ACGT", b"ACGT") == 0
+
+
+def _lowcomplexity_reads():
+    rng = np.random.default_rng(17)
+    seqs = [rng.integers(0, 4, 400, dtype=np.uint8)]
+    seqs.append(np.repeat(rng.integers(0, 4, 60, dtype=np.uint8), rng.integers(1, 9, 60)))  # homopolymer runs
+    seqs.append(np.tile(np.array([0, 1], np.uint8), 150))            # (AC)n
+    seqs.append(np.tile(np.array([0, 1, 1, 0], np.uint8), 80))       # ACCA..
+    seqs.append(np.tile(np.array([2, 0, 1], np.uint8), 100))         # (GAC)n
+    seqs.append(np.concatenate([np.tile(np.array([3, 2], np.uint8), 40),
+                                rng.integers(0, 4, 100, dtype=np.uint8)]))
+    seqs.append(rng.integers(0, 4, 20, dtype=np.uint8))              # shorter than k near the end
+    return seqio.pack_codes(seqs)
+
+
+def test_kmer_complexity_port_equals_reference_pile(oracle, reference):
+    rs = _lowcomplexity_reads()
+    idx, pos = [], []
+    for r in range(rs.n):
+        for p in range(0, int(rs.lens[r]), 3):
+            idx.append(r); pos.append(p)
+    for k in (15, 19, 9, 4):
+        a = oracle.kmer_complexity(oracle.reads(rs), idx, pos, k)
+        b = reference.kmer_complexity(reference.reads(rs), idx, pos, k)
+        assert np.array_equal(a, b), k
+        assert 0 < a.sum() < a.size
