@@ -13,6 +13,8 @@
  *                          MinimizerEngine::Map        RavenLib/src/construct.cc:59-64,377-381
  *   rvn_pile_add_layers    raven::Pile::AddLayers      RavenLib/src/pile.cc:33-62
  *   rvn_kmer_complexity    raven::Pile::AddKmers       RavenLib/src/pile.cc:64-120
+ *   rvn_poa_batch          racon::Polisher::Polish (window consensus: racon::Window +
+ *                          spoa)                       RavenLib/src/polish.cc:43-51
  *   rvn_find_overlaps_and_create_piles
  *                          raven::FindOverlapsAndCreatePiles
  *                                                      RavenLib/src/construct.cc:14-121
@@ -152,6 +154,27 @@ int rvn_find_overlaps_and_create_piles(rvn_ctx* ctx, double frequency,
 int rvn_stage1_results(rvn_ctx* ctx, const rvn_overlap** overlaps,
                        const uint64_t** ovl_off, const uint16_t** pile,
                        const uint64_t** pile_off, uint64_t* n_mapped);
+
+/* racon::Window::GenerateConsensus over a batch of windows - the unit of the
+ * "POA windows/s" metric; stands in for the consensus phase of
+ * racon::Polisher::Polish (RavenLib/src/polish.cc:43-51; raven passes w = 500,
+ * trim = true, m/n/g = PolishCfg polish.hpp:13-17). Flat layout: window w owns
+ * sequences [win_first[w], win_first[w+1]); the first is the backbone (draft),
+ * the others are layers aligned to backbone positions [seq_begin, seq_end]
+ * (inclusive, < backbone length); sequence s = bases[seq_off[s]..seq_off[s+1])
+ * as ACGT letters, quals (Phred+33) at the same offsets or NULL (layers weigh 1,
+ * the backbone 0 like racon's dummy '!' quality).
+ * g must be negative (racon throws otherwise -> RVN_ERR_INVALID).
+ * Results: consensus letters per window (cons_off has n_windows+1 entries),
+ * status bit 0 = polished (>= 3 sequences), bit 1 = trimming skipped
+ * ("might be chimeric"), coverage per consensus base if requested. */
+int rvn_poa_batch(rvn_ctx* ctx, uint32_t n_windows, const uint32_t* win_first,
+                  const uint64_t* seq_off, const char* bases, const char* quals,
+                  const uint32_t* seq_begin, const uint32_t* seq_end, int8_t m,
+                  int8_t n, int8_t g, int trim, int tgs, int want_coverage);
+int rvn_poa_results(rvn_ctx* ctx, const char** consensus, const uint64_t** cons_off,
+                    const uint8_t** status, const uint32_t** coverage,
+                    uint64_t* cells);
 
 /* ---- introspection (parity tests, profiling) ---- */
 

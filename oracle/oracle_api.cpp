@@ -262,3 +262,72 @@ ORC_EXPORT void orc_kmer_complexity(orc_reads* r, const std::uint32_t* read_inde
 ORC_EXPORT void orc_reads_set_ids(orc_reads* r, const std::uint32_t* ids) {
   for (std::size_t i = 0; i < r->seqs.size(); ++i) r->seqs[i]->id = ids[i];
 }
+
+// ---------------------------------------------------------------------------
+// racon window consensus (POA) over a flat batch of windows; the same layout
+// as rvn_poa_batch (include/raven_b200.h): window w owns sequences
+// [win_first[w], win_first[w+1]), the first one is the backbone; sequence s is
+// bases[seq_off[s] .. seq_off[s+1]) (+ quals at the same offsets, or NULL),
+// layered at backbone positions [seq_begin[s], seq_end[s]].
+// ---------------------------------------------------------------------------
+#include "racon/window.hpp"
+
+ORC_EXPORT orc_bag* orc_poa_batch(std::uint32_t n_windows,
+                                  const std::uint32_t* win_first,
+                                  const std::uint64_t* seq_off, const char* bases,
+                                  const char* quals, const std::uint32_t* seq_begin,
+                                  const std::uint32_t* seq_end, int m, int n, int g,
+                                  int trim, int tgs, std::uint32_t threads) {
+  std::vector<std::string> cons(n_windows);
+  std::vector<std::vector<std::uint32_t>> covs(n_windows);
+  std::vector<std::uint8_t> status(n_windows, 0);
+  std::vector<std::uint64_t> cells(n_windows, 0);
+  auto pool = std::make_shared<thread_pool::ThreadPool>(std::max(1U, threads));
+  std::vector<std::future<void>> fut;
+  auto t0 = std::chrono::steady_clock::now();
+  for (std::uint32_t w = 0; w < n_windows; ++w) {
+    fut.emplace_back(pool->Submit(
+        [&](std::uint32_t w) {
+          const std::uint32_t s0 = win_first[w], s1 = win_first[w + 1];
+          racon::Window win(w, 0, tgs ? racon::WindowType::kTGS : racon::WindowType::kNGS,
+                            bases + seq_off[s0], seq_off[s0 + 1] - seq_off[s0],
+                            quals ? quals + seq_off[s0] : nullptr,
+                            quals ? seq_off[s0 + 1] - seq_off[s0] : 0);
+          for (std::uint32_t s = s0 + 1; s < s1; ++s) {
+            const std::uint32_t len = seq_off[s + 1] - seq_off[s];
+            win.AddLayer(bases + seq_off[s], len, quals ? quals + seq_off[s] : nullptr,
+                         quals ? len : 0, seq_begin[s], seq_end[s]);
+          }
+          spoa::AlignmentEngine engine(m, n, g);
+          status[w] = win.GenerateConsensus(&engine, trim != 0) ? 1 : 0;
+          if (win.chimeric_warning()) status[w] |= 2;
+          cons[w] = win.consensus();
+          covs[w] = win.coverages();
+          // unpolished windows (backbone returned) carry no coverage: zeros
+          if (!(status[w] & 1)) covs[w].assign(cons[w].size(), 0);
+          cells[w] = engine.cells();
+        },
+        w));
+  }
+  for (auto& f : fut) f.get();
+  double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  auto* bag = new orc_bag();
+  std::vector<char> flat;
+  std::vector<std::uint64_t> off{0}, coff{0};
+  std::vector<std::uint32_t> cov;
+  for (std::uint32_t w = 0; w < n_windows; ++w) {
+    flat.insert(flat.end(), cons[w].begin(), cons[w].end());
+    off.emplace_back(flat.size());
+    cov.insert(cov.end(), covs[w].begin(), covs[w].end());
+    coff.emplace_back(cov.size());
+  }
+  bag->Put("consensus", flat);
+  bag->Put("cons_off", off);
+  bag->Put("coverage", cov);
+  bag->Put("cov_off", coff);
+  bag->Put("status", status);
+  bag->Put("cells", cells);
+  std::vector<double> t{s};
+  bag->Put("seconds", t);
+  return bag;
+}

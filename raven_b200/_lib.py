@@ -48,6 +48,11 @@ SIGNATURES = {
                                   U64P, C.POINTER(U32P), C.POINTER(U64P)]),
     "rvn_pile_add_layers": (C.c_int, [C.c_void_p, U16P, U64P, C.c_uint32, OVLP,
                                       C.c_uint64]),
+    "rvn_poa_batch": (C.c_int, [C.c_void_p, C.c_uint32, U32P, U64P, C.c_char_p, C.c_char_p,
+                                U32P, U32P, C.c_int8, C.c_int8, C.c_int8, C.c_int, C.c_int,
+                                C.c_int]),
+    "rvn_poa_results": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(U64P),
+                                  C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(U32P), U64P]),
     "rvn_kmer_complexity": (C.c_int, [C.c_void_p, U32P, U32P, C.c_uint64, C.c_uint32,
                                       C.POINTER(C.c_uint8)]),
     "rvn_find_overlaps_and_create_piles": (

@@ -372,6 +372,36 @@ RVN_API int rvn_pile_add_layers(rvn_ctx* ctx, uint16_t* data,
   });
 }
 
+RVN_API int rvn_poa_batch(rvn_ctx* ctx, uint32_t n_windows, const uint32_t* win_first,
+                          const uint64_t* seq_off, const char* bases,
+                          const char* quals, const uint32_t* seq_begin,
+                          const uint32_t* seq_end, int8_t m, int8_t n, int8_t g,
+                          int trim, int tgs, int want_coverage) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (n_windows && (!win_first || !seq_off || !bases || !seq_begin || !seq_end)) {
+      throw InvalidArgument("null window batch");
+    }
+    TimerReset(c);
+    PoaBatch(c, n_windows, win_first, seq_off, reinterpret_cast<const uint8_t*>(bases),
+             reinterpret_cast<const uint8_t*>(quals), seq_begin, seq_end, m, n, g,
+             trim != 0, tgs != 0, want_coverage != 0);
+    TimerCollect(c);
+  });
+}
+
+RVN_API int rvn_poa_results(rvn_ctx* ctx, const char** consensus,
+                            const uint64_t** cons_off, const uint8_t** status,
+                            const uint32_t** coverage, uint64_t* cells) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (!c.poa_valid) throw StateError("no POA results");
+    if (consensus) *consensus = reinterpret_cast<const char*>(c.po_out_cons.data());
+    if (cons_off) *cons_off = c.po_out_off.data();
+    if (status) *status = c.po_h_status.data();
+    if (coverage) *coverage = c.po_has_cov ? c.po_out_cov.data() : nullptr;
+    if (cells) *cells = c.po_cells;
+  });
+}
+
 RVN_API int rvn_kmer_complexity(rvn_ctx* ctx, const uint32_t* read_index,
                                 const uint32_t* positions, uint64_t n,
                                 uint32_t kmer_len, uint8_t* keep) {

@@ -133,6 +133,17 @@ struct Ctx {
   DevBuf<uint32_t> g_cnt, g_kept, g_key, g_idx, g_key2, g_idx2, g_rhs_cnt,
       g_total_cnt;
 
+  // ---- POA (poa.cu) ----
+  DevBuf<uint32_t> po_win_first, po_seq_begin, po_seq_end, po_cons_len, po_cov, po_list;
+  DevBuf<uint64_t> po_seq_off, po_d_cons_off;
+  DevBuf<uint8_t> po_bases, po_quals, po_cons, po_status, po_scratch;
+  std::vector<uint64_t> po_cons_off, po_out_off;
+  std::vector<uint8_t> po_h_status, po_h_cons, po_out_cons;
+  std::vector<uint32_t> po_h_clen, po_h_cov, po_out_cov;
+  uint64_t po_cells = 0;
+  uint32_t po_n_windows = 0;
+  bool po_has_cov = false, poa_valid = false;
+
   // ---- stage-1 results ----
   std::vector<rvn_overlap> st_ovl;
   std::vector<uint64_t> st_ovl_off;
@@ -187,6 +198,12 @@ void GatherFetch(Ctx& c);
 void PileAddLayersDevice(Ctx& c, uint16_t* d_data, const uint64_t* d_off,
                          const uint64_t* h_off, uint32_t n_piles,
                          const rvn_overlap* d_ovl, uint64_t n_ovl);
+
+// ---- poa.cu ---- racon window consensus over a flat batch of windows
+void PoaBatch(Ctx& c, uint32_t n_windows, const uint32_t* h_win_first,
+              const uint64_t* h_seq_off, const uint8_t* h_bases, const uint8_t* h_quals,
+              const uint32_t* h_seq_begin, const uint32_t* h_seq_end, int m, int n,
+              int gap, bool trim, bool tgs, bool want_coverage);
 
 // Pile::AddKmers low-complexity test for (read index, position) pairs
 void KmerComplexity(Ctx& c, const uint32_t* h_read_idx, const uint32_t* h_pos,

@@ -133,6 +133,33 @@ class Engine:
             C.cast(o.ctypes.data, OVLP), o.shape[0]))
         return d
 
+    # ---- racon::Polisher consensus phase (racon::Window + spoa) ----
+    def poa_batch(self, w, m=3, n=-5, g=-4, trim=True, tgs=True, want_coverage=True):
+        """Consensus of a flat batch of windows (layout: synth.make_windows)."""
+        wf = np.ascontiguousarray(w["win_first"], dtype=np.uint32)
+        so = np.ascontiguousarray(w["seq_off"], dtype=np.uint64)
+        ba = np.ascontiguousarray(w["bases"], dtype=np.uint8)
+        qu = None if w.get("quals") is None else np.ascontiguousarray(w["quals"], dtype=np.uint8)
+        sb = np.ascontiguousarray(w["seq_begin"], dtype=np.uint32)
+        se = np.ascontiguousarray(w["seq_end"], dtype=np.uint32)
+        nw = wf.size - 1
+        self._check(self.lib.rvn_poa_batch(
+            self.h, nw, wf.ctypes.data_as(U32P), so.ctypes.data_as(U64P),
+            ba.ctypes.data_as(C.c_char_p),
+            qu.ctypes.data_as(C.c_char_p) if qu is not None else None,
+            sb.ctypes.data_as(U32P), se.ctypes.data_as(U32P), m, n, g, int(trim), int(tgs),
+            int(want_coverage)))
+        cons, off, st, cov = C.c_void_p(), U64P(), C.POINTER(C.c_uint8)(), U32P()
+        cells = C.c_uint64(0)
+        self._check(self.lib.rvn_poa_results(self.h, C.byref(cons), C.byref(off),
+                                             C.byref(st), C.byref(cov), C.byref(cells)))
+        cons_off = _arr(off, nw + 1, np.uint64)
+        total = int(cons_off[-1]) if nw else 0
+        return dict(consensus=_arr(cons, total, np.uint8), cons_off=cons_off,
+                    status=_arr(st, nw, np.uint8),
+                    coverage=_arr(cov, total if want_coverage else 0, np.uint32),
+                    cells=cells.value)
+
     def kmer_complexity(self, read_index, positions, kmer_len):
         """Pile::AddKmers' low-complexity test (pile.cc:64-120): 1 = bin gets marked."""
         ri = np.ascontiguousarray(read_index, dtype=np.uint32)

@@ -188,6 +188,28 @@ class Oracle(_Flat):
                                      _ptr(keep, _U8P))
         return keep
 
+    def poa_batch(self, w, m=3, n=-5, g=-4, trim=True, tgs=True, threads=4):
+        """racon window consensus over the flat window batch `w` (synth.make_windows)."""
+        L = self.lib
+        L.orc_poa_batch.restype = C.c_void_p
+        L.orc_poa_batch.argtypes = [C.c_uint32, _U32P, _U64P, C.c_char_p, C.c_char_p, _U32P,
+                                    _U32P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_uint32]
+        wf = np.ascontiguousarray(w["win_first"], dtype=np.uint32)
+        so = np.ascontiguousarray(w["seq_off"], dtype=np.uint64)
+        ba = np.ascontiguousarray(w["bases"], dtype=np.uint8)
+        qu = None if w.get("quals") is None else np.ascontiguousarray(w["quals"], dtype=np.uint8)
+        sb = np.ascontiguousarray(w["seq_begin"], dtype=np.uint32)
+        se = np.ascontiguousarray(w["seq_end"], dtype=np.uint32)
+        bag = L.orc_poa_batch(wf.size - 1, _ptr(wf, _U32P), _ptr(so, _U64P),
+                              ba.ctypes.data_as(C.c_char_p),
+                              qu.ctypes.data_as(C.c_char_p) if qu is not None else None,
+                              _ptr(sb, _U32P), _ptr(se, _U32P), m, n, g, int(trim), int(tgs),
+                              threads)
+        return self.unbag(bag, dict(consensus=np.uint8, cons_off=np.uint64, coverage=np.uint32,
+                                    cov_off=np.uint64, status=np.uint8, cells=np.uint64,
+                                    seconds=np.float64))
+
     def edit_distance(self, a: bytes, b: bytes) -> int:
         return self.lib.orc_edit_distance(a, len(a), b, len(b))
 

@@ -1,0 +1,71 @@
+"""GPU parity: racon window consensus (POA) through the C ABI vs the CPU oracle
+(oracle/spoa_graph.cpp + oracle/racon_window.cpp) - consensus letters,
+coverages and status bit-exact."""
+import numpy as np
+import pytest
+
+from raven_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def check(gpu_engine, oracle, w, **kw):
+    got = gpu_engine.poa_batch(w, **kw)
+    want = oracle.poa_batch(w, threads=8, **kw)
+    assert np.array_equal(got["cons_off"], want["cons_off"])
+    assert np.array_equal(got["consensus"], want["consensus"])
+    assert np.array_equal(got["status"], want["status"])
+    assert np.array_equal(got["coverage"], want["coverage"])
+    assert got["cells"] == int(want["cells"].sum())
+    return got
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_poa_ont_windows(gpu_engine, oracle, seed):
+    w = synth.make_windows(n_windows=24, backbone_len=500, layers=30, seed=seed)
+    got = check(gpu_engine, oracle, w)
+    assert (got["status"] & 1).all()
+    # the consensus is much closer to the hidden truth than the draft backbone
+    err_c = err_b = 0
+    for i in range(24):
+        c = got["consensus"][int(got["cons_off"][i]):int(got["cons_off"][i + 1])].tobytes()
+        s0 = int(w["win_first"][i])
+        b = w["bases"][int(w["seq_off"][s0]):int(w["seq_off"][s0 + 1])].tobytes()
+        err_c += oracle.edit_distance(c, w["truths"][i])
+        err_b += oracle.edit_distance(b, w["truths"][i])
+    assert err_c * 10 < err_b
+
+
+def test_poa_variants(gpu_engine, oracle):
+    # no qualities (weight 1), all layers partial, other scores, no trimming, NGS type
+    w = synth.make_windows(n_windows=12, backbone_len=300, layers=12, seed=5,
+                           with_quality=False, partial=1.0)
+    check(gpu_engine, oracle, w)
+    check(gpu_engine, oracle, w, m=5, n=-4, g=-8)
+    check(gpu_engine, oracle, w, trim=False)
+    check(gpu_engine, oracle, w, tgs=False)
+    # HiFi-like: few errors, deep
+    w = synth.make_windows(n_windows=6, backbone_len=500, layers=60, seed=6, sub=0.002,
+                           ins=0.0015, dele=0.0015)
+    check(gpu_engine, oracle, w)
+    # ragged: windows with 0, 1, 2, ... layers (fewer than 3 sequences = backbone)
+    w = synth.make_windows(n_windows=16, backbone_len=200, layers=6, seed=7, min_layers=0)
+    got = check(gpu_engine, oracle, w)
+    nl = np.diff(w["win_first"].astype(np.int64))
+    assert ((got["status"] & 1) == (nl >= 3)).all()
+
+
+def test_poa_rejects_bad_input(gpu_engine):
+    w = synth.make_windows(n_windows=2, backbone_len=100, layers=4, seed=8)
+    with pytest.raises(ValueError):
+        gpu_engine.poa_batch(w, g=0)          # racon: gap must be negative
+    bad = dict(w)
+    bad["seq_end"] = w["seq_end"].copy()
+    bad["seq_end"][1] = 5000                  # beyond the backbone
+    with pytest.raises(ValueError):
+        gpu_engine.poa_batch(bad)
+    empty = dict(win_first=np.zeros(1, np.uint32), seq_off=np.zeros(1, np.uint64),
+                 bases=np.zeros(0, np.uint8), quals=None, seq_begin=np.zeros(0, np.uint32),
+                 seq_end=np.zeros(0, np.uint32))
+    got = gpu_engine.poa_batch(empty)
+    assert got["cons_off"].tolist() == [0]
