@@ -765,6 +765,11 @@ PoaKernel(uint32_t n_windows, const uint32_t* __restrict__ win_list,
 }
 
 }  // namespace
+}  // namespace rvn
+
+#include "poa_fast.cuh"
+
+namespace rvn {
 
 // Host driver: windows in batches sized by the scratch budget; windows that
 // outgrow the first-tier capacity are retried with the exact upper bound.
@@ -835,7 +840,15 @@ void PoaBatch(Ctx& c, uint32_t n_windows, const uint32_t* h_win_first,
     shape.ecap = std::min<uint32_t>(3 * shape.ncap, 65000);
     shape.rows = shape.ncap + 1;
     shape.width = (lmax + 1 + 31) & ~31u;
-    const size_t stride = (MakePoaLayout(shape).bytes + 255) & ~size_t(255);
+    const bool fast = lmax + 1 <= kFastCols;  // the register-row kernel
+    const size_t stride = ((fast ? MakeFastLayout(shape).bytes : MakePoaLayout(shape).bytes) +
+                           255) & ~size_t(255);
+    const size_t fast_smem = ((shape.ncap + 15) & ~15u) + 4ULL * shape.ncap + 16;
+    if (fast) {
+      RVN_CUDA(cudaFuncSetAttribute(PoaKernelFast,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(std::min<size_t>(fast_smem, 220 * 1024))));
+    }
     const size_t budget = 48ULL << 30;  // scratch budget per batch
     const uint32_t batch = static_cast<uint32_t>(
         std::max<size_t>(1, std::min<size_t>(todo.size(), budget / stride)));
@@ -844,10 +857,17 @@ void PoaBatch(Ctx& c, uint32_t n_windows, const uint32_t* h_win_first,
     RVN_CUDA(cudaMemcpyAsync(d_list, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, c.stream));
     for (size_t b0 = 0; b0 < todo.size(); b0 += batch) {
       const uint32_t nb = static_cast<uint32_t>(std::min<size_t>(batch, todo.size() - b0));
-      PoaKernel<<<nb, 32, 0, c.stream>>>(
-          nb, d_list + b0, d_wf, d_so, d_bases, d_quals, d_sb, d_se, m, n, gap, trim, tgs,
-          shape, scratch, stride, d_cons, d_coff, d_clen, d_cov, d_status,
-          reinterpret_cast<unsigned long long*>(d_cells));
+      if (fast && fast_smem <= 220 * 1024) {
+        PoaKernelFast<<<nb, 32, fast_smem, c.stream>>>(
+            nb, d_list + b0, d_wf, d_so, d_bases, d_quals, d_sb, d_se, m, n, gap, trim,
+            tgs, shape, scratch, stride, d_cons, d_coff, d_clen, d_cov, d_status,
+            reinterpret_cast<unsigned long long*>(d_cells));
+      } else {
+        PoaKernel<<<nb, 32, 0, c.stream>>>(
+            nb, d_list + b0, d_wf, d_so, d_bases, d_quals, d_sb, d_se, m, n, gap, trim,
+            tgs, shape, scratch, stride, d_cons, d_coff, d_clen, d_cov, d_status,
+            reinterpret_cast<unsigned long long*>(d_cells));
+      }
       RVN_LAUNCH_CHECK();
       ++c.launches;
     }
