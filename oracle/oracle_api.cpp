@@ -331,3 +331,10 @@ ORC_EXPORT orc_bag* orc_poa_batch(std::uint32_t n_windows,
   bag->Put("seconds", t);
   return bag;
 }
+
+#include "racon/polisher.hpp"
+ORC_EXPORT std::int64_t orc_nw_path(const char* q, int nq, const char* t, int nt, char* out) {
+  const std::string p = racon::GlobalAlignmentPath(std::string(q, nq), std::string(t, nt));
+  std::memcpy(out, p.data(), p.size());
+  return static_cast<std::int64_t>(p.size());
+}

@@ -2,6 +2,7 @@
 #include "racon/window.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <stdexcept>
 
 namespace racon {
@@ -56,10 +57,14 @@ bool Window::GenerateConsensus(spoa::AlignmentEngine* engine, bool trim) {
   for (std::uint32_t i = 0; i < sequences_.size(); ++i) {
     rank.emplace_back(i);
   }
-  std::stable_sort(rank.begin() + 1, rank.end(),
-                   [&](std::uint32_t lhs, std::uint32_t rhs) {
-                     return positions_[lhs].first < positions_[rhs].first;
-                   });
+  auto by_begin = [&](std::uint32_t lhs, std::uint32_t rhs) {
+    return positions_[lhs].first < positions_[rhs].first;
+  };
+  if (std::getenv("ORC_WINDOW_UNSTABLE_SORT")) {  // experiment knob
+    std::sort(rank.begin() + 1, rank.end(), by_begin);
+  } else {
+    std::stable_sort(rank.begin() + 1, rank.end(), by_begin);
+  }
 
   const std::uint32_t offset = 0.01 * sequences_.front().second;
   for (std::uint32_t j = 1; j < sequences_.size(); ++j) {

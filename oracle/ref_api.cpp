@@ -15,7 +15,10 @@
 
 #include "flat_api.hpp"
 #include "ram/minimizer_engine.hpp"
+#include "raven/graph/assemble.h"
+#include "raven/graph/common.h"
 #include "raven/graph/construct.h"
+#include "raven/graph/polish.hpp"
 #include "raven/graph/overlap_utils.h"
 #include "raven/graph/serialization/binary.h"
 #include "raven/pile.h"
@@ -130,6 +133,42 @@ ORC_EXPORT void ref_kmer_complexity(orc_reads* r, const std::uint32_t* read_inde
     cereal::access::member_serialize(probe, p);
     keep[t] = probe.any;
   }
+}
+
+// The reference's only golden value: RavenTest.Assemble
+// (RavenTest/src/raven_test.cpp:50-67) = ConstructGraph(useMinhash) ->
+// Assemble -> Polish(2 rounds, m3 n-5 g-4) on the lambda reads, then the edit
+// distance of the reverse-complemented first unitig to NC_001416 (1137).
+// The reference's own construct/assemble/polish/common sources run here over
+// the oracle restatements of ram / racon / spoa / edlib.
+ORC_EXPORT orc_bag* ref_assemble(orc_reads* r, int minhash, std::uint32_t rounds,
+                                 std::uint32_t threads) {
+  biosoup::NucleicAcid::num_objects = r->seqs.size();
+  raven::Graph graph;
+  auto pool = std::make_shared<thread_pool::ThreadPool>(threads ? threads : 1);
+  raven::OverlapPhaseCfg cfg{};
+  cfg.useMinhash = minhash != 0;
+  raven::ConstructGraph(graph, r->seqs, pool, false, cfg);
+  raven::Assemble(pool, graph, false);
+  raven::PolishCfg pcfg{};
+  pcfg.num_rounds = rounds;
+  raven::Polish(pool, graph, false, r->seqs, pcfg);
+  auto unitigs = raven::GetUnitigs(graph);
+  auto* bag = new orc_bag();
+  std::vector<char> flat;
+  std::vector<std::uint64_t> off{0};
+  std::vector<char> names;
+  for (const auto& u : unitigs) {
+    auto s = u->InflateData();
+    flat.insert(flat.end(), s.begin(), s.end());
+    off.emplace_back(flat.size());
+    names.insert(names.end(), u->name.begin(), u->name.end());
+    names.push_back('\n');
+  }
+  bag->Put("unitigs", flat);
+  bag->Put("unitig_off", off);
+  bag->Put("names", names);
+  return bag;
 }
 
 ORC_EXPORT std::uint32_t ref_overlap_length(const std::uint32_t* o) {

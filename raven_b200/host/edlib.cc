@@ -1,10 +1,11 @@
 // raven-b200 host-side implementation of the `edlib` C surface the reference
 // calls (include/edlib.h). Exact global (NW) edit distance by Myers/Hyyro
-// bit-vector blocks; prefix (SHW) and infix (HW) modes come from the same
-// recurrence with different boundary conditions (only NW is on the
-// reference's path and only NW is served). The edit distance is unique, so
-// any exact algorithm is bit-identical with upstream edlib on `editDistance`
-// (reference use: construct.cc:190-199,407-416 - identity = 1 - ed/max(len)).
+// bit-vector blocks (only the NW mode is on the reference's path and only NW
+// is served). The edit distance is unique, so any exact algorithm is
+// bit-identical with upstream edlib on `editDistance` (reference use:
+// construct.cc:190-199,407-416 - identity = 1 - ed/max(len)). EDLIB_TASK_PATH
+// (used by the polisher for the read-to-unitig alignment) walks back over the
+// stored vertical deltas.
 #include "edlib.h"
 
 #include <algorithm>
@@ -48,9 +49,17 @@ inline int Step(std::uint64_t eq, int hin, std::uint64_t high,
   return hout;
 }
 
+// Column-wise state kept for the traceback: vertical deltas of every block and
+// the cell value at the bottom of every block, after each target column.
+struct Trace {
+  int blocks = 0;
+  std::vector<std::uint64_t> pv, mv;  // [column][block]
+  std::vector<std::int32_t> bottom;   // [column][block] = D[last row of block][column]
+};
+
 // Global distance between query (rows) and target (columns).
 int GlobalDistance(const unsigned char* q, int m, const unsigned char* t,
-                   int n) {
+                   int n, Trace* trace = nullptr) {
   if (m == 0) {
     return n;
   }
@@ -67,17 +76,30 @@ int GlobalDistance(const unsigned char* q, int m, const unsigned char* t,
   const std::uint64_t last_high = 1ULL << (last_bits - 1);
 
   std::vector<std::uint64_t> pv(blocks, ~0ULL), mv(blocks, 0);
-  int score = m;
+  std::vector<std::int32_t> bottom(blocks);
+  for (int b = 0; b < blocks; ++b) bottom[b] = std::min(m, (b + 1) * kWord);
+  if (trace) {
+    trace->blocks = blocks;
+    trace->pv.resize(static_cast<std::size_t>(n) * blocks);
+    trace->mv.resize(static_cast<std::size_t>(n) * blocks);
+    trace->bottom.resize(static_cast<std::size_t>(n) * blocks);
+  }
   for (int j = 0; j < n; ++j) {
     const std::uint64_t* eq = peq.data() + static_cast<std::size_t>(t[j]) * blocks;
     int h = 1;  // D[0][j] - D[0][j-1] = +1 in global mode
     for (int b = 0; b < blocks; ++b) {
       h = Step(eq[b], h, b == blocks - 1 ? last_high : (1ULL << 63), pv[b],
                mv[b]);
+      bottom[b] += h;
     }
-    score += h;
+    if (trace) {
+      const std::size_t at = static_cast<std::size_t>(j) * blocks;
+      std::copy(pv.begin(), pv.end(), trace->pv.begin() + at);
+      std::copy(mv.begin(), mv.end(), trace->mv.begin() + at);
+      std::copy(bottom.begin(), bottom.end(), trace->bottom.begin() + at);
+    }
   }
-  return score;
+  return bottom[blocks - 1];
 }
 
 }  // namespace
@@ -123,13 +145,9 @@ EdlibAlignResult edlibAlign(const char* query, int queryLength,
     for (bool s : seen) r.alphabetLength += s;
   }
 
-  if (config.task == EDLIB_TASK_PATH) {
-    // alignment paths are produced by the polish engine's own aligner
-    // (raven_b200/host/nw_path.cc); this entry point serves distances
-    r.status = EDLIB_STATUS_ERROR;
-    return r;
-  }
-  int d = GlobalDistance(q, queryLength, t, targetLength);
+  const bool want_path = config.task == EDLIB_TASK_PATH;
+  Trace trace;
+  int d = GlobalDistance(q, queryLength, t, targetLength, want_path ? &trace : nullptr);
   if (config.k >= 0 && d > config.k) {
     return r;  // editDistance stays -1
   }
@@ -140,6 +158,54 @@ EdlibAlignResult edlibAlign(const char* query, int queryLength,
   r.endLocations[0] = targetLength - 1;
   r.startLocations[0] = 0;
 
+  if (want_path) {
+    // Walk back from (m, n). Among equally good moves: up (a query symbol
+    // alone, EDLIB_EDOP_INSERT), then left (a target symbol alone,
+    // EDLIB_EDOP_DELETE), then the diagonal - the order we recall of edlib's
+    // own traceback (upstream's choice is not pinned by the reference tree).
+    const int m = queryLength, n = targetLength;
+    auto cell = [&](int i, int j) -> int {  // D[i][j], i rows of query, j columns
+      if (j == 0) return i;
+      if (i == 0) return j;
+      const int b = (i - 1) / kWord;
+      const std::size_t at = static_cast<std::size_t>(j - 1) * trace.blocks + b;
+      const int last_row = std::min(m, (b + 1) * kWord);  // 1-based row of the block bottom
+      // rows i+1 .. last_row lie below cell i inside the block
+      const int below = last_row - i;
+      int v = trace.bottom[at];
+      if (below > 0) {
+        const int lo_bit = (i - 1) % kWord + 1;  // first bit below row i
+        const std::uint64_t mask = (below >= 64 ? ~0ULL : ((1ULL << below) - 1)) << lo_bit;
+        v -= __builtin_popcountll(trace.pv[at] & mask);
+        v += __builtin_popcountll(trace.mv[at] & mask);
+      }
+      return v;
+    };
+    std::vector<unsigned char> ops;
+    ops.reserve(static_cast<std::size_t>(m) + n);
+    int i = m, j = n, cur = d;
+    while (i > 0 || j > 0) {
+      if (i > 0 && cell(i - 1, j) + 1 == cur) {
+        ops.push_back(EDLIB_EDOP_INSERT);
+        --i;
+        --cur;
+      } else if (j > 0 && cell(i, j - 1) + 1 == cur) {
+        ops.push_back(EDLIB_EDOP_DELETE);
+        --j;
+        --cur;
+      } else {
+        const bool eq = q[i - 1] == t[j - 1];
+        ops.push_back(eq ? EDLIB_EDOP_MATCH : EDLIB_EDOP_MISMATCH);
+        --i;
+        --j;
+        if (!eq) --cur;
+      }
+    }
+    std::reverse(ops.begin(), ops.end());
+    r.alignmentLength = static_cast<int>(ops.size());
+    r.alignment = static_cast<unsigned char*>(std::malloc(ops.size() + 1));
+    std::memcpy(r.alignment, ops.data(), ops.size());
+  }
   return r;
 }
 

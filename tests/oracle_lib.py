@@ -255,3 +255,16 @@ class Reference(_Flat):
         o = np.ascontiguousarray(overlaps, dtype=np.uint32).reshape(-1, 8)
         bag = self.lib.ref_pile_add_layers(read_id, length, _ptr(o, _U32P), o.shape[0], rounds)
         return self.unbag(bag, dict(pile=np.uint16))["pile"]
+
+
+def ref_assemble(ref, rs, minhash=True, rounds=2, threads=4):
+    """RavenTest.Assemble through the compiled reference sources (oracle/_ref)."""
+    ref.lib.ref_assemble.restype = C.c_void_p
+    ref.lib.ref_assemble.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32]
+    reads = ref.reads(rs)
+    bag = ref.lib.ref_assemble(reads.h, int(minhash), rounds, threads)
+    r = ref.unbag(bag, dict(unitigs=np.uint8, unitig_off=np.uint64, names=np.uint8))
+    names = r["names"].tobytes().decode().split("\n")[:-1]
+    seqs = [r["unitigs"][int(r["unitig_off"][i]):int(r["unitig_off"][i + 1])].tobytes()
+            for i in range(len(names))]
+    return names, seqs

@@ -64,3 +64,31 @@ def test_dropin_synthetic_small_kmax(tmp_path, oracle):
     for got in (a, b):
         for key in ("overlaps", "ovl_off", "pile", "pile_off"):
             assert np.array_equal(got[key], want[key]), key
+
+
+def test_full_pipeline_on_b200_equals_oracle_pipeline(tmp_path, oracle, reference, lambda_reads):
+    """RavenTest.Assemble with the reference's own sources on the B200 facades
+    (ram::MinimizerEngine, racon::Polisher incl. GPU POA) == the same sources over
+    the CPU oracle: identical polished unitig, 1141 edits to NC_001416 (golden 1137)."""
+    import oracle_lib
+    from raven_b200 import seqio
+    binary = os.path.join(HERE, "cpp", "_build", "assemble_test")
+    if not os.path.exists(binary):
+        pytest.skip("tests/cpp/_build/assemble_test not built")
+    inp, out = str(tmp_path / "reads.bin"), str(tmp_path / "unitigs.txt")
+    with open(inp, "wb") as f:
+        write_vec(f, lambda_reads.words.astype(np.uint64))
+        write_vec(f, lambda_reads.word_off.astype(np.uint64))
+        write_vec(f, lambda_reads.lens.astype(np.uint32))
+        write_vec(f, lambda_reads.block_quality.astype(np.uint8))
+        write_vec(f, lambda_reads.bq_off.astype(np.uint64))
+    subprocess.run([binary, inp, out, "1", "2"], check=True, stderr=subprocess.DEVNULL,
+                   timeout=900)
+    lines = open(out).read().split("\n")
+    names, seqs = lines[0:-1:2], [s.encode() for s in lines[1::2]]
+    want_names, want_seqs = oracle_lib.ref_assemble(reference, lambda_reads, True, 2, 8)
+    assert names == want_names
+    assert seqs == want_seqs
+    genome = seqio.ReadSet.load(os.path.join(HERE, "golden", "lambda_genome.npz")).ascii(0)
+    rc = seqs[0].translate(bytes.maketrans(b"ACGT", b"TGCA"))[::-1]
+    assert oracle.edit_distance(rc, genome) == 1141
