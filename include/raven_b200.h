@@ -206,6 +206,51 @@ int rvn_set_option(rvn_ctx* ctx, const char* name, int64_t value);
 int rvn_get_timings(rvn_ctx* ctx, const char* const** names,
                     const float** ms, uint32_t* n);
 
+/* ---- multi-GPU building blocks -------------------------------------------
+ * One context per rank (one process per GPU); the collectives between the
+ * steps are the caller's (raven_b200/distributed.py: torch.distributed over
+ * NCCL). Reads are owned by contiguous id ranges (read_bounds[n_parts + 1]),
+ * index keys by owner = value mod n_parts.
+ * Every d_* pointer is DEVICE memory owned by the context (valid until the
+ * next call on it) or by the caller (inputs). The sequence per index batch of
+ * raven::FindOverlapsAndCreatePiles (RavenLib/src/construct.cc:36-112):
+ *   sketch_split -> all-to-all -> index -> histogram -> all-reduce ->
+ *   set_occurrence -> hits_split -> all-to-all -> chain -> all-gather ->
+ *   stage1_add. Results through rvn_stage1_results on every rank. */
+int rvn_dist_sketch_split(rvn_ctx* ctx, uint32_t first, uint32_t last, int minhash,
+                          uint32_t n_parts, const uint64_t** d_value,
+                          const uint64_t** d_origin, uint64_t* counts);
+int rvn_dist_index(rvn_ctx* ctx, const uint64_t* d_value, const uint64_t* d_origin,
+                   uint64_t n_records, uint64_t index_bases);
+/* run-length histogram of this rank's keys (u64 bins; bin i = keys with i
+ * postings, last bin = longer runs) */
+int rvn_dist_histogram(rvn_ctx* ctx, const uint64_t** d_hist, uint32_t* n_bins,
+                       uint64_t* n_keys);
+/* MinimizerEngine::Filter on the summed (host) histogram: one global threshold */
+int rvn_dist_set_occurrence(rvn_ctx* ctx, const uint64_t* hist, uint64_t n_keys,
+                            double frequency, uint32_t* occurrence);
+/* seed hits of the received query records against this rank's keys, split by
+ * the owner of the query read; d_lhs = query read of every hit */
+int rvn_dist_hits_split(rvn_ctx* ctx, const uint64_t* d_qvalue,
+                        const uint64_t* d_qorigin, uint64_t n_queries,
+                        int avoid_equal, int avoid_symmetric, uint32_t n_parts,
+                        const uint32_t* read_bounds, const uint64_t** d_group,
+                        const uint64_t** d_positions, const uint32_t** d_lhs,
+                        uint64_t* counts);
+/* chains the hits of the owned reads [first,last): overlaps in query order
+ * and the number of overlaps of every owned read */
+int rvn_dist_chain(rvn_ctx* ctx, const uint64_t* d_group, const uint64_t* d_positions,
+                   const uint32_t* d_lhs, uint64_t n_hits, uint32_t first,
+                   uint32_t last, const rvn_overlap** d_overlaps,
+                   const uint32_t** d_counts, uint64_t* n_overlaps);
+/* piles + per-read overlap lists from the complete ordered overlap list of
+ * queries [0, n_query) of one index batch (overlap_off: host, n_query + 1) */
+int rvn_dist_stage1_begin(rvn_ctx* ctx);
+int rvn_dist_stage1_add(rvn_ctx* ctx, const rvn_overlap* d_overlaps,
+                        const uint64_t* overlap_off, uint32_t n_query,
+                        uint64_t max_overlaps, uint64_t query_batch_bases);
+int rvn_dist_stage1_end(rvn_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

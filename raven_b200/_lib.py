@@ -71,6 +71,24 @@ SIGNATURES = {
     "rvn_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "rvn_get_timings": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(C.c_char_p)),
                                   C.POINTER(C.POINTER(C.c_float)), U32P]),
+    "rvn_dist_sketch_split": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
+                                        C.c_uint32, C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_void_p), U64P]),
+    "rvn_dist_index": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                 C.c_uint64]),
+    "rvn_dist_histogram": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), U32P, U64P]),
+    "rvn_dist_set_occurrence": (C.c_int, [C.c_void_p, U64P, C.c_uint64, C.c_double, U32P]),
+    "rvn_dist_hits_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                      C.c_int, C.c_int, C.c_uint32, U32P,
+                                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                      C.POINTER(C.c_void_p), U64P]),
+    "rvn_dist_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_uint64, C.c_uint32, C.c_uint32,
+                                 C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), U64P]),
+    "rvn_dist_stage1_begin": (C.c_int, [C.c_void_p]),
+    "rvn_dist_stage1_add": (C.c_int, [C.c_void_p, C.c_void_p, U64P, C.c_uint32,
+                                      C.c_uint64, C.c_uint64]),
+    "rvn_dist_stage1_end": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

@@ -104,7 +104,7 @@ void Stage1(Ctx& c, double freq, uint64_t kmax, bool minhash, uint64_t ib,
       MapRange(c, k0, k + 1, true, true, true, false, /*fetch=*/false);
       PileAddLayersDevice(c, d_pile, d_poff, c.st_pile_off.data(), n,
                           c.m_ovl.get(), c.r_n_ovl);
-      GatherFlush(c, k0, k + 1, kmax);
+      GatherFlush(c, c.m_ovl.get(), c.m_ovl_off.get(), c.r_n_ovl, k0, k + 1, kmax);
       c.st_mapped += c.r_n_ovl;
       k0 = k + 1;
     }
@@ -538,6 +538,115 @@ RVN_API int rvn_get_timings(rvn_ctx* ctx, const char* const** names,
     if (ms) *ms = c.timer.ms.data();
     if (n) *n = static_cast<uint32_t>(c.timer.names.size());
   });
+}
+
+// ---- multi-GPU building blocks (dist.cu); device pointers in and out ----
+RVN_API int rvn_dist_sketch_split(rvn_ctx* ctx, uint32_t first, uint32_t last,
+                                  int minhash, uint32_t n_parts,
+                                  const uint64_t** d_value, const uint64_t** d_origin,
+                                  uint64_t* counts) {
+  return Guard(ctx, [&](Ctx& c) {
+    CheckRange(c, first, last);
+    if (!d_value || !d_origin || !counts) throw InvalidArgument("null output");
+    DistSketchSplit(c, first, last, minhash ? 1 : 0, n_parts, d_value, d_origin, counts);
+  });
+}
+
+RVN_API int rvn_dist_index(rvn_ctx* ctx, const uint64_t* d_value,
+                           const uint64_t* d_origin, uint64_t n_records,
+                           uint64_t index_bases) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (n_records && (!d_value || !d_origin)) throw InvalidArgument("null records");
+    c.i_first = c.i_last = 0;
+    BuildIndexFrom(c, d_value, d_origin, n_records, index_bases);
+    RVN_CUDA(cudaStreamSynchronize(c.stream));
+  });
+}
+
+RVN_API int rvn_dist_histogram(rvn_ctx* ctx, const uint64_t** d_hist, uint32_t* n_bins,
+                               uint64_t* n_keys) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (!c.i_valid) throw StateError("Filter before Minimize");
+    if (!d_hist) throw InvalidArgument("null output");
+    *d_hist = IndexHistogram(c);
+    RVN_CUDA(cudaStreamSynchronize(c.stream));
+    if (n_bins) *n_bins = 65536;
+    if (n_keys) *n_keys = c.i_keys;
+  });
+}
+
+RVN_API int rvn_dist_set_occurrence(rvn_ctx* ctx, const uint64_t* hist, uint64_t n_keys,
+                                    double frequency, uint32_t* occurrence) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (!(0 <= frequency && frequency <= 1)) {
+      throw InvalidArgument("[ram::MinimizerEngine::Filter] error: invalid frequency");
+    }
+    if (!c.i_valid) throw StateError("Filter before Minimize");
+    if (frequency == 0 || n_keys == 0) {
+      c.occurrence = 0xFFFFFFFFu;
+    } else {
+      if (!hist) throw InvalidArgument("null histogram");
+      bool long_runs = false;
+      const uint32_t occ = ThresholdFromHistogram(c, hist, n_keys, frequency, &long_runs);
+      if (long_runs) throw LimitError("occurrence threshold above 65534 postings");
+      c.occurrence = occ;
+    }
+    if (occurrence) *occurrence = c.occurrence;
+  });
+}
+
+RVN_API int rvn_dist_hits_split(rvn_ctx* ctx, const uint64_t* d_qvalue,
+                                const uint64_t* d_qorigin, uint64_t n_queries,
+                                int avoid_equal, int avoid_symmetric, uint32_t n_parts,
+                                const uint32_t* read_bounds, const uint64_t** d_group,
+                                const uint64_t** d_positions, const uint32_t** d_lhs,
+                                uint64_t* counts) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (!read_bounds || !d_group || !d_positions || !d_lhs || !counts) {
+      throw InvalidArgument("null argument");
+    }
+    if (n_queries && (!d_qvalue || !d_qorigin)) throw InvalidArgument("null queries");
+    DistHitsSplit(c, d_qvalue, d_qorigin, n_queries, avoid_equal != 0,
+                  avoid_symmetric != 0, n_parts, read_bounds, d_group, d_positions, d_lhs,
+                  counts);
+  });
+}
+
+RVN_API int rvn_dist_chain(rvn_ctx* ctx, const uint64_t* d_group,
+                           const uint64_t* d_positions, const uint32_t* d_lhs,
+                           uint64_t n_hits, uint32_t first, uint32_t last,
+                           const rvn_overlap** d_overlaps, const uint32_t** d_counts,
+                           uint64_t* n_overlaps) {
+  return Guard(ctx, [&](Ctx& c) {
+    CheckRange(c, first, last);
+    if (n_hits && (!d_group || !d_positions || !d_lhs)) throw InvalidArgument("null hits");
+    if (!d_overlaps || !d_counts || !n_overlaps) throw InvalidArgument("null output");
+    DistChainOwned(c, d_group, d_positions, d_lhs, n_hits, first, last, d_overlaps,
+                   d_counts, n_overlaps);
+  });
+}
+
+RVN_API int rvn_dist_stage1_begin(rvn_ctx* ctx) {
+  return Guard(ctx, [&](Ctx& c) {
+    c.s_valid = c.q_valid = c.i_valid = c.r_valid = false;
+    TimerReset(c);
+    std::memset(&c.stats, 0, sizeof(c.stats));
+    DistStage1Begin(c);
+  });
+}
+
+RVN_API int rvn_dist_stage1_add(rvn_ctx* ctx, const rvn_overlap* d_overlaps,
+                                const uint64_t* overlap_off, uint32_t n_query,
+                                uint64_t max_overlaps, uint64_t query_batch_bases) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (!overlap_off) throw InvalidArgument("null offsets");
+    if (overlap_off[n_query] && !d_overlaps) throw InvalidArgument("null overlaps");
+    DistStage1Add(c, d_overlaps, overlap_off, n_query, max_overlaps, query_batch_bases);
+  });
+}
+
+RVN_API int rvn_dist_stage1_end(rvn_ctx* ctx) {
+  return Guard(ctx, [&](Ctx& c) { DistStage1End(c); });
 }
 
 }  // extern "C"

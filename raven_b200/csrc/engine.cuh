@@ -152,6 +152,11 @@ struct Ctx {
   uint64_t st_mapped = 0;
   bool st_valid = false;
 
+  // ---- multi-GPU partition / exchange staging (dist.cu) ----
+  DevBuf<uint64_t> ds_split_val, ds_split_org, ds_qsplit_val, ds_qsplit_org;
+  DevBuf<uint64_t> ds_grouped_grp, ds_grouped_pos, ds_rel_off;
+  DevBuf<uint32_t> ds_masked, ds_hit_lhs, ds_read_cnt, ds_read_cursor, ds_ovl_cnt;
+
   // pinned scalars for small D2H reads
   PinBuf<uint64_t> pin64;
 
@@ -179,6 +184,13 @@ void EnsureMicromizers(Ctx& c, uint32_t first, uint32_t last);
 
 // ---- index.cu ----
 void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash);
+// index from device records already in (read, position) order
+void BuildIndexFrom(Ctx& c, const uint64_t* src_val, const uint64_t* src_org, uint64_t n,
+                    uint64_t index_bases);
+// run-length histogram of the index keys into c.m_counter (65536 u64 bins)
+uint64_t* IndexHistogram(Ctx& c);
+uint32_t ThresholdFromHistogram(Ctx& c, const uint64_t* h_hist, uint64_t n_keys,
+                                double frequency, bool* needs_long_runs);
 uint32_t FilterIndex(Ctx& c, double frequency);
 
 // ---- map.cu ----
@@ -188,10 +200,34 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
               bool avoid_symmetric, bool minhash, bool want_filtered,
               bool fetch = true);
 
+// chains hits grouped by query read (see map.cu); overlaps land in c.m_ovl
+uint64_t ChainGroupedHits(Ctx& c, const uint64_t* hg, const uint64_t* hp,
+                          const uint64_t* read_hit_off,
+                          const std::vector<uint64_t>& h_rho, uint32_t first,
+                          uint32_t nr, uint64_t n_hits, uint64_t n_q);
+
 // ---- gather.cu ----
 void GatherReset(Ctx& c);
-void GatherFlush(Ctx& c, uint32_t k0, uint32_t k1, uint64_t kmax);
+void GatherFlush(Ctx& c, const rvn_overlap* ovl, const uint64_t* q_ovl_off,
+                 uint64_t m, uint32_t k0, uint32_t k1, uint64_t kmax);
 void GatherFetch(Ctx& c);
+
+// ---- dist.cu ---- key-partitioned index / read-partitioned chaining
+// which: 0 = full minimizers, 1 = micromizers; records of reads [first,last)
+// stably split by key owner; counts[parts]
+void DistSketchSplit(Ctx& c, uint32_t first, uint32_t last, int which, uint32_t parts,
+                     const uint64_t** d_val, const uint64_t** d_org, uint64_t* counts);
+void DistHitsSplit(Ctx& c, const uint64_t* d_qval, const uint64_t* d_qorg, uint64_t n_q,
+                   bool avoid_equal, bool avoid_symmetric, uint32_t parts,
+                   const uint32_t* h_bounds, const uint64_t** d_grp,
+                   const uint64_t** d_pos, const uint32_t** d_lhs, uint64_t* counts);
+void DistChainOwned(Ctx& c, const uint64_t* d_grp, const uint64_t* d_pos,
+                    const uint32_t* d_lhs, uint64_t n_hits, uint32_t first, uint32_t last,
+                    const rvn_overlap** d_ovl, const uint32_t** d_ovl_cnt, uint64_t* n_ovl);
+void DistStage1Begin(Ctx& c);
+void DistStage1Add(Ctx& c, const rvn_overlap* d_ovl, const uint64_t* h_ovl_off,
+                   uint32_t n_query, uint64_t kmax, uint64_t qb);
+void DistStage1End(Ctx& c);
 
 // ---- pile.cu ----
 // data: device u16 bins, off: device u64 offsets (n_piles + 1)

@@ -164,18 +164,16 @@ void GatherReset(Ctx& c) {
   RVN_CUDA(cudaMemsetAsync(off, 0, (n + 2ULL) * sizeof(uint64_t), c.stream));
 }
 
-// consumes the ordered overlaps of the last MapRange(k0, k1): c.m_ovl,
-// c.m_ovl_off (per query of the range), c.r_n_ovl
-void GatherFlush(Ctx& c, uint32_t k0, uint32_t k1, uint64_t kmax) {
+// one flush of the reference's gather: `ovl` holds the m64 overlaps mapped for
+// the queries [k0, k1) in query order, q_ovl_off their per-query offsets
+// (relative to ovl, k1 - k0 + 1 entries); both on the device
+void GatherFlush(Ctx& c, const rvn_overlap* ovl, const uint64_t* q_ovl_off,
+                 uint64_t m64, uint32_t k0, uint32_t k1, uint64_t kmax) {
   const uint32_t n = c.n_reads;
-  const uint64_t m64 = c.r_n_ovl;
   if (m64 == 0) return;
   if (m64 >= 0xFFFFFFFFULL) throw LimitError("2^32 or more overlaps in one flush");
   const uint32_t m = static_cast<uint32_t>(m64);
   TimerBegin(c, "gather");
-  const rvn_overlap* ovl = c.m_ovl.get();
-  const uint64_t* q_ovl_off = c.m_ovl_off.get();
-
   // arrival order of the mirrored records: overlap indices stably sorted by rhs
   uint32_t* key = c.g_key.reserve(m);
   uint32_t* idx = c.g_idx.reserve(m);

@@ -112,12 +112,21 @@ void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash) {
     src_org = c.q_org.get();
     n = c.q_n;
   }
+  uint64_t bases = 0;
+  for (uint32_t r = first; r < last; ++r) bases += c.h_len[r];
+  c.i_first = first;
+  c.i_last = last;
+  BuildIndexFrom(c, src_val, src_org, n, bases);
+}
+
+void BuildIndexFrom(Ctx& c, const uint64_t* src_val, const uint64_t* src_org, uint64_t n,
+                    uint64_t index_bases) {
+  c.i_valid = false;
+  c.occurrence = 0xFFFFFFFFu;
   if (n >= 0xFFFFFFFFULL) {
     throw LimitError("index batch holds 2^32 or more minimizers");
   }
   c.i_n = n;
-  c.i_first = first;
-  c.i_last = last;
   c.i_keys = 0;
 
   TimerBegin(c, "index_sort");
@@ -184,11 +193,42 @@ void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash) {
   }
   TimerEnd(c);
 
-  c.stats.index_bases = 0;
-  for (uint32_t r = first; r < last; ++r) c.stats.index_bases += c.h_len[r];
+  c.stats.index_bases = index_bases;
   c.stats.index_records = n;
   c.stats.index_keys = c.i_keys;
   c.i_valid = true;
+}
+
+uint64_t* IndexHistogram(Ctx& c) {
+  static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
+  uint64_t* hist = c.m_counter.reserve(kHistBins + 8);
+  RVN_CUDA(cudaMemsetAsync(hist, 0, (kHistBins + 8) * sizeof(uint64_t), c.stream));
+  if (c.i_keys) {
+    RunLengthHistogram<<<std::min<unsigned>(CeilDiv(c.i_keys, kThreads), 148 * 16),
+                         kThreads, 0, c.stream>>>(
+        c.i_run_start.get(), c.i_keys, c.i_n,
+        reinterpret_cast<unsigned long long*>(hist));
+    RVN_LAUNCH_CHECK();
+    ++c.launches;
+  }
+  return hist;
+}
+
+// same arithmetic as the reference engine: index = (1 - f) * #keys, truncated
+// towards zero; the value at that ascending rank, plus one
+uint32_t ThresholdFromHistogram(Ctx& c, const uint64_t* h, uint64_t n_keys,
+                                double frequency, bool* needs_long_runs) {
+  (void)c;
+  *needs_long_runs = false;
+  std::size_t rank = static_cast<std::size_t>((1 - frequency) * static_cast<double>(n_keys));
+  if (rank >= n_keys) rank = n_keys - 1;
+  uint64_t cum = 0;
+  for (uint32_t len = 0; len + 1 < kHistBins; ++len) {
+    cum += h[len];
+    if (cum > rank) return len + 1;
+  }
+  *needs_long_runs = true;  // the rank falls among runs of >= 65535 postings
+  return 0;
 }
 
 // occurrence_ = (run length at ascending rank (1-f)*#keys) + 1
@@ -203,39 +243,19 @@ uint32_t FilterIndex(Ctx& c, double frequency) {
     return c.occurrence;
   }
   TimerBegin(c, "filter");
-  static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
-  uint64_t* hist = c.m_counter.reserve(kHistBins + 8);
-  RVN_CUDA(cudaMemsetAsync(hist, 0, (kHistBins + 8) * sizeof(uint64_t), c.stream));
-  RunLengthHistogram<<<std::min<unsigned>(CeilDiv(c.i_keys, kThreads), 148 * 16),
-                       kThreads, 0, c.stream>>>(
-      c.i_run_start.get(), c.i_keys, c.i_n,
-      reinterpret_cast<unsigned long long*>(hist));
-  RVN_LAUNCH_CHECK();
-  ++c.launches;
+  uint64_t* hist = IndexHistogram(c);
   TimerEnd(c);
   std::vector<uint64_t> h(kHistBins);
   RVN_CUDA(cudaMemcpyAsync(h.data(), hist, kHistBins * sizeof(uint64_t),
                            cudaMemcpyDeviceToHost, c.stream));
   RVN_CUDA(cudaStreamSynchronize(c.stream));
-
-  // same arithmetic as the reference engine: index = (1 - f) * #keys,
-  // truncated towards zero
-  std::size_t rank = static_cast<std::size_t>((1 - frequency) *
-                                              static_cast<double>(c.i_keys));
-  if (rank >= c.i_keys) rank = c.i_keys - 1;
-  uint64_t cum = 0;
-  uint32_t value = 0;
-  bool found = false;
-  for (uint32_t len = 0; len + 1 < kHistBins; ++len) {
-    cum += h[len];
-    if (cum > rank) {
-      value = len;
-      found = true;
-      break;
-    }
-  }
-  if (!found) {
-    // the rank falls among runs of >= 65535 postings: order those exactly
+  bool long_runs = false;
+  uint32_t occ = ThresholdFromHistogram(c, h.data(), c.i_keys, frequency, &long_runs);
+  if (long_runs) {
+    uint64_t cum = 0;
+    for (uint32_t len = 0; len + 1 < kHistBins; ++len) cum += h[len];
+    std::size_t rank = static_cast<std::size_t>((1 - frequency) * static_cast<double>(c.i_keys));
+    if (rank >= c.i_keys) rank = c.i_keys - 1;
     const uint64_t n_long = h[kHistBins - 1];
     uint32_t* out = c.m_cnt.reserve(n_long + 1);
     RVN_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint64_t), c.stream));
@@ -249,9 +269,9 @@ uint32_t FilterIndex(Ctx& c, double frequency) {
                              cudaMemcpyDeviceToHost, c.stream));
     RVN_CUDA(cudaStreamSynchronize(c.stream));
     std::sort(lens.begin(), lens.end());
-    value = lens[rank - cum];
+    occ = lens[rank - cum] + 1;
   }
-  c.occurrence = value + 1;
+  c.occurrence = occ;
   c.stats.occurrence = c.occurrence;
   return c.occurrence;
 }

@@ -1028,128 +1028,13 @@ __global__ void ReorderOverlaps(const rvn_overlap* __restrict__ raw,
 
 }  // namespace
 
-void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
-              bool avoid_symmetric, bool minhash, bool want_filtered,
-              bool fetch) {
-  if (!c.i_valid) throw StateError("Map before Minimize");
-  c.r_valid = false;
-  const uint32_t nr = last - first;
-
-  // ---- query records ----
-  const uint64_t *qv, *qo, *d_read_off;
-  const std::vector<uint64_t>* h_read_off;
-  uint64_t off_base_read;  // index of `first` inside the offsets arrays
-  if (minhash) {
-    if (!(c.q_valid && c.q_first <= first && last <= c.q_last)) {
-      EnsureMicromizers(c, first, last);
-    }
-    qv = c.q_val.get();
-    qo = c.q_org.get();
-    d_read_off = c.q_off.get();
-    h_read_off = &c.h_q_off;
-    off_base_read = first - c.q_first;
-  } else {
-    if (!(c.s_valid && c.s_first <= first && last <= c.s_last)) {
-      EnsureSketch(c, first, last);
-    }
-    qv = c.s_val.get();
-    qo = c.s_org.get();
-    d_read_off = c.s_off.get();
-    h_read_off = &c.h_s_off;
-    off_base_read = first - c.s_first;
-  }
-  const uint64_t q_begin = (*h_read_off)[off_base_read];
-  const uint64_t n_q = (*h_read_off)[off_base_read + nr] - q_begin;
-
-  IndexView ix{c.i_val.get(), c.i_org.get(), c.i_bucket.get(), c.i_n,
-               static_cast<int>(2 * c.prm.k) - c.i_bucket_bits, c.occurrence};
-
-  // ---- probe + expand ----
-  TimerBegin(c, "probe");
-  uint32_t* cnt = c.m_cnt.reserve(n_q + 1);
-  uint32_t* frst = c.m_first.reserve(n_q + 1);
-  uint8_t* filt = c.m_filt.reserve(n_q + 1);
-  uint64_t* hit_off = c.m_hit_off.reserve(n_q + 2);
-  uint64_t n_hits = 0;
-  if (n_q > 0) {
-    ProbeKernel<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
-        ix, qv, qo, q_begin, n_q, avoid_equal, avoid_symmetric, cnt, frst, filt);
-    RVN_LAUNCH_CHECK();
-    ++c.launches;
-    ExclusiveScanU32(c, cnt, hit_off, n_q);
-    n_hits = ReadU64(c, hit_off + n_q);
-  } else {
-    RVN_CUDA(cudaMemsetAsync(hit_off, 0, sizeof(uint64_t), c.stream));
-  }
-  TimerEnd(c);
-  TimerBegin(c, "expand");
-  uint64_t* hg = c.h_grp.reserve(n_hits + 1);
-  uint64_t* hp = c.h_pos.reserve(n_hits + 1);
-  if (n_hits > 0) {
-    ExpandKernel<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
-        ix, qv, qo, q_begin, n_q, avoid_equal, avoid_symmetric, cnt, frst,
-        hit_off, hg, hp);
-    RVN_LAUNCH_CHECK();
-    ++c.launches;
-  }
-  // per-read hit ranges
-  uint64_t* read_hit_off = c.m_read_hit_off.reserve(nr + 2ULL);
-  GatherU64<<<CeilDiv(nr + 1ULL, kThreads), kThreads, 0, c.stream>>>(
-      hit_off, d_read_off + off_base_read, q_begin, nr + 1ULL, read_hit_off);
-  RVN_LAUNCH_CHECK();
-  ++c.launches;
-  std::vector<uint64_t> h_rho(nr + 1ULL);
-  RVN_CUDA(cudaMemcpyAsync(h_rho.data(), read_hit_off,
-                           (nr + 1ULL) * sizeof(uint64_t),
-                           cudaMemcpyDeviceToHost, c.stream));
-  RVN_CUDA(cudaStreamSynchronize(c.stream));
-  TimerEnd(c);
-
-  // ---- filtered positions (stage 2 only) ----
-  c.r_filt_off.reserve(nr + 2ULL);
-  for (uint32_t i = 0; i <= nr; ++i) c.r_filt_off.get()[i] = 0;
-  uint64_t n_filtered = 0;
-  if (want_filtered && n_q > 0) {
-    uint32_t* f32 = c.m_first.get();  // `first` is dead after ExpandKernel
-    FilteredFlagsToU32<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
-        filt, n_q, f32);
-    uint64_t* fpos = c.m_filt_off.reserve(n_q + 2);
-    ExclusiveScanU32(c, f32, fpos, n_q);
-    n_filtered = ReadU64(c, fpos + n_q);
-    uint32_t* fout = c.m_filtered.reserve(n_filtered + 1);
-    ScatterFiltered<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
-        filt, fpos, qo, q_begin, n_q, fout);
-    RVN_LAUNCH_CHECK();
-    c.launches += 2;
-    // per-read offsets of the filtered list
-    uint64_t* froff = c.m_ovl_off.reserve(nr + 2ULL);
-    GatherU64<<<CeilDiv(nr + 1ULL, kThreads), kThreads, 0, c.stream>>>(
-        fpos, d_read_off + off_base_read, q_begin, nr + 1ULL, froff);
-    RVN_LAUNCH_CHECK();
-    ++c.launches;
-    uint32_t* hf = c.r_filtered.reserve(n_filtered + 1);
-    RVN_CUDA(cudaMemcpyAsync(hf, fout, n_filtered * sizeof(uint32_t),
-                             cudaMemcpyDeviceToHost, c.stream));
-    RVN_CUDA(cudaMemcpyAsync(c.r_filt_off.get(), froff,
-                             (nr + 1ULL) * sizeof(uint64_t),
-                             cudaMemcpyDeviceToHost, c.stream));
-    RVN_CUDA(cudaStreamSynchronize(c.stream));
-  }
-
-  if (c.keep_hits) {
-    uint64_t* g = c.r_hit_grp.reserve(n_hits + 1);
-    uint64_t* p = c.r_hit_pos.reserve(n_hits + 1);
-    uint64_t* o = c.r_hit_off.reserve(nr + 2ULL);
-    RVN_CUDA(cudaMemcpyAsync(g, hg, n_hits * sizeof(uint64_t),
-                             cudaMemcpyDeviceToHost, c.stream));
-    RVN_CUDA(cudaMemcpyAsync(p, hp, n_hits * sizeof(uint64_t),
-                             cudaMemcpyDeviceToHost, c.stream));
-    for (uint32_t i = 0; i <= nr; ++i) o[i] = h_rho[i];
-    RVN_CUDA(cudaStreamSynchronize(c.stream));
-    c.r_n_hits = n_hits;
-  }
-
-  // ---- chain ----
+// Chains hits that are already grouped by query read: hits of read i of the
+// range are h_grp/h_pos[read_hit_off[i] .. read_hit_off[i+1]) (any order inside
+// a read). Leaves the overlaps in query order in c.m_ovl / c.m_ovl_off.
+uint64_t ChainGroupedHits(Ctx& c, const uint64_t* hg, const uint64_t* hp,
+                          const uint64_t* read_hit_off,
+                          const std::vector<uint64_t>& h_rho, uint32_t first,
+                          uint32_t nr, uint64_t n_hits, uint64_t n_q) {
   TimerBegin(c, "chain");
   ChainParams cp{c.prm.k, c.prm.bandwidth, c.prm.chain, c.prm.matches, c.prm.gap};
   const uint32_t* lhs_ids = c.d_ids.get() + first;
@@ -1383,6 +1268,135 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
     ++c.launches;
   }
   TimerEnd(c);
+  return n_ovl;
+}
+
+void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
+              bool avoid_symmetric, bool minhash, bool want_filtered,
+              bool fetch) {
+  if (!c.i_valid) throw StateError("Map before Minimize");
+  c.r_valid = false;
+  const uint32_t nr = last - first;
+
+  // ---- query records ----
+  const uint64_t *qv, *qo, *d_read_off;
+  const std::vector<uint64_t>* h_read_off;
+  uint64_t off_base_read;  // index of `first` inside the offsets arrays
+  if (minhash) {
+    if (!(c.q_valid && c.q_first <= first && last <= c.q_last)) {
+      EnsureMicromizers(c, first, last);
+    }
+    qv = c.q_val.get();
+    qo = c.q_org.get();
+    d_read_off = c.q_off.get();
+    h_read_off = &c.h_q_off;
+    off_base_read = first - c.q_first;
+  } else {
+    if (!(c.s_valid && c.s_first <= first && last <= c.s_last)) {
+      EnsureSketch(c, first, last);
+    }
+    qv = c.s_val.get();
+    qo = c.s_org.get();
+    d_read_off = c.s_off.get();
+    h_read_off = &c.h_s_off;
+    off_base_read = first - c.s_first;
+  }
+  const uint64_t q_begin = (*h_read_off)[off_base_read];
+  const uint64_t n_q = (*h_read_off)[off_base_read + nr] - q_begin;
+
+  IndexView ix{c.i_val.get(), c.i_org.get(), c.i_bucket.get(), c.i_n,
+               static_cast<int>(2 * c.prm.k) - c.i_bucket_bits, c.occurrence};
+
+  // ---- probe + expand ----
+  TimerBegin(c, "probe");
+  uint32_t* cnt = c.m_cnt.reserve(n_q + 1);
+  uint32_t* frst = c.m_first.reserve(n_q + 1);
+  uint8_t* filt = c.m_filt.reserve(n_q + 1);
+  uint64_t* hit_off = c.m_hit_off.reserve(n_q + 2);
+  uint64_t n_hits = 0;
+  if (n_q > 0) {
+    ProbeKernel<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
+        ix, qv, qo, q_begin, n_q, avoid_equal, avoid_symmetric, cnt, frst, filt);
+    RVN_LAUNCH_CHECK();
+    ++c.launches;
+    ExclusiveScanU32(c, cnt, hit_off, n_q);
+    n_hits = ReadU64(c, hit_off + n_q);
+  } else {
+    RVN_CUDA(cudaMemsetAsync(hit_off, 0, sizeof(uint64_t), c.stream));
+  }
+  TimerEnd(c);
+  TimerBegin(c, "expand");
+  uint64_t* hg = c.h_grp.reserve(n_hits + 1);
+  uint64_t* hp = c.h_pos.reserve(n_hits + 1);
+  if (n_hits > 0) {
+    ExpandKernel<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
+        ix, qv, qo, q_begin, n_q, avoid_equal, avoid_symmetric, cnt, frst,
+        hit_off, hg, hp);
+    RVN_LAUNCH_CHECK();
+    ++c.launches;
+  }
+  // per-read hit ranges
+  uint64_t* read_hit_off = c.m_read_hit_off.reserve(nr + 2ULL);
+  GatherU64<<<CeilDiv(nr + 1ULL, kThreads), kThreads, 0, c.stream>>>(
+      hit_off, d_read_off + off_base_read, q_begin, nr + 1ULL, read_hit_off);
+  RVN_LAUNCH_CHECK();
+  ++c.launches;
+  std::vector<uint64_t> h_rho(nr + 1ULL);
+  RVN_CUDA(cudaMemcpyAsync(h_rho.data(), read_hit_off,
+                           (nr + 1ULL) * sizeof(uint64_t),
+                           cudaMemcpyDeviceToHost, c.stream));
+  RVN_CUDA(cudaStreamSynchronize(c.stream));
+  TimerEnd(c);
+
+  // ---- filtered positions (stage 2 only) ----
+  c.r_filt_off.reserve(nr + 2ULL);
+  for (uint32_t i = 0; i <= nr; ++i) c.r_filt_off.get()[i] = 0;
+  uint64_t n_filtered = 0;
+  if (want_filtered && n_q > 0) {
+    uint32_t* f32 = c.m_first.get();  // `first` is dead after ExpandKernel
+    FilteredFlagsToU32<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
+        filt, n_q, f32);
+    uint64_t* fpos = c.m_filt_off.reserve(n_q + 2);
+    ExclusiveScanU32(c, f32, fpos, n_q);
+    n_filtered = ReadU64(c, fpos + n_q);
+    uint32_t* fout = c.m_filtered.reserve(n_filtered + 1);
+    ScatterFiltered<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
+        filt, fpos, qo, q_begin, n_q, fout);
+    RVN_LAUNCH_CHECK();
+    c.launches += 2;
+    // per-read offsets of the filtered list
+    uint64_t* froff = c.m_ovl_off.reserve(nr + 2ULL);
+    GatherU64<<<CeilDiv(nr + 1ULL, kThreads), kThreads, 0, c.stream>>>(
+        fpos, d_read_off + off_base_read, q_begin, nr + 1ULL, froff);
+    RVN_LAUNCH_CHECK();
+    ++c.launches;
+    uint32_t* hf = c.r_filtered.reserve(n_filtered + 1);
+    RVN_CUDA(cudaMemcpyAsync(hf, fout, n_filtered * sizeof(uint32_t),
+                             cudaMemcpyDeviceToHost, c.stream));
+    RVN_CUDA(cudaMemcpyAsync(c.r_filt_off.get(), froff,
+                             (nr + 1ULL) * sizeof(uint64_t),
+                             cudaMemcpyDeviceToHost, c.stream));
+    RVN_CUDA(cudaStreamSynchronize(c.stream));
+  }
+
+  if (c.keep_hits) {
+    uint64_t* g = c.r_hit_grp.reserve(n_hits + 1);
+    uint64_t* p = c.r_hit_pos.reserve(n_hits + 1);
+    uint64_t* o = c.r_hit_off.reserve(nr + 2ULL);
+    RVN_CUDA(cudaMemcpyAsync(g, hg, n_hits * sizeof(uint64_t),
+                             cudaMemcpyDeviceToHost, c.stream));
+    RVN_CUDA(cudaMemcpyAsync(p, hp, n_hits * sizeof(uint64_t),
+                             cudaMemcpyDeviceToHost, c.stream));
+    for (uint32_t i = 0; i <= nr; ++i) o[i] = h_rho[i];
+    RVN_CUDA(cudaStreamSynchronize(c.stream));
+    c.r_n_hits = n_hits;
+  }
+
+  // ---- chain ----
+  const uint64_t n_ovl =
+      ChainGroupedHits(c, hg, hp, read_hit_off, h_rho, first, nr, n_hits, n_q);
+  const rvn_overlap* ordered = c.m_ovl.get();
+  const uint64_t* ooff = c.m_ovl_off.get();
 
   // ---- results to the host ----
   if (fetch) {
