@@ -13,8 +13,13 @@ Workload at N=1 = BASELINE.json configs[1]: 200k synthetic ONT reads ~10 kb
           construct.cc/pile.cc/overlap_utils.cc compiled in place, over the
           restated ram engine) on a bounded sample, all host threads.
 
-N>1 (torchrun): every rank runs the same-size workload on its own, seeded
-shard ("weak", no data-path collective); value = sum of overlaps / max time.
+N>1 (torchrun): the SAME 200k-read set (strong scaling: total work fixed),
+overlapped all-vs-all by all ranks together: reads sharded by id, index keys by
+value, all-to-all of minimizer records, of seed hits and of overlaps
+(raven_b200/distributed.py); value = all overlaps of the job / max-over-ranks
+device time. (N x reads would not be N x work: with k=15 the random-match
+part of the seed hits grows with the square of the read count - measured
+350 M hits/GPU at 200k reads, 604 M at 2 x 200k on 2 GPUs.)
 """
 from __future__ import annotations
 
@@ -166,7 +171,7 @@ def main_reference(a):
     out = {
         "impl": "reference", "metric": "overlaps/s", "value": v, "unit": "overlaps/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1),
-        "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": workload_name(a), "measured_on": sample,
                    "reference": "RavenLib construct.cc/pile.cc/overlap_utils.cc compiled "
@@ -196,9 +201,10 @@ def main_ours(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from bench import synth
-    from raven_b200 import engine
+    from raven_b200 import distributed, engine
 
-    rs = synth.make_reads(SEED + 1000 * rank, a.genome, a.reads, a.mean_len)
+    # every rank holds the same read set (N>1: strong scaling of one job)
+    rs = synth.make_reads(SEED, a.genome, a.reads, a.mean_len)
     # pinned host copies: the e2e leg uploads from these every step
     words = torch.from_numpy(rs.words.view(np.int64)).pin_memory()
     woff = torch.from_numpy(rs.word_off.view(np.int64)).pin_memory()
@@ -213,22 +219,32 @@ def main_ours(a):
     prs.lens = lens.numpy().view(np.uint32)
     prs.n = rs.n
 
-    stream = torch.cuda.current_stream()
-    eng = engine.Engine(device=local, stream=stream.cuda_stream)
-    eng.configure(K, W)
-    eng.upload(prs)
+    if world > 1:
+        de = distributed.DistEngine(f"cuda:{local}", k=K, w=W)
+        stream, eng = de.stream, de.engine
+        de.upload(prs)
+    else:
+        stream = torch.cuda.current_stream()
+        eng = engine.Engine(device=local, stream=stream.cuda_stream)
+        eng.configure(K, W)
+        eng.upload(prs)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    last = {}
+
     def step_resident():
-        eng.find_overlaps_and_create_piles(FREQ, KMAX, False, fetch=False)
+        if world > 1:
+            last.update(de.find_overlaps_and_create_piles(FREQ, KMAX, False, fetch=False))
+        else:
+            eng.find_overlaps_and_create_piles(FREQ, KMAX, False, fetch=False)
 
     def step_e2e():
-        eng.upload(prs)
-        eng.find_overlaps_and_create_piles(FREQ, KMAX, False, fetch=False)
+        (de if world > 1 else eng).upload(prs)
+        step_resident()
         # results are host-resident after the call (D2H inside the step)
 
     def timed(fn, steps):
@@ -251,7 +267,7 @@ def main_ours(a):
     sampler = ClockSampler(local) if rank == 0 else None
     eng.set_option("reset_stats", 1)
     ms_total = timed(step_resident, a.steps)
-    st = eng.stats()          # counters of the LAST step
+    st = eng.stats()          # counters of the LAST step (this rank's share)
     phases = eng.timings()    # device ms per phase of the LAST step
     launches_step = st["kernel_launches"]
     n_mapped = st["overlaps"]
@@ -285,19 +301,29 @@ def main_ours(a):
         if os.path.exists(prof):
             traffic = json.load(open(prof)).get(dom)
         h2d = int(prs.words.nbytes + prs.word_off.nbytes + prs.lens.nbytes)
-        res = eng.find_overlaps_and_create_piles(FREQ, KMAX, False, fetch=True)
-        d2h = int(res["overlaps"].nbytes + res["ovl_off"].nbytes + res["pile"].nbytes
-                  + n_mapped * 32)
+        if world > 1:
+            res = distributed.CudaSteps(eng, f"cuda:{local}").stage1_results()  # this rank's share
+            d2h = int(res["overlaps"].nbytes + res["ovl_off"].nbytes + res["pile"].nbytes)
+        else:
+            res = eng.find_overlaps_and_create_piles(FREQ, KMAX, False, fetch=True)
+            d2h = int(res["overlaps"].nbytes + res["ovl_off"].nbytes + res["pile"].nbytes
+                      + n_mapped * 32)
         out = {
             "metric": "overlaps/s", "value": total_mapped * a.steps / (ms_total * 1e-3),
             "unit": "overlaps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+            "scaling": "strong",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "reads_per_gpu": rs.n,
-                       "bases_per_gpu": int(rs.bases), "overlaps_per_step_per_gpu": n_mapped,
+            "config": {"workload": workload_name(a), "reads_per_gpu": rs.n // world,
+                       "bases_per_gpu": int(rs.bases) // world,
+                       "reads_total": rs.n, "overlaps_per_step": int(total_mapped),
                        "l2": "inputs (0.5 GB packed reads, 10.7 GB minimizer records) "
                              "exceed the 126 MB L2; no explicit flush",
-                       "parallelism": f"{world} independent shard(s), no collective"},
+                       "parallelism": "1 GPU" if world == 1 else
+                       f"{world} ranks: reads sharded by id, index keys by value mod "
+                       f"{world}, reads (queries, piles, lists) by id mod {world}; NCCL "
+                       "all-to-all of minimizer records, of seed hits and of overlaps; "
+                       "results stay sharded (d2h = this rank's share)"},
             "clocks": clocks,
             "e2e": {"value": total_mapped * a.steps / (ms_e2e * 1e-3), "unit": "overlaps/s",
                     "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d,
@@ -315,6 +341,8 @@ def main_ours(a):
                               "achieved": sum(alg.values()) / (ms_total / a.steps * 1e-3) / 1e9,
                               "frac": sum(alg.values()) / (ms_total / a.steps * 1e-3) / 1e9 / peak},
         }
+        if "trace_ms" in last:  # RVN_DIST_TRACE=1 (analysis run, not a bench value)
+            out["dist_trace_ms"] = {k: round(v, 2) for k, v in last["trace_ms"].items()}
         if world == 1 and a.poa_windows > 0:
             out["poa"] = bench_poa(eng, a, peak, not a.no_cpu_baseline)
         if world == 1 and not a.no_cpu_baseline:

@@ -209,14 +209,18 @@ int rvn_get_timings(rvn_ctx* ctx, const char* const** names,
 /* ---- multi-GPU building blocks -------------------------------------------
  * One context per rank (one process per GPU); the collectives between the
  * steps are the caller's (raven_b200/distributed.py: torch.distributed over
- * NCCL). Reads are owned by contiguous id ranges (read_bounds[n_parts + 1]),
- * index keys by owner = value mod n_parts.
- * Every d_* pointer is DEVICE memory owned by the context (valid until the
- * next call on it) or by the caller (inputs). The sequence per index batch of
+ * NCCL). With n_parts ranks: index keys are owned by value mod n_parts; a read
+ * (as a query, and its pile and overlap list) by id mod n_parts; sketching is
+ * split by any contiguous read ranges, ascending with the rank.
+ * Every d_* pointer is DEVICE memory, owned by the context (outputs: valid
+ * until the next call on it) or by the caller (inputs). Per index batch of
  * raven::FindOverlapsAndCreatePiles (RavenLib/src/construct.cc:36-112):
  *   sketch_split -> all-to-all -> index -> histogram -> all-reduce ->
- *   set_occurrence -> hits_split -> all-to-all -> chain -> all-gather ->
- *   stage1_add. Results through rvn_stage1_results on every rank. */
+ *   set_occurrence -> hits_split -> all-to-all -> chain -> overlaps_split ->
+ *   all-to-all -> stage1_add; then stage1_end and rvn_dist_stage1_results
+ *   (the piles and overlap lists of the reads this rank owns).
+ * "runs": an all-to-all delivers one run per source rank; run_off (host,
+ * n_runs + 1 entries) are their offsets in the received array. */
 int rvn_dist_sketch_split(rvn_ctx* ctx, uint32_t first, uint32_t last, int minhash,
                           uint32_t n_parts, const uint64_t** d_value,
                           const uint64_t** d_origin, uint64_t* counts);
@@ -229,27 +233,40 @@ int rvn_dist_histogram(rvn_ctx* ctx, const uint64_t** d_hist, uint32_t* n_bins,
 /* MinimizerEngine::Filter on the summed (host) histogram: one global threshold */
 int rvn_dist_set_occurrence(rvn_ctx* ctx, const uint64_t* hist, uint64_t n_keys,
                             double frequency, uint32_t* occurrence);
-/* seed hits of the received query records against this rank's keys, split by
- * the owner of the query read; d_lhs = query read of every hit */
+/* seed hits of the received query records (sorted by read id; reads
+ * [0, n_query_reads)) against this rank's keys, written as n_parts runs by the
+ * owner of the query read; d_lhs = query read of every hit */
 int rvn_dist_hits_split(rvn_ctx* ctx, const uint64_t* d_qvalue,
                         const uint64_t* d_qorigin, uint64_t n_queries,
                         int avoid_equal, int avoid_symmetric, uint32_t n_parts,
-                        const uint32_t* read_bounds, const uint64_t** d_group,
+                        uint32_t n_query_reads, const uint64_t** d_group,
                         const uint64_t** d_positions, const uint32_t** d_lhs,
                         uint64_t* counts);
-/* chains the hits of the owned reads [first,last): overlaps in query order
- * and the number of overlaps of every owned read */
+/* chains the hits of the owned reads below n_query_reads (runs sorted by query
+ * read): overlaps in query order */
 int rvn_dist_chain(rvn_ctx* ctx, const uint64_t* d_group, const uint64_t* d_positions,
-                   const uint32_t* d_lhs, uint64_t n_hits, uint32_t first,
-                   uint32_t last, const rvn_overlap** d_overlaps,
-                   const uint32_t** d_counts, uint64_t* n_overlaps);
-/* piles + per-read overlap lists from the complete ordered overlap list of
- * queries [0, n_query) of one index batch (overlap_off: host, n_query + 1) */
-int rvn_dist_stage1_begin(rvn_ctx* ctx);
+                   const uint32_t* d_lhs, uint64_t n_hits, uint32_t n_runs,
+                   const uint64_t* run_off, uint32_t n_parts, uint32_t rank,
+                   uint32_t n_query_reads, const rvn_overlap** d_overlaps,
+                   uint64_t* n_overlaps);
+/* the overlaps of the last rvn_dist_chain as n_parts runs: run d != rank holds
+ * those whose rhs read rank d owns, run `rank` holds all of them */
+int rvn_dist_overlaps_split(rvn_ctx* ctx, uint32_t n_parts, uint32_t rank,
+                            const rvn_overlap** d_overlaps, uint64_t* counts);
+/* piles + per-read overlap lists of the owned reads: begin once, add once per
+ * index batch (runs sorted by query read; reference flush schedule), end */
+int rvn_dist_stage1_begin(rvn_ctx* ctx, uint32_t n_parts, uint32_t rank);
 int rvn_dist_stage1_add(rvn_ctx* ctx, const rvn_overlap* d_overlaps,
-                        const uint64_t* overlap_off, uint32_t n_query,
-                        uint64_t max_overlaps, uint64_t query_batch_bases);
+                        uint64_t n_overlaps, uint32_t n_runs, const uint64_t* run_off,
+                        uint32_t n_query_reads, uint64_t max_overlaps,
+                        uint64_t query_batch_bases);
 int rvn_dist_stage1_end(rvn_ctx* ctx);
+/* owned read j is read rank + j * n_parts; arrays as rvn_stage1_results, over
+ * the n_owned owned reads; n_mapped = overlaps found by this rank's queries */
+int rvn_dist_stage1_results(rvn_ctx* ctx, const rvn_overlap** overlaps,
+                            const uint64_t** overlap_off, const uint16_t** pile,
+                            const uint64_t** pile_off, uint32_t* n_owned,
+                            uint64_t* n_mapped);
 
 #ifdef __cplusplus
 }

@@ -79,16 +79,20 @@ SIGNATURES = {
     "rvn_dist_histogram": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), U32P, U64P]),
     "rvn_dist_set_occurrence": (C.c_int, [C.c_void_p, U64P, C.c_uint64, C.c_double, U32P]),
     "rvn_dist_hits_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
-                                      C.c_int, C.c_int, C.c_uint32, U32P,
+                                      C.c_int, C.c_int, C.c_uint32, C.c_uint32,
                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                       C.POINTER(C.c_void_p), U64P]),
     "rvn_dist_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                 C.c_uint64, C.c_uint32, C.c_uint32,
-                                 C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), U64P]),
-    "rvn_dist_stage1_begin": (C.c_int, [C.c_void_p]),
-    "rvn_dist_stage1_add": (C.c_int, [C.c_void_p, C.c_void_p, U64P, C.c_uint32,
-                                      C.c_uint64, C.c_uint64]),
+                                 C.c_uint64, C.c_uint32, U64P, C.c_uint32, C.c_uint32,
+                                 C.c_uint32, C.POINTER(C.c_void_p), U64P]),
+    "rvn_dist_overlaps_split": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32,
+                                          C.POINTER(C.c_void_p), U64P]),
+    "rvn_dist_stage1_begin": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "rvn_dist_stage1_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
+                                      U64P, C.c_uint32, C.c_uint64, C.c_uint64]),
     "rvn_dist_stage1_end": (C.c_int, [C.c_void_p]),
+    "rvn_dist_stage1_results": (C.c_int, [C.c_void_p, C.POINTER(OVLP), C.POINTER(U64P),
+                                          C.POINTER(U16P), C.POINTER(U64P), U32P, U64P]),
 }
 
 _lib = None

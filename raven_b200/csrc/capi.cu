@@ -61,6 +61,8 @@ void Stage1(Ctx& c, double freq, uint64_t kmax, bool minhash, uint64_t ib,
     throw StateError("stage 1 needs read ids equal to their index");
   }
   c.st_valid = false;
+  c.own_mod = 1;
+  c.own_rem = 0;
   // a stage-1 pass owns its intermediates: nothing is carried over from an
   // earlier call (sketches, micromizers and the index are rebuilt)
   c.s_valid = c.q_valid = c.i_valid = c.r_valid = false;
@@ -598,55 +600,77 @@ RVN_API int rvn_dist_set_occurrence(rvn_ctx* ctx, const uint64_t* hist, uint64_t
 RVN_API int rvn_dist_hits_split(rvn_ctx* ctx, const uint64_t* d_qvalue,
                                 const uint64_t* d_qorigin, uint64_t n_queries,
                                 int avoid_equal, int avoid_symmetric, uint32_t n_parts,
-                                const uint32_t* read_bounds, const uint64_t** d_group,
+                                uint32_t n_query_reads, const uint64_t** d_group,
                                 const uint64_t** d_positions, const uint32_t** d_lhs,
                                 uint64_t* counts) {
   return Guard(ctx, [&](Ctx& c) {
-    if (!read_bounds || !d_group || !d_positions || !d_lhs || !counts) {
-      throw InvalidArgument("null argument");
-    }
+    if (!d_group || !d_positions || !d_lhs || !counts) throw InvalidArgument("null argument");
     if (n_queries && (!d_qvalue || !d_qorigin)) throw InvalidArgument("null queries");
     DistHitsSplit(c, d_qvalue, d_qorigin, n_queries, avoid_equal != 0,
-                  avoid_symmetric != 0, n_parts, read_bounds, d_group, d_positions, d_lhs,
+                  avoid_symmetric != 0, n_parts, n_query_reads, d_group, d_positions, d_lhs,
                   counts);
   });
 }
 
 RVN_API int rvn_dist_chain(rvn_ctx* ctx, const uint64_t* d_group,
                            const uint64_t* d_positions, const uint32_t* d_lhs,
-                           uint64_t n_hits, uint32_t first, uint32_t last,
-                           const rvn_overlap** d_overlaps, const uint32_t** d_counts,
-                           uint64_t* n_overlaps) {
+                           uint64_t n_hits, uint32_t n_runs, const uint64_t* run_off,
+                           uint32_t n_parts, uint32_t rank, uint32_t n_query_reads,
+                           const rvn_overlap** d_overlaps, uint64_t* n_overlaps) {
   return Guard(ctx, [&](Ctx& c) {
-    CheckRange(c, first, last);
     if (n_hits && (!d_group || !d_positions || !d_lhs)) throw InvalidArgument("null hits");
-    if (!d_overlaps || !d_counts || !n_overlaps) throw InvalidArgument("null output");
-    DistChainOwned(c, d_group, d_positions, d_lhs, n_hits, first, last, d_overlaps,
-                   d_counts, n_overlaps);
+    if (!d_overlaps || !n_overlaps || !run_off) throw InvalidArgument("null argument");
+    DistChainOwned(c, d_group, d_positions, d_lhs, n_hits, n_runs, run_off, n_parts, rank,
+                   n_query_reads, d_overlaps, n_overlaps);
   });
 }
 
-RVN_API int rvn_dist_stage1_begin(rvn_ctx* ctx) {
+RVN_API int rvn_dist_overlaps_split(rvn_ctx* ctx, uint32_t n_parts, uint32_t rank,
+                                    const rvn_overlap** d_overlaps, uint64_t* counts) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (!d_overlaps || !counts) throw InvalidArgument("null output");
+    DistOverlapsSplit(c, n_parts, rank, d_overlaps, counts);
+  });
+}
+
+RVN_API int rvn_dist_stage1_begin(rvn_ctx* ctx, uint32_t n_parts, uint32_t rank) {
   return Guard(ctx, [&](Ctx& c) {
     c.s_valid = c.q_valid = c.i_valid = c.r_valid = false;
     TimerReset(c);
     std::memset(&c.stats, 0, sizeof(c.stats));
-    DistStage1Begin(c);
+    DistStage1Begin(c, n_parts, rank);
   });
 }
 
 RVN_API int rvn_dist_stage1_add(rvn_ctx* ctx, const rvn_overlap* d_overlaps,
-                                const uint64_t* overlap_off, uint32_t n_query,
+                                uint64_t n_overlaps, uint32_t n_runs,
+                                const uint64_t* run_off, uint32_t n_query_reads,
                                 uint64_t max_overlaps, uint64_t query_batch_bases) {
   return Guard(ctx, [&](Ctx& c) {
-    if (!overlap_off) throw InvalidArgument("null offsets");
-    if (overlap_off[n_query] && !d_overlaps) throw InvalidArgument("null overlaps");
-    DistStage1Add(c, d_overlaps, overlap_off, n_query, max_overlaps, query_batch_bases);
+    if (!run_off) throw InvalidArgument("null run offsets");
+    if (n_overlaps && !d_overlaps) throw InvalidArgument("null overlaps");
+    DistStage1Add(c, d_overlaps, n_overlaps, n_runs, run_off, n_query_reads, max_overlaps,
+                  query_batch_bases);
   });
 }
 
 RVN_API int rvn_dist_stage1_end(rvn_ctx* ctx) {
   return Guard(ctx, [&](Ctx& c) { DistStage1End(c); });
+}
+
+RVN_API int rvn_dist_stage1_results(rvn_ctx* ctx, const rvn_overlap** overlaps,
+                                    const uint64_t** overlap_off, const uint16_t** pile,
+                                    const uint64_t** pile_off, uint32_t* n_owned,
+                                    uint64_t* n_mapped) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (!c.ds_results_valid) throw StateError("no partitioned stage-1 results");
+    if (overlaps) *overlaps = c.ds_r_ovl.get();
+    if (overlap_off) *overlap_off = c.ds_r_ovl_off.get();
+    if (pile) *pile = c.ds_r_pile.get();
+    if (pile_off) *pile_off = c.ds_r_pile_off.get();
+    if (n_owned) *n_owned = c.ds_n_own;
+    if (n_mapped) *n_mapped = c.st_mapped;
+  });
 }
 
 }  // extern "C"

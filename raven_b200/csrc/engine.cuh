@@ -152,10 +152,22 @@ struct Ctx {
   uint64_t st_mapped = 0;
   bool st_valid = false;
 
+  // ---- read ownership of the stage-1 tail: read r is owned iff r % own_mod ==
+  // own_rem (1 / 0 = every read: the single-GPU path) ----
+  uint32_t own_mod = 1, own_rem = 0;
+
   // ---- multi-GPU partition / exchange staging (dist.cu) ----
   DevBuf<uint64_t> ds_split_val, ds_split_org, ds_qsplit_val, ds_qsplit_org;
-  DevBuf<uint64_t> ds_grouped_grp, ds_grouped_pos, ds_rel_off;
-  DevBuf<uint32_t> ds_masked, ds_hit_lhs, ds_read_cnt, ds_read_cursor, ds_ovl_cnt;
+  DevBuf<uint64_t> ds_grouped_grp, ds_grouped_pos, ds_rel_off, ds_seg_start, ds_seg_base,
+      ds_bounds, ds_q_off;
+  DevBuf<uint32_t> ds_masked, ds_hit_lhs, ds_read_cnt, ds_flag, ds_own_ids;
+  DevBuf<rvn_overlap> ds_ovl_split, ds_merged;
+  // results of the owned reads (pinned host)
+  PinBuf<rvn_overlap> ds_r_ovl;
+  PinBuf<uint64_t> ds_r_ovl_off, ds_r_pile_off;
+  PinBuf<uint16_t> ds_r_pile;
+  uint32_t ds_n_own = 0;
+  bool ds_results_valid = false;
 
   // pinned scalars for small D2H reads
   PinBuf<uint64_t> pin64;
@@ -201,9 +213,10 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
               bool fetch = true);
 
 // chains hits grouped by query read (see map.cu); overlaps land in c.m_ovl
+// lhs_ids[i] = id of query read i of the batch (device)
 uint64_t ChainGroupedHits(Ctx& c, const uint64_t* hg, const uint64_t* hp,
                           const uint64_t* read_hit_off,
-                          const std::vector<uint64_t>& h_rho, uint32_t first,
+                          const std::vector<uint64_t>& h_rho, const uint32_t* lhs_ids,
                           uint32_t nr, uint64_t n_hits, uint64_t n_q);
 
 // ---- gather.cu ----
@@ -212,21 +225,24 @@ void GatherFlush(Ctx& c, const rvn_overlap* ovl, const uint64_t* q_ovl_off,
                  uint64_t m, uint32_t k0, uint32_t k1, uint64_t kmax);
 void GatherFetch(Ctx& c);
 
-// ---- dist.cu ---- key-partitioned index / read-partitioned chaining
+// ---- dist.cu ---- key-partitioned index, reads owned by id mod parts
 // which: 0 = full minimizers, 1 = micromizers; records of reads [first,last)
-// stably split by key owner; counts[parts]
+// stably partitioned by value % parts; counts[parts]
 void DistSketchSplit(Ctx& c, uint32_t first, uint32_t last, int which, uint32_t parts,
                      const uint64_t** d_val, const uint64_t** d_org, uint64_t* counts);
 void DistHitsSplit(Ctx& c, const uint64_t* d_qval, const uint64_t* d_qorg, uint64_t n_q,
-                   bool avoid_equal, bool avoid_symmetric, uint32_t parts,
-                   const uint32_t* h_bounds, const uint64_t** d_grp,
-                   const uint64_t** d_pos, const uint32_t** d_lhs, uint64_t* counts);
+                   bool avoid_equal, bool avoid_symmetric, uint32_t parts, uint32_t n_query,
+                   const uint64_t** d_grp, const uint64_t** d_pos, const uint32_t** d_lhs,
+                   uint64_t* counts);
 void DistChainOwned(Ctx& c, const uint64_t* d_grp, const uint64_t* d_pos,
-                    const uint32_t* d_lhs, uint64_t n_hits, uint32_t first, uint32_t last,
-                    const rvn_overlap** d_ovl, const uint32_t** d_ovl_cnt, uint64_t* n_ovl);
-void DistStage1Begin(Ctx& c);
-void DistStage1Add(Ctx& c, const rvn_overlap* d_ovl, const uint64_t* h_ovl_off,
-                   uint32_t n_query, uint64_t kmax, uint64_t qb);
+                    const uint32_t* d_lhs, uint64_t n_hits, uint32_t n_seg,
+                    const uint64_t* h_seg_off, uint32_t mod, uint32_t rem, uint32_t n_query,
+                    const rvn_overlap** d_ovl, uint64_t* n_ovl);
+void DistOverlapsSplit(Ctx& c, uint32_t parts, uint32_t self, const rvn_overlap** d_out,
+                       uint64_t* counts);
+void DistStage1Begin(Ctx& c, uint32_t parts, uint32_t rank);
+void DistStage1Add(Ctx& c, const rvn_overlap* d_ovl, uint64_t n_ovl, uint32_t n_seg,
+                   const uint64_t* h_seg_off, uint32_t n_query, uint64_t kmax, uint64_t qb);
 void DistStage1End(Ctx& c);
 
 // ---- pile.cu ----

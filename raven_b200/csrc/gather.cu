@@ -56,9 +56,14 @@ __global__ void RhsKeys(const rvn_overlap* __restrict__ ovl, uint32_t m,
 __global__ void ListTotals(const uint32_t* __restrict__ old_cnt,
                            const uint32_t* __restrict__ rhs_cnt,
                            const uint64_t* __restrict__ q_ovl_off, uint32_t k0,
-                           uint32_t k1, uint32_t n, uint32_t* __restrict__ total) {
+                           uint32_t k1, uint32_t n, uint32_t mod, uint32_t rem,
+                           uint32_t* __restrict__ total) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
+  if (r % mod != rem) {  // not this context's read: its list stays empty
+    total[r] = old_cnt[r];
+    return;
+  }
   uint32_t lhs = 0;
   if (r >= k0 && r < k1) {
     lhs = static_cast<uint32_t>(q_ovl_off[r - k0 + 1] - q_ovl_off[r - k0]);
@@ -83,12 +88,13 @@ __global__ void PlaceRhs(const rvn_overlap* __restrict__ ovl,
                          const uint32_t* __restrict__ sorted_idx, uint32_t m,
                          const uint64_t* __restrict__ rhs_off,
                          const uint32_t* __restrict__ old_cnt,
-                         const uint64_t* __restrict__ t_off,
+                         const uint64_t* __restrict__ t_off, uint32_t mod, uint32_t rem,
                          rvn_overlap* __restrict__ stage) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= m) return;
   const rvn_overlap o = ovl[sorted_idx[p]];
   const uint32_t r = o.rhs_id;
+  if (r % mod != rem) return;
   const uint64_t rank = p - rhs_off[r];
   stage[t_off[r] + old_cnt[r] + rank] = ReverseOverlap(o);
 }
@@ -97,12 +103,13 @@ __global__ void PlaceLhs(const rvn_overlap* __restrict__ ovl, uint32_t m,
                          const uint64_t* __restrict__ q_ovl_off, uint32_t k0,
                          const uint32_t* __restrict__ rhs_cnt,
                          const uint32_t* __restrict__ old_cnt,
-                         const uint64_t* __restrict__ t_off,
+                         const uint64_t* __restrict__ t_off, uint32_t mod, uint32_t rem,
                          rvn_overlap* __restrict__ stage) {
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= m) return;
   const rvn_overlap o = ovl[e];
   const uint32_t r = o.lhs_id;
+  if (r % mod != rem) return;
   const uint64_t rank = e - q_ovl_off[r - k0];
   stage[t_off[r] + old_cnt[r] + rhs_cnt[r] + rank] = o;
 }
@@ -201,7 +208,7 @@ void GatherFlush(Ctx& c, const rvn_overlap* ovl, const uint64_t* q_ovl_off,
   uint32_t* total = c.g_total_cnt.reserve(n + 1ULL);
   uint64_t* t_off = c.g_t_off.reserve(n + 2ULL);
   ListTotals<<<CeilDiv(n, kThreads), kThreads, 0, c.stream>>>(
-      c.g_cnt.get(), rhs_cnt, q_ovl_off, k0, k1, n, total);
+      c.g_cnt.get(), rhs_cnt, q_ovl_off, k0, k1, n, c.own_mod, c.own_rem, total);
   RVN_LAUNCH_CHECK();
   ++c.launches;
   ExclusiveScanU32(c, total, t_off, n);
@@ -214,9 +221,9 @@ void GatherFlush(Ctx& c, const rvn_overlap* ovl, const uint64_t* q_ovl_off,
   CopyOld<<<CeilDiv(n, kThreads / 32), kThreads, 0, c.stream>>>(
       lists, c.g_off.get(), c.g_cnt.get(), t_off, n, stage);
   PlaceRhs<<<CeilDiv(m, kThreads), kThreads, 0, c.stream>>>(
-      ovl, sorted_idx, m, rhs_off, c.g_cnt.get(), t_off, stage);
+      ovl, sorted_idx, m, rhs_off, c.g_cnt.get(), t_off, c.own_mod, c.own_rem, stage);
   PlaceLhs<<<CeilDiv(m, kThreads), kThreads, 0, c.stream>>>(
-      ovl, m, q_ovl_off, k0, rhs_cnt, c.g_cnt.get(), t_off, stage);
+      ovl, m, q_ovl_off, k0, rhs_cnt, c.g_cnt.get(), t_off, c.own_mod, c.own_rem, stage);
   Truncate<<<CeilDiv(n, 128), 128, 0, c.stream>>>(stage, t_off, total,
                                                    c.g_cnt.get(), n, kmax, pairs,
                                                    kept);

@@ -1033,11 +1033,10 @@ __global__ void ReorderOverlaps(const rvn_overlap* __restrict__ raw,
 // a read). Leaves the overlaps in query order in c.m_ovl / c.m_ovl_off.
 uint64_t ChainGroupedHits(Ctx& c, const uint64_t* hg, const uint64_t* hp,
                           const uint64_t* read_hit_off,
-                          const std::vector<uint64_t>& h_rho, uint32_t first,
+                          const std::vector<uint64_t>& h_rho, const uint32_t* lhs_ids,
                           uint32_t nr, uint64_t n_hits, uint64_t n_q) {
   TimerBegin(c, "chain");
   ChainParams cp{c.prm.k, c.prm.bandwidth, c.prm.chain, c.prm.matches, c.prm.gap};
-  const uint32_t* lhs_ids = c.d_ids.get() + first;
   const uint64_t ovl_cap = n_hits / std::max(1u, std::min(c.prm.chain, 4u)) + 16;
   rvn_overlap* raw = c.m_ovl_raw.reserve(ovl_cap);
   uint64_t* loc = c.m_ovl_loc.reserve(nr + 1ULL);
@@ -1394,7 +1393,7 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
 
   // ---- chain ----
   const uint64_t n_ovl =
-      ChainGroupedHits(c, hg, hp, read_hit_off, h_rho, first, nr, n_hits, n_q);
+      ChainGroupedHits(c, hg, hp, read_hit_off, h_rho, c.d_ids.get() + first, nr, n_hits, n_q);
   const rvn_overlap* ordered = c.m_ovl.get();
   const uint64_t* ooff = c.m_ovl_off.get();
 

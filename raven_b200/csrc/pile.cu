@@ -15,12 +15,14 @@ namespace {
 
 __global__ void ScatterMarks(const rvn_overlap* __restrict__ ovl, uint64_t n,
                              const uint64_t* __restrict__ bin_off,
-                             uint32_t n_piles, int32_t* __restrict__ diff) {
+                             uint32_t n_piles, uint32_t mod, uint32_t rem,
+                             int32_t* __restrict__ diff) {
   const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const rvn_overlap o = ovl[i];
-  // pile p owns diff[bin_off[p] + p .. bin_off[p+1] + p]  (bins + 1 slots)
-  if (o.lhs_id < n_piles) {
+  // pile p owns diff[bin_off[p] + p .. bin_off[p+1] + p]  (bins + 1 slots);
+  // only the piles this context owns (p % mod == rem) are maintained
+  if (o.lhs_id < n_piles && o.lhs_id % mod == rem) {
     const uint64_t base = bin_off[o.lhs_id] + o.lhs_id;
     const uint64_t bins = bin_off[o.lhs_id + 1] - bin_off[o.lhs_id];
     const uint32_t b = (o.lhs_begin >> 4) + 1, e = (o.lhs_end >> 4) - 1;
@@ -29,7 +31,7 @@ __global__ void ScatterMarks(const rvn_overlap* __restrict__ ovl, uint64_t n,
       atomicAdd(diff + base + e, -1);
     }
   }
-  if (o.rhs_id < n_piles) {
+  if (o.rhs_id < n_piles && o.rhs_id % mod == rem) {
     const uint64_t base = bin_off[o.rhs_id] + o.rhs_id;
     const uint64_t bins = bin_off[o.rhs_id + 1] - bin_off[o.rhs_id];
     const uint32_t b = (o.rhs_begin >> 4) + 1, e = (o.rhs_end >> 4) - 1;
@@ -44,9 +46,10 @@ __global__ void ScatterMarks(const rvn_overlap* __restrict__ ovl, uint64_t n,
 // and the differences are cleared for the next call
 __global__ void __launch_bounds__(256)
 ApplyCoverage(uint16_t* __restrict__ data, const uint64_t* __restrict__ bin_off,
-              uint32_t n_piles, int32_t* __restrict__ diff) {
-  const uint32_t p = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (p >= n_piles) return;
+              uint32_t n_piles, uint32_t mod, uint32_t rem, int32_t* __restrict__ diff) {
+  const uint64_t p64 = static_cast<uint64_t>(blockIdx.x * 8 + (threadIdx.x >> 5)) * mod + rem;
+  if (p64 >= n_piles) return;
+  const uint32_t p = static_cast<uint32_t>(p64);
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t b0 = bin_off[p];
   const uint32_t bins = static_cast<uint32_t>(bin_off[p + 1] - b0);
@@ -84,10 +87,11 @@ void PileAddLayersDevice(Ctx& c, uint16_t* d_data, const uint64_t* d_off,
     RVN_CUDA(cudaMemsetAsync(d, 0, c.p_diff.cap * sizeof(int32_t), c.stream));
   }
   TimerBegin(c, "pile");
-  ScatterMarks<<<CeilDiv(n_ovl, 256), 256, 0, c.stream>>>(d_ovl, n_ovl, d_off,
-                                                          n_piles, c.p_diff.get());
-  ApplyCoverage<<<CeilDiv(n_piles, 8), 256, 0, c.stream>>>(d_data, d_off, n_piles,
-                                                           c.p_diff.get());
+  ScatterMarks<<<CeilDiv(n_ovl, 256), 256, 0, c.stream>>>(
+      d_ovl, n_ovl, d_off, n_piles, c.own_mod, c.own_rem, c.p_diff.get());
+  const uint32_t owned = CeilDiv(n_piles, c.own_mod);
+  ApplyCoverage<<<CeilDiv(owned, 8), 256, 0, c.stream>>>(d_data, d_off, n_piles, c.own_mod,
+                                                         c.own_rem, c.p_diff.get());
   RVN_LAUNCH_CHECK();
   c.launches += 2;
   TimerEnd(c);

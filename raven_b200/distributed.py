@@ -9,12 +9,13 @@ Sharding (DESIGN.md "Multi-GPU"):
                  minimizer records builds each rank's slice, an all-reduce of the
                  run-length histogram gives ONE global occurrence threshold;
 * seed hits      found where the key lives, sent (all-to-all, 20 B per hit) to
-                 the rank that owns the query read;
-* chaining       per owned read - ranges balanced for the triangular work of
-                 ``avoid_symmetric`` (read i only meets reads above it);
-* piles + lists  every rank gets all overlaps (all-gather, 32 B each) and runs
-                 the cheap tail itself: the result is complete on every rank and
-                 bit-identical to the single-GPU path.
+                 the rank that owns the query read: read ``r`` belongs to rank
+                 ``r mod world`` (with ``avoid_symmetric`` a read only meets higher
+                 ids - the interleave gives every rank the same mix);
+* chaining       per owned read, the single-GPU kernels;
+* piles + lists  of the owned reads: every overlap also goes to the owner of its
+                 rhs read (all-to-all, 32 B each); results stay sharded, bit-
+                 identical to the single-GPU path (``assemble`` rebuilds the whole).
 
 The exchange logic is written against a small "steps" interface so that the
 same code runs over gloo on CPU tensors in the tests (tests/test_dist_cpu.py
@@ -23,7 +24,8 @@ plugs a numpy + oracle implementation in); ``CudaSteps`` is the product one.
 from __future__ import annotations
 
 import ctypes as C
-import math
+import os
+import time
 
 import numpy as np
 import torch
@@ -43,24 +45,6 @@ def sketch_bounds(lens, parts):
         b.append(int(np.searchsorted(cum, total * p // parts, side="left")))
     b.append(len(lens))
     return [min(max(x, b[i - 1] if i else 0), len(lens)) for i, x in enumerate(b)]
-
-
-def chain_bounds(lens, parts):
-    """Contiguous read ranges of equal CHAIN work.  With avoid_symmetric a read
-    only keeps hits against higher ids, so the work of the read at base
-    fraction x falls like (1 - x): the boundary of part p sits at
-    x = 1 - sqrt(1 - p / parts)."""
-    lens = np.asarray(lens, dtype=np.uint64)
-    cum = np.concatenate([[0], np.cumsum(lens, dtype=np.uint64)])
-    total = int(cum[-1])
-    b = [0]
-    for p in range(1, parts):
-        x = 1.0 - math.sqrt(1.0 - p / parts)
-        b.append(int(np.searchsorted(cum, int(total * x), side="left")))
-    b.append(len(lens))
-    for i in range(1, len(b)):
-        b[i] = min(max(b[i], b[i - 1]), len(lens))
-    return b
 
 
 def index_batches(lens, index_batch_bases):
@@ -96,7 +80,8 @@ class TorchComm:
 
     def all_to_all_v(self, tensors, send_counts):
         """Rows [sum(send_counts)] of every tensor, split by destination rank ->
-        rows received from every rank, concatenated in source-rank order."""
+        (rows received from every rank, concatenated in source-rank order;
+        rows per source rank)."""
         device = tensors[0].device
         recv_counts = self._exchange_counts(send_counts, device)
         n_recv = sum(recv_counts)
@@ -106,7 +91,7 @@ class TorchComm:
             dist.all_to_all_single(r, t.contiguous(), recv_counts, list(send_counts),
                                    group=self.group)
             out.append(r)
-        return out
+        return out, recv_counts
 
     def all_gather_v(self, t):
         """Concatenation of every rank's rows, in rank order."""
@@ -129,14 +114,20 @@ class TorchComm:
         dist.all_reduce(t, group=self.group)
         return t
 
+    def gather_objects(self, obj):
+        """[obj of rank 0, obj of rank 1, ...] on every rank (host data)."""
+        out = [None] * self.world
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
 
 # ---------------------------------------------------------------- the schedule
 def find_overlaps_and_create_piles(steps, lens, frequency=0.001, max_overlaps=32,
-                                   index_batch_bases=0, query_batch_bases=0,
-                                   comm=None):
+                                   use_minhash=False, index_batch_bases=0,
+                                   query_batch_bases=0, comm=None, fetch=True):
     """The reference's stage 1 over ``world`` ranks.  ``steps`` does the compute
-    on this rank (CudaSteps); returns what ``steps.stage1_results()`` returns -
-    the same on every rank."""
+    on this rank (CudaSteps); returns this rank's share - the overlap lists and
+    piles of the reads ``rank, rank + world, ...`` (``assemble`` gives the whole)."""
     comm = comm or TorchComm()
     rank, world = comm.rank, comm.world
     lens = np.asarray(lens, dtype=np.uint32)
@@ -144,50 +135,112 @@ def find_overlaps_and_create_piles(steps, lens, frequency=0.001, max_overlaps=32
     if not 0 <= frequency <= 1:
         raise ValueError("[ram::MinimizerEngine::Filter] error: invalid frequency")
     sb = sketch_bounds(lens, world)
-    cb = chain_bounds(lens, world)
-    steps.stage1_begin()
+    # RVN_DIST_TRACE=1: wall time per step of the schedule (adds a device sync
+    # after each; for analysis, never for a reported number)
+    trace = {} if os.environ.get("RVN_DIST_TRACE") else None
+    t_last = [time.perf_counter()]
+
+    def tick(name):
+        if trace is None:
+            return
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        now = time.perf_counter()
+        trace[name] = trace.get(name, 0.0) + 1e3 * (now - t_last[0])
+        t_last[0] = now
+
+    steps.stage1_begin(world, rank)
+    tick("begin")
     occurrences = []
     for (j, i1) in index_batches(lens, index_batch_bases):
         # -- 1. sketch own reads; records to the owners of their keys
+        # (index: micromizers only with use_minhash, construct.cc:42-43;
+        #  queries: always micromizers, construct.cc:62)
         lo, hi = max(sb[rank], j), min(sb[rank + 1], i1)
         lo, hi = (lo, hi) if lo < hi else (0, 0)
-        val, org, cnt = steps.sketch_split(lo, hi, world)
-        ival, iorg = comm.all_to_all_v([val, org], cnt)
+        val, org, cnt = steps.sketch_split(lo, hi, world, use_minhash)
+        tick("sketch_split(index)")
+        (ival, iorg), _ = comm.all_to_all_v([val, org], cnt)
+        tick("a2a index records")
         qlo, qhi = sb[rank], min(sb[rank + 1], i1)
         qlo, qhi = (qlo, qhi) if qlo < qhi else (0, 0)
-        if j == 0:  # (same decision on every rank) first batch: queries == index reads
+        if use_minhash and j == 0:  # (same decision on every rank)
             qval, qorg = ival, iorg  # one exchange serves index and queries
         else:
-            val, org, cnt = steps.sketch_split(qlo, qhi, world)
-            qval, qorg = comm.all_to_all_v([val, org], cnt)
+            val, org, cnt = steps.sketch_split(qlo, qhi, world, True)
+            tick("sketch_split(query)")
+            (qval, qorg), _ = comm.all_to_all_v([val, org], cnt)
+            tick("a2a query records")
 
         # -- 2. index slice + ONE global occurrence threshold
         steps.build_index(ival, iorg, int(lens[j:i1].astype(np.uint64).sum()))
+        tick("build_index")
         hist, n_keys = steps.histogram()
         tot = torch.cat([hist, torch.tensor([n_keys], dtype=torch.int64,
                                             device=hist.device)])
         tot = comm.all_reduce_sum(tot).cpu().numpy().astype(np.uint64)
         occurrences.append(steps.set_occurrence(tot[:-1], int(tot[-1]), frequency))
+        tick("filter (histogram + all-reduce)")
 
         # -- 3. seed hits where the key lives -> owner of the query read
-        qb_ = [min(b, i1) for b in cb]
-        grp, pos, lhs, cnt = steps.hits_split(qval, qorg, qb_)
-        grp, pos, lhs = comm.all_to_all_v([grp, pos, lhs], cnt)
+        # (the received queries are sorted by read: ascending sketch ranges)
+        grp, pos, lhs, cnt = steps.hits_split(qval, qorg, world, i1)
+        tick("hits_split")
+        (grp, pos, lhs), runs = comm.all_to_all_v([grp, pos, lhs], cnt)
+        tick("a2a hits")
 
-        # -- 4. chain the owned reads; everybody gets every overlap
-        ovl, per_read = steps.chain(grp, pos, lhs, qb_[rank], qb_[rank + 1])
-        all_ovl = comm.all_gather_v(ovl)
-        all_cnt = comm.all_gather_v(per_read)
-        off = np.zeros(i1 + 1, dtype=np.uint64)
-        np.cumsum(all_cnt.cpu().numpy().astype(np.uint64), out=off[1:])
-        assert int(off[-1]) == all_ovl.shape[0]
+        # -- 4. chain the owned reads (one run of hits per source rank)
+        steps.chain(grp, pos, lhs, runs, world, rank, i1)
+        tick("chain")
 
-        # -- 5. piles + per-read lists (replicated; the reference's flush schedule)
-        steps.stage1_add(all_ovl, off, i1, max_overlaps, query_batch_bases)
+        # -- 5. every overlap also to the owner of its rhs read; piles + lists of
+        # the owned reads with the reference's flush schedule
+        ovl, cnt = steps.overlaps_split(world, rank)
+        (ovl,), runs = comm.all_to_all_v([ovl], cnt)
+        tick("a2a overlaps")
+        steps.stage1_add(ovl, runs, i1, max_overlaps, query_batch_bases)
+        tick("piles + lists")
     steps.stage1_end()
-    res = steps.stage1_results(n)
-    res["occurrences"] = occurrences
+    tick("end (D2H)")
+    res = steps.stage1_results() if fetch else {}
+    res.update(occurrences=occurrences, rank=rank, world=world, n_reads=n)
+    if trace is not None:
+        for k, v in getattr(steps, "call_ms", {}).items():
+            trace["call:" + k] = v
+        res["trace_ms"] = trace
     return res
+
+
+def assemble(res, comm=None):
+    """The complete stage-1 result (the layout of Engine.find_overlaps_and_
+    create_piles) from the per-rank shares, on every rank."""
+    comm = comm or TorchComm()
+    keys = ("overlaps", "ovl_off", "pile", "pile_off", "num_mapped")
+    shares = comm.gather_objects({k: res[k] for k in keys})
+    n, world = res["n_reads"], res["world"]
+    ocnt = np.zeros(n, dtype=np.uint64)
+    pcnt = np.zeros(n, dtype=np.uint64)
+    for r, sh in enumerate(shares):
+        ocnt[r::world] = np.diff(sh["ovl_off"])
+        pcnt[r::world] = np.diff(sh["pile_off"])
+    ovl_off = np.concatenate([[0], np.cumsum(ocnt)]).astype(np.uint64)
+    pile_off = np.concatenate([[0], np.cumsum(pcnt)]).astype(np.uint64)
+    overlaps = np.zeros((int(ovl_off[-1]), 8), dtype=np.uint32)
+    pile = np.zeros(int(pile_off[-1]), dtype=np.uint16)
+    for r, sh in enumerate(shares):
+        ids = np.arange(r, n, world)
+        for src_off, dst_off, src, dst in ((sh["ovl_off"], ovl_off, sh["overlaps"], overlaps),
+                                           (sh["pile_off"], pile_off, sh["pile"], pile)):
+            cnt = np.diff(src_off).astype(np.int64)
+            if cnt.sum() == 0:
+                continue
+            # destination index of every element of the share
+            start = np.repeat(dst_off[ids].astype(np.int64), cnt)
+            within = np.arange(int(cnt.sum())) - np.repeat(src_off[:-1].astype(np.int64), cnt)
+            dst[start + within] = src
+    return dict(overlaps=overlaps, ovl_off=ovl_off, pile=pile, pile_off=pile_off,
+                num_mapped=int(sum(int(sh["num_mapped"]) for sh in shares)),
+                occurrences=res["occurrences"])
 
 
 # ---------------------------------------------------------------- CUDA steps
@@ -217,15 +270,28 @@ class CudaSteps:
         self.lib = engine.lib
         self.h = engine.h
         self.device = torch.device(device)
+        self.call_ms = {}  # RVN_DIST_TRACE: wall time inside the C calls
+        if os.environ.get("RVN_DIST_TRACE"):
+            for name in ("sketch_split", "build_index", "hits_split", "chain",
+                         "overlaps_split", "stage1_add", "stage1_end"):
+                setattr(self, name, self._timed(name, getattr(self, name)))
+
+    def _timed(self, name, fn):
+        def wrapped(*a):
+            t = time.perf_counter()
+            out = fn(*a)
+            self.call_ms[name] = self.call_ms.get(name, 0.0) + 1e3 * (time.perf_counter() - t)
+            return out
+        return wrapped
 
     def _p(self, t):
         return C.c_void_p(t.data_ptr() if t.numel() else 0)
 
-    def sketch_split(self, first, last, parts):
+    def sketch_split(self, first, last, parts, minhash):
         v, o = C.c_void_p(), C.c_void_p()
         cnt = (C.c_uint64 * parts)()
         self.e._check(self.lib.rvn_dist_sketch_split(
-            self.h, first, last, 1, parts, C.byref(v), C.byref(o), cnt))
+            self.h, first, last, int(minhash), parts, C.byref(v), C.byref(o), cnt))
         cnt = [int(x) for x in cnt]
         n = sum(cnt)
         return (_view(v.value, (n,), "<i8", torch.int64, self.device),
@@ -249,13 +315,11 @@ class CudaSteps:
             self.h, h.ctypes.data_as(U64P), n_keys, float(frequency), C.byref(occ)))
         return occ.value
 
-    def hits_split(self, qval, qorg, bounds):
-        parts = len(bounds) - 1
-        b = (C.c_uint32 * (parts + 1))(*bounds)
+    def hits_split(self, qval, qorg, parts, n_query):
         g, p, l = C.c_void_p(), C.c_void_p(), C.c_void_p()
         cnt = (C.c_uint64 * parts)()
         self.e._check(self.lib.rvn_dist_hits_split(
-            self.h, self._p(qval), self._p(qorg), qval.numel(), 1, 1, parts, b,
+            self.h, self._p(qval), self._p(qorg), qval.numel(), 1, 1, parts, n_query,
             C.byref(g), C.byref(p), C.byref(l), cnt))
         cnt = [int(x) for x in cnt]
         n = sum(cnt)
@@ -263,34 +327,44 @@ class CudaSteps:
                 _view(p.value, (n,), "<i8", torch.int64, self.device),
                 _view(l.value, (n,), "<i4", torch.int32, self.device), cnt)
 
-    def chain(self, grp, pos, lhs, first, last):
-        o, c, n = C.c_void_p(), C.c_void_p(), C.c_uint64(0)
+    @staticmethod
+    def _runs(counts):
+        return (C.c_uint64 * (len(counts) + 1))(0, *np.cumsum(counts).tolist())
+
+    def chain(self, grp, pos, lhs, run_counts, parts, rank, n_query):
+        o, n = C.c_void_p(), C.c_uint64(0)
         self.e._check(self.lib.rvn_dist_chain(
-            self.h, self._p(grp), self._p(pos), self._p(lhs), grp.numel(), first, last,
-            C.byref(o), C.byref(c), C.byref(n)))
-        return (_view(o.value, (n.value, 8), "<i4", torch.int32, self.device),
-                _view(c.value, (last - first,), "<i4", torch.int32, self.device))
+            self.h, self._p(grp), self._p(pos), self._p(lhs), grp.numel(), len(run_counts),
+            self._runs(run_counts), parts, rank, n_query, C.byref(o), C.byref(n)))
+        return n.value
 
-    def stage1_begin(self):
-        self.e._check(self.lib.rvn_dist_stage1_begin(self.h))
+    def overlaps_split(self, parts, rank):
+        o = C.c_void_p()
+        cnt = (C.c_uint64 * parts)()
+        self.e._check(self.lib.rvn_dist_overlaps_split(self.h, parts, rank, C.byref(o), cnt))
+        cnt = [int(x) for x in cnt]
+        return _view(o.value, (sum(cnt), 8), "<i4", torch.int32, self.device), cnt
 
-    def stage1_add(self, ovl, off, n_query, max_overlaps, query_batch_bases):
-        off = np.ascontiguousarray(off, dtype=np.uint64)
+    def stage1_begin(self, parts, rank):
+        self.e._check(self.lib.rvn_dist_stage1_begin(self.h, parts, rank))
+
+    def stage1_add(self, ovl, run_counts, n_query, max_overlaps, query_batch_bases):
         self.e._check(self.lib.rvn_dist_stage1_add(
-            self.h, self._p(ovl), off.ctypes.data_as(U64P), n_query, max_overlaps,
-            query_batch_bases))
+            self.h, self._p(ovl), ovl.shape[0], len(run_counts), self._runs(run_counts),
+            n_query, max_overlaps, query_batch_bases))
 
     def stage1_end(self):
         self.e._check(self.lib.rvn_dist_stage1_end(self.h))
 
-    def stage1_results(self, n):
+    def stage1_results(self):
         from .engine import _arr
-        o, off, p, poff, nm = OVLP(), U64P(), U16P(), U64P(), C.c_uint64(0)
-        self.e._check(self.lib.rvn_stage1_results(self.h, C.byref(o), C.byref(off),
-                                                  C.byref(p), C.byref(poff),
-                                                  C.byref(nm)))
-        ovl_off = _arr(off, n + 1, np.uint64)
-        pile_off = _arr(poff, n + 1, np.uint64)
+        o, off, p, poff = OVLP(), U64P(), U16P(), U64P()
+        n_own, nm = C.c_uint32(0), C.c_uint64(0)
+        self.e._check(self.lib.rvn_dist_stage1_results(
+            self.h, C.byref(o), C.byref(off), C.byref(p), C.byref(poff), C.byref(n_own),
+            C.byref(nm)))
+        ovl_off = _arr(off, n_own.value + 1, np.uint64)
+        pile_off = _arr(poff, n_own.value + 1, np.uint64)
         return dict(overlaps=_arr(o, int(ovl_off[-1]) * 8, np.uint32).reshape(-1, 8),
                     ovl_off=ovl_off, pile=_arr(p, int(pile_off[-1]), np.uint16),
                     pile_off=pile_off, num_mapped=nm.value)
@@ -316,8 +390,9 @@ class DistEngine:
         self.lens = np.asarray(rs.lens, dtype=np.uint32)
 
     def find_overlaps_and_create_piles(self, freq=0.001, max_overlaps=32,
-                                       index_batch_bases=0, query_batch_bases=0):
+                                       use_minhash=False, index_batch_bases=0,
+                                       query_batch_bases=0, fetch=True):
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             return find_overlaps_and_create_piles(
                 CudaSteps(self.engine, self.device), self.lens, freq, max_overlaps,
-                index_batch_bases, query_batch_bases, self.comm)
+                use_minhash, index_batch_bases, query_batch_bases, self.comm, fetch)

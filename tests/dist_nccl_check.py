@@ -25,15 +25,17 @@ def main():
         (dict(genome_len=100_000, n_reads=600, mean_len=5000, seed=22), 0.01, 8,
          1_200_000, 400_000),
     ]
-    for reads, freq, kmax, ib, qb in cases:
+    for case_no, (reads, freq, kmax, ib, qb) in enumerate(cases * 2):
+        minhash = case_no >= len(cases)
         rs = synth.make_reads(**reads)
         single = engine.Engine(device=local)
         single.upload(rs)
-        want = single.find_overlaps_and_create_piles(freq, kmax, True, ib, qb)
+        want = single.find_overlaps_and_create_piles(freq, kmax, minhash, ib, qb)
         single.close()
         de = distributed.DistEngine(f"cuda:{local}")
         de.upload(rs)
-        got = de.find_overlaps_and_create_piles(freq, kmax, ib, qb)
+        got = distributed.assemble(
+            de.find_overlaps_and_create_piles(freq, kmax, minhash, ib, qb))
         same = all(np.array_equal(got[k], want[k]) for k in ("ovl_off", "overlaps", "pile"))
         same = same and int(got["num_mapped"]) == int(want["num_mapped"])
         print(f"rank {rank}: {int(want['ovl_off'][-1])} kept overlaps, "

@@ -22,9 +22,9 @@ class NumpySteps:
         self.lens = np.asarray(reads.lens, dtype=np.uint32)
 
     # -- sketch of reads [first,last), stably split by value mod parts
-    def sketch_split(self, first, last, parts):
+    def sketch_split(self, first, last, parts, minhash):
         if last > first:
-            s = self.o.sketch(self.eng, self.oreads, first, last, True)
+            s = self.o.sketch(self.eng, self.oreads, first, last, bool(minhash))
             val, org = s["value"], s["origin"]
         else:
             val = org = np.zeros(0, np.uint64)
@@ -58,10 +58,11 @@ class NumpySteps:
         self.occ = length + 1
         return self.occ
 
-    # -- hits of the query records against this slice, split by read owner
-    def hits_split(self, qval, qorg, bounds):
+    # -- hits of the query records against this slice, runs by owner of the read
+    def hits_split(self, qval, qorg, parts, n_query):
         qv = qval.numpy().view(np.uint64)
         qo = qorg.numpy().view(np.uint64)
+        assert np.all(np.diff((qo >> np.uint64(32)).astype(np.int64)) >= 0)  # the contract
         lo = np.searchsorted(self.i_val, qv, side="left")
         hi = np.searchsorted(self.i_val, qv, side="right")
         n = hi - lo
@@ -79,58 +80,72 @@ class NumpySteps:
         diag = np.where(strand == 0, rpos + lpos, rpos - lpos + np.uint64(3 << 30))
         grp = (((rid << np.uint64(1)) | strand) << np.uint64(32)) | diag
         pos = (lpos << np.uint64(32)) | rpos
-        b = np.asarray(bounds, dtype=np.uint64)
-        dest = np.searchsorted(b[1:-1], lid, side="right")
+        dest = (lid % np.uint64(parts)).astype(np.int64)
         order = np.argsort(dest, kind="stable")
-        cnt = np.bincount(dest, minlength=len(bounds) - 1).tolist()
+        cnt = np.bincount(dest, minlength=parts).tolist()
         return (_t(grp[order], np.int64), _t(pos[order], np.int64),
                 _t(lid[order].astype(np.uint32), np.int32), cnt)
 
-    def chain(self, grp, pos, lhs, first, last):
+    @staticmethod
+    def _check_runs(keys, run_counts):
+        assert sum(run_counts) == keys.size
+        at = 0
+        for c in run_counts:
+            assert np.all(np.diff(keys[at:at + c].astype(np.int64)) >= 0)
+            at += c
+
+    def chain(self, grp, pos, lhs, run_counts, parts, rank, n_query):
         g = grp.numpy().view(np.uint64)
         p = pos.numpy().view(np.uint64)
         l = lhs.numpy().view(np.uint32)
-        out, cnt = [], []
+        self._check_runs(l, run_counts)  # the contract of rvn_dist_chain
+        assert np.all(l % parts == rank) and (l.size == 0 or l.max() < n_query)
         order = np.argsort(l, kind="stable")
         g, p, l = g[order], p[order], l[order]
-        starts = np.searchsorted(l, np.arange(first, last + 1))
-        for r in range(first, last):
-            a, b = starts[r - first], starts[r - first + 1]
-            ov = self.o.chain(self.eng, r, g[a:b], p[a:b]) if b > a else \
-                np.zeros((0, 8), np.uint32)
-            out.append(ov)
-            cnt.append(ov.shape[0])
-        ov = np.concatenate(out) if out else np.zeros((0, 8), np.uint32)
-        return (torch.from_numpy(ov.view(np.int32).reshape(-1, 8).copy()),
-                torch.tensor(cnt, dtype=torch.int32))
+        out = []
+        for r in range(rank, n_query, parts):
+            a, b = np.searchsorted(l, [r, r + 1])
+            if b > a:
+                out.append(self.o.chain(self.eng, r, g[a:b], p[a:b]))
+        self.ovl = np.concatenate(out) if out else np.zeros((0, 8), np.uint32)
+        self.mapped += self.ovl.shape[0]
+        return self.ovl.shape[0]
 
-    # -- construct.cc:66-112 on the complete ordered overlap list
-    def stage1_begin(self):
-        n = self.rs.n
-        self.piles = [np.zeros(int(x) >> 4, np.uint16) for x in self.lens]
-        self.lists = [np.zeros((0, 8), np.uint32) for _ in range(n)]
+    def overlaps_split(self, parts, rank):
+        runs = [self.ovl if d == rank else self.ovl[self.ovl[:, 3] % parts == d]
+                for d in range(parts)]
+        ov = np.concatenate(runs)
+        return (torch.from_numpy(ov.view(np.int32).reshape(-1, 8).copy()),
+                [r.shape[0] for r in runs])
+
+    # -- construct.cc:66-112 for the owned reads
+    def stage1_begin(self, parts, rank):
+        self.parts, self.rank = parts, rank
+        self.own = list(range(rank, self.rs.n, parts))
+        self.piles = {r: np.zeros(int(self.lens[r]) >> 4, np.uint16) for r in self.own}
+        self.lists = {r: np.zeros((0, 8), np.uint32) for r in self.own}
         self.mapped = 0
 
-    def stage1_add(self, ovl, off, n_query, kmax, qb):
+    def stage1_add(self, ovl, run_counts, n_query, kmax, qb):
         qb = qb or (1 << 30)
         ovl = ovl.numpy().view(np.uint32).reshape(-1, 8)
-        n = self.rs.n
-        seen = [x.shape[0] for x in self.lists]
+        self._check_runs(ovl[:, 0], run_counts)
+        ovl = ovl[np.argsort(ovl[:, 0], kind="stable")]  # merge by query
+        off = np.searchsorted(ovl[:, 0], np.arange(n_query + 1))
         bases, k0 = 0, 0
         for k in range(n_query):
             bases += int(self.lens[k])
             if k != n_query - 1 and bases < qb:
                 continue
             bases = 0
-            new = [[] for _ in range(n)]
+            new = {}
             for o in ovl[int(off[k0]):int(off[k + 1])]:
-                self.mapped += 1
-                new[o[0]].append(o)
-                new[o[3]].append(o[[3, 4, 5, 0, 1, 2, 6, 7]])
-            for r in range(n):
-                if not new[r]:
-                    continue
-                add = np.array(new[r], dtype=np.uint32).reshape(-1, 8)
+                if o[0] % self.parts == self.rank:
+                    new.setdefault(int(o[0]), []).append(o)
+                if o[3] % self.parts == self.rank:
+                    new.setdefault(int(o[3]), []).append(o[[3, 4, 5, 0, 1, 2, 6, 7]])
+            for r, add in new.items():
+                add = np.array(add, dtype=np.uint32).reshape(-1, 8)
                 self.piles[r] = self.o.pile_add_layers(r, self.piles[r], add)
                 self.lists[r] = self.o.truncate(np.concatenate([self.lists[r], add]), kmax)
             k0 = k + 1
@@ -138,10 +153,13 @@ class NumpySteps:
     def stage1_end(self):
         pass
 
-    def stage1_results(self, n):
+    def stage1_results(self):
+        n = len(self.own)
         off = np.zeros(n + 1, np.uint64)
-        off[1:] = np.cumsum([x.shape[0] for x in self.lists])
+        off[1:] = np.cumsum([self.lists[r].shape[0] for r in self.own])
         poff = np.zeros(n + 1, np.uint64)
-        poff[1:] = np.cumsum([x.size for x in self.piles])
-        return dict(overlaps=np.concatenate(self.lists).reshape(-1, 8), ovl_off=off,
-                    pile=np.concatenate(self.piles), pile_off=poff, num_mapped=self.mapped)
+        poff[1:] = np.cumsum([self.piles[r].size for r in self.own])
+        ov = np.concatenate([self.lists[r] for r in self.own]) if n else np.zeros((0, 8))
+        pl = np.concatenate([self.piles[r] for r in self.own]) if n else np.zeros(0)
+        return dict(overlaps=ov.reshape(-1, 8).astype(np.uint32), ovl_off=off,
+                    pile=pl.astype(np.uint16), pile_off=poff, num_mapped=self.mapped)

@@ -36,7 +36,10 @@ def _worker(rank, world, port, cfg, out_dir):
         rs = synth.make_reads(**cfg["reads"])
         steps = NumpySteps(oracle_lib.Oracle(), rs)
         res = distributed.find_overlaps_and_create_piles(
-            steps, rs.lens, cfg["freq"], cfg["kmax"], cfg["ib"], cfg["qb"])
+            steps, rs.lens, cfg["freq"], cfg["kmax"], cfg["minhash"], cfg["ib"], cfg["qb"])
+        share = int(res["ovl_off"].size) - 1
+        assert share == len(range(rank, rs.n, world))
+        res = distributed.assemble(res)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"),
                  **{k: np.asarray(v) for k, v in res.items()})
     finally:
@@ -45,15 +48,19 @@ def _worker(rank, world, port, cfg, out_dir):
 
 CASES = [
     dict(reads=dict(genome_len=40_000, n_reads=90, mean_len=5000, seed=3), freq=0.001,
-         kmax=16, ib=0, qb=0),
+         kmax=16, ib=0, qb=0, minhash=True),
+    dict(reads=dict(genome_len=40_000, n_reads=90, mean_len=5000, seed=4), freq=0.001,
+         kmax=16, ib=0, qb=0, minhash=False),
     # several index batches and query flushes; truncation active
     dict(reads=dict(genome_len=30_000, n_reads=100, mean_len=4000, seed=5), freq=0.01,
-         kmax=8, ib=150_000, qb=60_000),
+         kmax=8, ib=150_000, qb=60_000, minhash=True),
+    dict(reads=dict(genome_len=30_000, n_reads=100, mean_len=4000, seed=6), freq=0.01,
+         kmax=8, ib=150_000, qb=60_000, minhash=False),
 ]
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("case", [0, 1])
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
 def test_schedule_over_gloo_equals_oracle(oracle, tmp_path, world, case):
     from raven_b200 import synth
     cfg = CASES[case]
@@ -61,7 +68,7 @@ def test_schedule_over_gloo_equals_oracle(oracle, tmp_path, world, case):
              join=True)
     rs = synth.make_reads(**cfg["reads"])
     want = oracle.stage1(oracle.engine(15, 5), oracle.reads(rs), cfg["freq"], cfg["kmax"],
-                         True, cfg["ib"] or 1 << 32, cfg["qb"] or 1 << 30)
+                         cfg["minhash"], cfg["ib"] or 1 << 32, cfg["qb"] or 1 << 30)
     assert want["overlaps"].shape[0] > 50
     for r in range(world):
         got = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
@@ -77,16 +84,11 @@ def test_partitions():
     rng = np.random.default_rng(1)
     lens = rng.integers(100, 20_000, 1000)
     for parts in (1, 2, 3, 8):
-        sb, cb = d.sketch_bounds(lens, parts), d.chain_bounds(lens, parts)
-        for b in (sb, cb):
-            assert b[0] == 0 and b[-1] == len(lens) and len(b) == parts + 1
-            assert all(x <= y for x, y in zip(b, b[1:]))
+        sb = d.sketch_bounds(lens, parts)
+        assert sb[0] == 0 and sb[-1] == len(lens) and len(sb) == parts + 1
+        assert all(x <= y for x, y in zip(sb, sb[1:]))
         share = [lens[a:b].sum() / lens.sum() for a, b in zip(sb, sb[1:])]
         assert max(share) - min(share) < 0.02
-        # equal triangular work: sum over the part of (bases above the read)
-        cum = np.cumsum(lens[::-1])[::-1]
-        work = [float((lens[a:b] * cum[a:b]).sum()) for a, b in zip(cb, cb[1:])]
-        assert max(work) / (sum(work) / parts) < 1.05
     assert d.index_batches([5, 5, 5, 5, 5], 10) == [(0, 2), (2, 4), (4, 5)]
     assert d.index_batches([5, 5], 0) == [(0, 2)]
     assert d.sketch_bounds([], 2) == [0, 0, 0]

@@ -41,8 +41,9 @@ class ThreadComm:
         got = self._swap(mine)
         out = [torch.cat([got[src][i][self.rank] for src in range(self.world)])
                for i in range(len(tensors))]
+        counts = [int(got[src][0][self.rank].shape[0]) for src in range(self.world)]
         torch.cuda.synchronize()
-        return out
+        return out, counts
 
     def all_gather_v(self, t):
         got = self._swap(t.clone())
@@ -54,8 +55,11 @@ class ThreadComm:
         got = self._swap(t.clone())
         return torch.stack(got).sum(0)
 
+    def gather_objects(self, obj):
+        return self._swap(obj)
 
-def run_virtual(rs, world, freq, kmax, ib, qb, params=None):
+
+def run_virtual(rs, world, freq, kmax, ib, qb, params=None, minhash=True):
     shared = ThreadComm.Shared(world)
     res, err = [None] * world, [None] * world
 
@@ -63,7 +67,9 @@ def run_virtual(rs, world, freq, kmax, ib, qb, params=None):
         try:
             de = distributed.DistEngine("cuda:0", ThreadComm(shared, rank), **(params or {}))
             de.upload(rs)
-            res[rank] = de.find_overlaps_and_create_piles(freq, kmax, ib, qb)
+            share = de.find_overlaps_and_create_piles(freq, kmax, minhash, ib, qb)
+            assert share["ovl_off"].size - 1 == len(range(rank, rs.n, world))
+            res[rank] = distributed.assemble(share, de.comm)
             de.engine.close()
         except BaseException as e:  # noqa: BLE001
             err[rank] = e
@@ -89,23 +95,25 @@ def check(res, want):
         assert int(got["num_mapped"]) == int(np.asarray(want["num_mapped"]).ravel()[0])
 
 
+@pytest.mark.parametrize("minhash", [False, True])
 @pytest.mark.parametrize("world", [1, 2, 3])
-def test_virtual_ranks_equal_oracle(oracle, world):
+def test_virtual_ranks_equal_oracle(oracle, world, minhash):
     rs = synth.make_reads(60_000, 150, 6000, seed=11)
-    want = oracle.stage1(oracle.engine(15, 5), oracle.reads(rs), 0.001, 16, True)
+    want = oracle.stage1(oracle.engine(15, 5), oracle.reads(rs), 0.001, 16, minhash)
     assert want["overlaps"].shape[0] > 200
-    res = run_virtual(rs, world, 0.001, 16, 0, 0)
+    res = run_virtual(rs, world, 0.001, 16, 0, 0, minhash=minhash)
     check(res, want)
     assert list(res[0]["occurrences"]) == list(want["occurrences"])
 
 
+@pytest.mark.parametrize("minhash", [False, True])
 @pytest.mark.parametrize("world", [2, 4])
-def test_virtual_ranks_multi_batch_schedule(oracle, world):
+def test_virtual_ranks_multi_batch_schedule(oracle, world, minhash):
     rs = synth.make_reads(40_000, 160, 4000, seed=12)
     ib, qb = 200_000, 70_000
-    want = oracle.stage1(oracle.engine(15, 5), oracle.reads(rs), 0.01, 8, True, ib, qb)
+    want = oracle.stage1(oracle.engine(15, 5), oracle.reads(rs), 0.01, 8, minhash, ib, qb)
     assert len(want["occurrences"]) >= 3
-    res = run_virtual(rs, world, 0.01, 8, ib, qb)
+    res = run_virtual(rs, world, 0.01, 8, ib, qb, minhash=minhash)
     check(res, want)
     assert list(res[0]["occurrences"]) == list(want["occurrences"])
 
