@@ -323,7 +323,9 @@ def main_ours(a):
                        f"{world} ranks: reads sharded by id, index keys by value mod "
                        f"{world}, reads (queries, piles, lists) by id mod {world}; NCCL "
                        "all-to-all of minimizer records, of seed hits and of overlaps; "
-                       "results stay sharded (d2h = this rank's share)"},
+                       "results stay sharded (d2h = this rank's share)",
+                       "exchange": "-" if world == 1 else
+                       f"{de.exchange} {getattr(de.comm, 'stats', '')}"},
             "clocks": clocks,
             "e2e": {"value": total_mapped * a.steps / (ms_e2e * 1e-3), "unit": "overlaps/s",
                     "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d,

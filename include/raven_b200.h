@@ -268,6 +268,23 @@ int rvn_dist_stage1_results(rvn_ctx* ctx, const rvn_overlap** overlaps,
                             const uint64_t** pile_off, uint32_t* n_owned,
                             uint64_t* n_mapped);
 
+/* ---- peer-memory exchange: the all-to-alls of the schedule as direct DMA
+ * writes into the destination rank's receive arena over NVLink (CUDA IPC; one
+ * process per GPU on one node). export: (re)allocate this rank's arena, 64-byte
+ * handle out; import: map the peers' arenas from all n_parts handles (own slot
+ * ignored); put: asynchronous copy of device memory into rank dest's arena at
+ * dst_offset; put_flush: wait for this rank's puts. All arenas must have the
+ * same size (the caller checks offsets against it); the caller brackets a
+ * round of puts with barriers and closes the peers before any re-export. */
+int rvn_dist_arena_export(rvn_ctx* ctx, uint64_t bytes, void* handle64);
+int rvn_dist_arena_import(rvn_ctx* ctx, uint32_t n_parts, uint32_t rank,
+                          const void* handles);
+int rvn_dist_arena_close_peers(rvn_ctx* ctx);
+int rvn_dist_arena(rvn_ctx* ctx, void** d_arena, uint64_t* bytes);
+int rvn_dist_put(rvn_ctx* ctx, uint32_t dest, uint64_t dst_offset, const void* d_src,
+                 uint64_t bytes);
+int rvn_dist_put_flush(rvn_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,13 @@ SIGNATURES = {
     "rvn_dist_stage1_end": (C.c_int, [C.c_void_p]),
     "rvn_dist_stage1_results": (C.c_int, [C.c_void_p, C.POINTER(OVLP), C.POINTER(U64P),
                                           C.POINTER(U16P), C.POINTER(U64P), U32P, U64P]),
+    "rvn_dist_arena_export": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
+    "rvn_dist_arena_import": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "rvn_dist_arena_close_peers": (C.c_int, [C.c_void_p]),
+    "rvn_dist_arena": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), U64P]),
+    "rvn_dist_put": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p,
+                               C.c_uint64]),
+    "rvn_dist_put_flush": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

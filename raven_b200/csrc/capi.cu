@@ -170,6 +170,7 @@ RVN_API void rvn_ctx_destroy(rvn_ctx* ctx) {
     if (p.second) cudaEventDestroy(p.second);
   }
   for (auto e : ctx->c.timer.pool) cudaEventDestroy(e);
+  ArenaRelease(ctx->c);
   if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
   delete ctx;
 }
@@ -671,6 +672,45 @@ RVN_API int rvn_dist_stage1_results(rvn_ctx* ctx, const rvn_overlap** overlaps,
     if (n_owned) *n_owned = c.ds_n_own;
     if (n_mapped) *n_mapped = c.st_mapped;
   });
+}
+
+// ---- peer-memory exchange (dist.cu) ----
+RVN_API int rvn_dist_arena_export(rvn_ctx* ctx, uint64_t bytes, void* handle64) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (!handle64) throw InvalidArgument("null handle");
+    ArenaExport(c, bytes, handle64);
+  });
+}
+
+RVN_API int rvn_dist_arena_import(rvn_ctx* ctx, uint32_t n_parts, uint32_t rank,
+                                  const void* handles) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (!handles) throw InvalidArgument("null handles");
+    ArenaImport(c, n_parts, rank, handles);
+  });
+}
+
+RVN_API int rvn_dist_arena_close_peers(rvn_ctx* ctx) {
+  return Guard(ctx, [&](Ctx& c) { ArenaClosePeers(c); });
+}
+
+RVN_API int rvn_dist_arena(rvn_ctx* ctx, void** d_arena, uint64_t* bytes) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (d_arena) *d_arena = c.x_arena;
+    if (bytes) *bytes = c.x_cap;
+  });
+}
+
+RVN_API int rvn_dist_put(rvn_ctx* ctx, uint32_t dest, uint64_t dst_offset,
+                         const void* d_src, uint64_t bytes) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (dst_offset + bytes > c.x_cap) throw LimitError("arena overflow");
+    ArenaPut(c, dest, dst_offset, d_src, bytes);
+  });
+}
+
+RVN_API int rvn_dist_put_flush(rvn_ctx* ctx) {
+  return Guard(ctx, [&](Ctx& c) { ArenaFlush(c); });
 }
 
 }  // extern "C"

@@ -27,6 +27,7 @@
 //   6. DistStage1Add     merge by query, then piles + lists of the OWNED reads
 //        with the reference's flush schedule; End compacts them for the host.
 #include <algorithm>
+#include <cstring>
 
 #include "engine.cuh"
 
@@ -782,6 +783,79 @@ void DistStage1End(Ctx& c) {
   c.ds_results_valid = true;
   c.own_mod = 1;
   c.own_rem = 0;
+}
+
+// ---------------------------------------------------------------------------
+// Peer-memory exchange: every rank owns a receive arena that its peers map
+// through CUDA IPC; an all-to-all is then one DMA write per (array, peer)
+// straight into the destination's arena over NVLink (copy engines, no staging,
+// no NCCL). The caller (raven_b200/distributed.py: P2PComm) agrees on the
+// layout from the exchanged count matrix and brackets the writes with barriers.
+// ---------------------------------------------------------------------------
+void ArenaClosePeers(Ctx& c) {
+  for (uint32_t p = 0; p < c.x_peers.size(); ++p) {
+    if (p != c.x_rank && c.x_peers[p]) cudaIpcCloseMemHandle(c.x_peers[p]);
+  }
+  c.x_peers.clear();
+}
+
+void ArenaExport(Ctx& c, uint64_t bytes, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  ArenaClosePeers(c);
+  if (c.x_arena) {
+    RVN_CUDA(cudaFree(c.x_arena));
+    c.x_arena = nullptr;
+    c.x_cap = 0;
+  }
+  if (bytes == 0) throw InvalidArgument("empty arena");
+  RVN_CUDA(cudaMalloc(&c.x_arena, bytes));
+  c.x_cap = bytes;
+  cudaIpcMemHandle_t h;
+  RVN_CUDA(cudaIpcGetMemHandle(&h, c.x_arena));
+  std::memcpy(handle64, &h, 64);
+}
+
+void ArenaImport(Ctx& c, uint32_t parts, uint32_t rank, const void* handles) {
+  CheckParts(parts, rank);
+  if (!c.x_arena) throw StateError("export the arena first");
+  ArenaClosePeers(c);
+  c.x_rank = rank;
+  c.x_peers.assign(parts, nullptr);
+  for (uint32_t p = 0; p < parts; ++p) {
+    if (p == rank) {
+      c.x_peers[p] = c.x_arena;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const char*>(handles) + 64ULL * p, 64);
+    RVN_CUDA(cudaIpcOpenMemHandle(&c.x_peers[p], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  while (c.x_streams.size() < parts) {
+    cudaStream_t st;
+    RVN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    c.x_streams.push_back(st);
+  }
+}
+
+void ArenaPut(Ctx& c, uint32_t dest, uint64_t dst_off, const void* d_src, uint64_t bytes) {
+  if (dest >= c.x_peers.size() || !c.x_peers[dest]) throw StateError("no such peer arena");
+  if (bytes == 0) return;
+  if (!d_src) throw InvalidArgument("null source");
+  RVN_CUDA(cudaMemcpyAsync(static_cast<char*>(c.x_peers[dest]) + dst_off, d_src, bytes,
+                           cudaMemcpyDefault, c.x_streams[dest]));
+}
+
+void ArenaFlush(Ctx& c) {
+  for (auto st : c.x_streams) RVN_CUDA(cudaStreamSynchronize(st));
+}
+
+void ArenaRelease(Ctx& c) {
+  ArenaClosePeers(c);
+  if (c.x_arena) cudaFree(c.x_arena);
+  c.x_arena = nullptr;
+  c.x_cap = 0;
+  for (auto st : c.x_streams) cudaStreamDestroy(st);
+  c.x_streams.clear();
 }
 
 }  // namespace rvn

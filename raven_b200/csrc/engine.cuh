@@ -168,6 +168,12 @@ struct Ctx {
   PinBuf<uint16_t> ds_r_pile;
   uint32_t ds_n_own = 0;
   bool ds_results_valid = false;
+  // peer-memory exchange: own receive arena + the peers' arenas (CUDA IPC)
+  void* x_arena = nullptr;
+  uint64_t x_cap = 0;
+  uint32_t x_rank = 0;
+  std::vector<void*> x_peers;
+  std::vector<cudaStream_t> x_streams;
 
   // pinned scalars for small D2H reads
   PinBuf<uint64_t> pin64;
@@ -244,6 +250,12 @@ void DistStage1Begin(Ctx& c, uint32_t parts, uint32_t rank);
 void DistStage1Add(Ctx& c, const rvn_overlap* d_ovl, uint64_t n_ovl, uint32_t n_seg,
                    const uint64_t* h_seg_off, uint32_t n_query, uint64_t kmax, uint64_t qb);
 void DistStage1End(Ctx& c);
+void ArenaClosePeers(Ctx& c);
+void ArenaExport(Ctx& c, uint64_t bytes, void* handle64);
+void ArenaImport(Ctx& c, uint32_t parts, uint32_t rank, const void* handles);
+void ArenaPut(Ctx& c, uint32_t dest, uint64_t dst_off, const void* d_src, uint64_t bytes);
+void ArenaFlush(Ctx& c);
+void ArenaRelease(Ctx& c);
 
 // ---- pile.cu ----
 // data: device u16 bins, off: device u64 offsets (n_piles + 1)

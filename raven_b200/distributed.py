@@ -48,17 +48,17 @@ def sketch_bounds(lens, parts):
 
 
 def index_batches(lens, index_batch_bases):
-    """[j, i1) read ranges of the reference's index batches (construct.cc:36-41)."""
-    ib = index_batch_bases or (1 << 32)
-    out, bases, j = [], 0, 0
+    """[j, i1) read ranges of the reference's index batches (construct.cc:36-41):
+    a batch closes with the read that brings its bases to the threshold."""
+    ib = int(index_batch_bases) or (1 << 32)
     n = len(lens)
-    for i in range(n):
-        bases += int(lens[i])
-        if i != n - 1 and bases < ib:
-            continue
-        bases = 0
-        out.append((j, i + 1))
-        j = i + 1
+    cum = np.concatenate([[0], np.cumsum(np.asarray(lens, dtype=np.uint64), dtype=np.uint64)])
+    out, j = [], 0
+    while j < n:
+        i1 = int(np.searchsorted(cum, int(cum[j]) + ib, side="left"))
+        i1 = min(max(i1, j + 1), n)
+        out.append((j, i1))
+        j = i1
     return out
 
 
@@ -82,6 +82,7 @@ class TorchComm:
         """Rows [sum(send_counts)] of every tensor, split by destination rank ->
         (rows received from every rank, concatenated in source-rank order;
         rows per source rank)."""
+        tensors = [_as_torch(t) for t in tensors]
         device = tensors[0].device
         recv_counts = self._exchange_counts(send_counts, device)
         n_recv = sum(recv_counts)
@@ -114,11 +115,116 @@ class TorchComm:
         dist.all_reduce(t, group=self.group)
         return t
 
+    def begin_step(self):
+        pass
+
     def gather_objects(self, obj):
         """[obj of rank 0, obj of rank 1, ...] on every rank (host data)."""
         out = [None] * self.world
         dist.all_gather_object(out, obj, group=self.group)
         return out
+
+
+class P2PComm(TorchComm):
+    """The all-to-alls as direct DMA writes into the destination's receive arena
+    over NVLink (rvn_dist_put: CUDA IPC peer memory, copy engines) instead of
+    NCCL send/recv.  The arena is bump-allocated over one step: every rank sees
+    the whole count matrix, so every rank knows every arena's layout.  An
+    exchange that does not fit goes through NCCL and the arena is re-sized at
+    the next step boundary."""
+
+    ALIGN = 256
+
+    def __init__(self, engine, device, group=None, arena_bytes=1 << 28):
+        super().__init__(group)
+        self.e, self.lib, self.h = engine, engine.lib, engine.h
+        self.device = torch.device(device)
+        self.cap = 0
+        self.want = int(arena_bytes)
+        self.bump = [0] * self.world
+        self.arena = 0
+        self.stats = {"p2p": 0, "nccl": 0}
+        self._resize()
+
+    def _resize(self):
+        err = None
+
+        def call(rc):  # keep taking part in the collectives even if a call fails
+            nonlocal err
+            if rc != 0 and err is None:
+                err = self.lib.rvn_last_error(self.h).decode()
+
+        dist.barrier(group=self.group)  # nobody reads or writes an arena now
+        call(self.lib.rvn_dist_arena_close_peers(self.h))
+        dist.barrier(group=self.group)  # every mapping is closed: arenas may be freed
+        handle = (C.c_uint8 * 64)()
+        call(self.lib.rvn_dist_arena_export(self.h, self.want, handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=self.group)
+        blob = (C.c_uint8 * (64 * self.world)).from_buffer_copy(b"".join(handles))
+        if err is None:
+            call(self.lib.rvn_dist_arena_import(self.h, self.world, self.rank, blob))
+        ptr, cap = C.c_void_p(), C.c_uint64(0)
+        call(self.lib.rvn_dist_arena(self.h, C.byref(ptr), C.byref(cap)))
+        self.arena, self.cap = ptr.value or 0, cap.value
+        bad = torch.tensor([0 if err is None else 1], device=self.device)
+        dist.all_reduce(bad, group=self.group)
+        if bad.item():
+            raise RuntimeError("peer-memory exchange unavailable: " + (err or "on another rank"))
+
+    def begin_step(self):
+        need = max(self.bump)  # bytes the last step wanted in the fullest arena
+        if need > self.cap:
+            self.want = int(need * 1.25) + (1 << 20)
+            self._resize()
+        else:
+            dist.barrier(group=self.group)  # the previous step is consumed everywhere
+        self.bump = [0] * self.world
+
+    def all_to_all_v(self, arrays, send_counts):
+        world, me = self.world, self.rank
+        s = torch.tensor(send_counts, dtype=torch.int64, device=self.device)
+        m = torch.empty(world * world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(m, s, group=self.group)
+        m = m.cpu().numpy().reshape(world, world)  # m[src][dst] rows
+        recv_counts = [int(x) for x in m[:, me]]
+        rows_to = m.sum(axis=0)
+        rb = [a.row_bytes() if isinstance(a, DevArray) else
+              a.element_size() * int(np.prod(a.shape[1:])) for a in arrays]
+        # layout of this exchange in every destination arena
+        base = [[0] * world for _ in arrays]
+        fits = True
+        for d in range(world):
+            at = self.bump[d]
+            for t, b in enumerate(rb):
+                at = (at + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+                base[t][d] = at
+                at += int(rows_to[d]) * b
+            self.bump[d] = at
+            fits = fits and at <= self.cap
+        if not fits:  # same verdict on every rank
+            self.stats["nccl"] += 1
+            return super().all_to_all_v(arrays, send_counts)
+        self.stats["p2p"] += 1
+        before = m[:me, :].sum(axis=0)  # rows of lower ranks in every destination
+        send_off = np.concatenate([[0], np.cumsum(send_counts)])
+        for t, a in enumerate(arrays):
+            src = a.data_ptr()
+            for k in range(world):
+                d = (me + k) % world
+                nbytes = int(send_counts[d]) * rb[t]
+                if nbytes:
+                    self.e._check(self.lib.rvn_dist_put(
+                        self.h, d, base[t][d] + int(before[d]) * rb[t],
+                        C.c_void_p(src + int(send_off[d]) * rb[t]), nbytes))
+        self.e._check(self.lib.rvn_dist_put_flush(self.h))
+        dist.barrier(group=self.group)  # every rank's writes have landed
+        n_recv = int(rows_to[me])
+        out = []
+        for t, a in enumerate(arrays):
+            shape = (n_recv,) + tuple(a.shape[1:])
+            out.append(DevArray(self.arena + base[t][me], shape, a.dtype, self.device))
+        return out, recv_counts
 
 
 # ---------------------------------------------------------------- the schedule
@@ -149,6 +255,7 @@ def find_overlaps_and_create_piles(steps, lens, frequency=0.001, max_overlaps=32
         trace[name] = trace.get(name, 0.0) + 1e3 * (now - t_last[0])
         t_last[0] = now
 
+    comm.begin_step()
     steps.stage1_begin(world, rank)
     tick("begin")
     occurrences = []
@@ -253,11 +360,39 @@ class _DevMem:
             "strides": None}
 
 
+_TYPESTR = {torch.int64: "<i8", torch.int32: "<i4"}
+
+
 def _view(ptr, shape, typestr, dtype, device):
     n = int(np.prod(shape))
     if n == 0 or not ptr:
         return torch.empty(shape, dtype=dtype, device=device)
     return torch.as_tensor(_DevMem(ptr, tuple(shape), typestr), device=device)
+
+
+class DevArray:
+    """A typed window of device memory (context- or arena-owned): just enough of
+    the tensor interface for the schedule; ``torch()`` gives a real tensor view
+    when an exchange goes through torch.distributed."""
+
+    def __init__(self, ptr, shape, dtype, device):
+        self.ptr, self.shape, self.dtype, self.device = ptr or 0, tuple(shape), dtype, device
+
+    def data_ptr(self):
+        return self.ptr
+
+    def numel(self):
+        return int(np.prod(self.shape))
+
+    def row_bytes(self):
+        return int(np.prod(self.shape[1:])) * torch.empty(0, dtype=self.dtype).element_size()
+
+    def torch(self):
+        return _view(self.ptr, self.shape, _TYPESTR[self.dtype], self.dtype, self.device)
+
+
+def _as_torch(t):
+    return t.torch() if isinstance(t, DevArray) else t
 
 
 class CudaSteps:
@@ -284,7 +419,7 @@ class CudaSteps:
             return out
         return wrapped
 
-    def _p(self, t):
+    def _p(self, t):  # torch tensor or DevArray
         return C.c_void_p(t.data_ptr() if t.numel() else 0)
 
     def sketch_split(self, first, last, parts, minhash):
@@ -294,8 +429,8 @@ class CudaSteps:
             self.h, first, last, int(minhash), parts, C.byref(v), C.byref(o), cnt))
         cnt = [int(x) for x in cnt]
         n = sum(cnt)
-        return (_view(v.value, (n,), "<i8", torch.int64, self.device),
-                _view(o.value, (n,), "<i8", torch.int64, self.device), cnt)
+        return (DevArray(v.value, (n,), torch.int64, self.device),
+                DevArray(o.value, (n,), torch.int64, self.device), cnt)
 
     def build_index(self, val, org, bases):
         self._keep_index = (val, org)
@@ -323,9 +458,9 @@ class CudaSteps:
             C.byref(g), C.byref(p), C.byref(l), cnt))
         cnt = [int(x) for x in cnt]
         n = sum(cnt)
-        return (_view(g.value, (n,), "<i8", torch.int64, self.device),
-                _view(p.value, (n,), "<i8", torch.int64, self.device),
-                _view(l.value, (n,), "<i4", torch.int32, self.device), cnt)
+        return (DevArray(g.value, (n,), torch.int64, self.device),
+                DevArray(p.value, (n,), torch.int64, self.device),
+                DevArray(l.value, (n,), torch.int32, self.device), cnt)
 
     @staticmethod
     def _runs(counts):
@@ -343,7 +478,7 @@ class CudaSteps:
         cnt = (C.c_uint64 * parts)()
         self.e._check(self.lib.rvn_dist_overlaps_split(self.h, parts, rank, C.byref(o), cnt))
         cnt = [int(x) for x in cnt]
-        return _view(o.value, (sum(cnt), 8), "<i4", torch.int32, self.device), cnt
+        return DevArray(o.value, (sum(cnt), 8), torch.int32, self.device), cnt
 
     def stage1_begin(self, parts, rank):
         self.e._check(self.lib.rvn_dist_stage1_begin(self.h, parts, rank))
@@ -375,15 +510,27 @@ class DistEngine:
     work stream is also torch's current stream while the schedule runs, so the
     NCCL exchanges and the kernels order on one stream."""
 
-    def __init__(self, device, comm=None, **params):
+    def __init__(self, device, comm=None, exchange="p2p", **params):
+        """comm: an exchange object (tests), or None for torch.distributed's
+        default group with exchange = "p2p" (peer-memory DMA, falls back to NCCL
+        if CUDA IPC is unavailable) or "nccl"."""
         from .engine import Engine
         self.device = torch.device(device)
-        self.comm = comm
         self.stream = torch.cuda.Stream(self.device)
         self.engine = Engine(self.device.index or 0, stream=self.stream.cuda_stream)
         if params:
             self.engine.configure(**params)
         self.lens = None
+        self.exchange = "custom"
+        if comm is None:
+            comm, self.exchange = TorchComm(), "nccl"
+            if exchange == "p2p" and comm.world > 1:
+                try:  # (fails on every rank together: no IPC / no peer access)
+                    with torch.cuda.device(self.device):
+                        comm, self.exchange = P2PComm(self.engine, self.device), "p2p"
+                except RuntimeError as e:
+                    self.p2p_error = str(e)
+        self.comm = comm
 
     def upload(self, rs):
         self.engine.upload(rs)

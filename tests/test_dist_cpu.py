@@ -89,6 +89,21 @@ def test_partitions():
         assert all(x <= y for x, y in zip(sb, sb[1:]))
         share = [lens[a:b].sum() / lens.sum() for a, b in zip(sb, sb[1:])]
         assert max(share) - min(share) < 0.02
+    def loop(lens, ib):  # construct.cc:36-41 as written
+        ib = ib or (1 << 32)
+        out, bases, j, n = [], 0, 0, len(lens)
+        for i in range(n):
+            bases += int(lens[i])
+            if i != n - 1 and bases < ib:
+                continue
+            bases = 0
+            out.append((j, i + 1))
+            j = i + 1
+        return out
+    for _ in range(200):
+        lens = rng.integers(0, 30, int(rng.integers(0, 40)))
+        ib = int(rng.integers(0, 60))
+        assert d.index_batches(lens, ib) == loop(lens, ib)
     assert d.index_batches([5, 5, 5, 5, 5], 10) == [(0, 2), (2, 4), (4, 5)]
     assert d.index_batches([5, 5], 0) == [(0, 2)]
     assert d.sketch_bounds([], 2) == [0, 0, 0]

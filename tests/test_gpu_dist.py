@@ -37,6 +37,7 @@ class ThreadComm:
 
     def all_to_all_v(self, tensors, send_counts):
         off = np.concatenate([[0], np.cumsum(send_counts)])
+        tensors = [distributed._as_torch(t) for t in tensors]
         mine = [[t[off[d]:off[d + 1]].clone() for d in range(self.world)] for t in tensors]
         got = self._swap(mine)
         out = [torch.cat([got[src][i][self.rank] for src in range(self.world)])
@@ -57,6 +58,9 @@ class ThreadComm:
 
     def gather_objects(self, obj):
         return self._swap(obj)
+
+    def begin_step(self):
+        pass
 
 
 def run_virtual(rs, world, freq, kmax, ib, qb, params=None, minhash=True):
