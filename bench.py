@@ -301,6 +301,10 @@ def main_ours(a):
         if os.path.exists(prof):
             traffic = json.load(open(prof)).get(dom)
         h2d = int(prs.words.nbytes + prs.word_off.nbytes + prs.lens.nbytes)
+        if world > 1:  # bases of this rank's sketch range, lengths of all reads
+            sb = distributed.sketch_bounds(prs.lens, world)
+            h2d = int(8 * (prs.word_off[sb[1]] - prs.word_off[sb[0]])
+                      + prs.word_off.nbytes + prs.lens.nbytes)
         if world > 1:
             res = distributed.CudaSteps(eng, f"cuda:{local}").stage1_results()  # this rank's share
             d2h = int(res["overlaps"].nbytes + res["ovl_off"].nbytes + res["pile"].nbytes)

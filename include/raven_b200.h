@@ -95,6 +95,14 @@ int rvn_reads_upload(rvn_ctx* ctx, const uint64_t* words,
                      const uint64_t* word_off, const uint32_t* lens,
                      uint32_t n_reads);
 
+/* As rvn_reads_upload, but only the bases of reads [first,last) are copied to
+ * the device (lengths of all reads are): a rank of a partitioned run only
+ * sketches its own range. Sketching any other read is RVN_ERR_STATE. */
+int rvn_reads_upload_range(rvn_ctx* ctx, const uint64_t* words,
+                           const uint64_t* word_off, const uint32_t* lens,
+                           uint32_t n_reads, uint32_t first, uint32_t last);
+
+
 /* Same, with explicit sequence ids (biosoup::NucleicAcid::id): origins and
  * overlap ids carry ids[i] instead of i. raven re-sorts its sequence vector
  * before stage 2 (construct.cc:324-349), so id != position there. */

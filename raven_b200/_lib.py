@@ -37,6 +37,8 @@ SIGNATURES = {
     "rvn_last_error": (C.c_char_p, [C.c_void_p]),
     "rvn_engine_configure": (C.c_int, [C.c_void_p] + [C.c_uint32] * 6),
     "rvn_reads_upload": (C.c_int, [C.c_void_p, U64P, U64P, U32P, C.c_uint32]),
+    "rvn_reads_upload_range": (C.c_int, [C.c_void_p, U64P, U64P, U32P, C.c_uint32,
+                                         C.c_uint32, C.c_uint32]),
     "rvn_reads_upload_ids": (C.c_int, [C.c_void_p, U64P, U64P, U32P, U32P, C.c_uint32]),
     "rvn_map_external": (C.c_int, [C.c_void_p, U64P, C.c_uint32, C.c_uint32, C.c_int,
                                    C.c_int, C.c_int, C.c_int]),

@@ -198,8 +198,11 @@ RVN_API int rvn_engine_configure(rvn_ctx* ctx, uint32_t k, uint32_t w,
 
 static void UploadReads(Ctx& c, const uint64_t* words, const uint64_t* word_off,
                         const uint32_t* lens, const uint32_t* ids,
-                        uint32_t n_reads) {
+                        uint32_t n_reads, uint32_t res_first = 0,
+                        uint32_t res_last = 0xFFFFFFFFu) {
   if (n_reads && (!word_off || !lens)) throw InvalidArgument("null read set");
+  res_last = std::min(res_last, n_reads);
+  if (res_first > res_last) throw InvalidArgument("resident range out of bounds");
   if (n_reads == 0xFFFFFFFFu) throw LimitError("too many reads");
   c.s_valid = c.q_valid = c.i_valid = c.r_valid = c.st_valid = false;
   c.tiles_k = 0;
@@ -224,8 +227,13 @@ static void UploadReads(Ctx& c, const uint64_t* words, const uint64_t* word_off,
   uint64_t* dwo = c.d_woff.reserve(n_reads + 2ULL);
   uint32_t* dl = c.d_len.reserve(n_reads + 2ULL);
   uint32_t* di = c.d_ids.reserve(n_reads + 2ULL);
-  if (c.n_words) {
-    RVN_CUDA(cudaMemcpyAsync(dw, words, c.n_words * 8, cudaMemcpyHostToDevice,
+  // bases of the resident reads only (a rank of a partitioned run sketches its
+  // own range; lengths and ids of all reads are always resident)
+  c.res_first = res_first;
+  c.res_last = res_last;
+  const uint64_t w0 = c.h_woff[res_first], w1 = c.h_woff[res_last];
+  if (w1 > w0) {
+    RVN_CUDA(cudaMemcpyAsync(dw + w0, words + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice,
                              c.stream));
   }
   RVN_CUDA(cudaMemcpyAsync(dwo, c.h_woff.data(), (n_reads + 1ULL) * 8,
@@ -244,6 +252,14 @@ RVN_API int rvn_reads_upload(rvn_ctx* ctx, const uint64_t* words,
                              uint32_t n_reads) {
   return Guard(ctx, [&](Ctx& c) {
     UploadReads(c, words, word_off, lens, nullptr, n_reads);
+  });
+}
+
+RVN_API int rvn_reads_upload_range(rvn_ctx* ctx, const uint64_t* words,
+                                   const uint64_t* word_off, const uint32_t* lens,
+                                   uint32_t n_reads, uint32_t first, uint32_t last) {
+  return Guard(ctx, [&](Ctx& c) {
+    UploadReads(c, words, word_off, lens, nullptr, n_reads, first, last);
   });
 }
 

@@ -51,6 +51,7 @@ struct Ctx {
   std::vector<uint64_t> h_woff;
   std::vector<uint32_t> h_len, h_ids;
   bool ids_identity = true;  // id == index (needed by the device-side gather)
+  uint32_t res_first = 0, res_last = 0;  // reads whose bases are in HBM
   // sketch tiles: tile_off[r] = first tile of read r (depends on k)
   std::vector<uint64_t> h_tile_off;
   DevBuf<uint64_t> d_tile_off;

@@ -373,6 +373,9 @@ void EnsureTiles(Ctx& c) {
 
 void EnsureSketch(Ctx& c, uint32_t first, uint32_t last) {
   if (c.s_valid && c.s_first == first && c.s_last == last) return;
+  if (first < last && (first < c.res_first || last > c.res_last)) {
+    throw StateError("the bases of these reads were not uploaded (rvn_reads_upload_range)");
+  }
   EnsureTiles(c);
   c.s_valid = false;
   c.q_valid = false;

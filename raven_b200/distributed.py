@@ -533,8 +533,10 @@ class DistEngine:
         self.comm = comm
 
     def upload(self, rs):
-        self.engine.upload(rs)
+        """Lengths of all reads, bases of this rank's sketch range only."""
         self.lens = np.asarray(rs.lens, dtype=np.uint32)
+        sb = sketch_bounds(self.lens, self.comm.world)
+        self.engine.upload(rs, resident=(sb[self.comm.rank], sb[self.comm.rank + 1]))
 
     def find_overlaps_and_create_piles(self, freq=0.001, max_overlaps=32,
                                        use_minhash=False, index_batch_bases=0,

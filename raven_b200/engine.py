@@ -64,14 +64,21 @@ class Engine:
         self._check(self.lib.rvn_engine_configure(self.h, k, w, bandwidth, chain,
                                                   matches, gap))
 
-    def upload(self, rs):
+    def upload(self, rs, resident=None):
+        """resident = (first, last): copy only the bases of those reads to the
+        device (a rank of a partitioned run sketches its own range)."""
         words = np.ascontiguousarray(rs.words, dtype=np.uint64)
         woff = np.ascontiguousarray(rs.word_off, dtype=np.uint64)
         lens = np.ascontiguousarray(rs.lens, dtype=np.uint32)
         self._keep = (words, woff, lens)
-        self._check(self.lib.rvn_reads_upload(
-            self.h, words.ctypes.data_as(U64P), woff.ctypes.data_as(U64P),
-            lens.ctypes.data_as(U32P), rs.n))
+        if resident is None:
+            self._check(self.lib.rvn_reads_upload(
+                self.h, words.ctypes.data_as(U64P), woff.ctypes.data_as(U64P),
+                lens.ctypes.data_as(U32P), rs.n))
+        else:
+            self._check(self.lib.rvn_reads_upload_range(
+                self.h, words.ctypes.data_as(U64P), woff.ctypes.data_as(U64P),
+                lens.ctypes.data_as(U32P), rs.n, resident[0], resident[1]))
         self.n_reads = rs.n
 
     def minimize(self, first, last, minhash=False):
