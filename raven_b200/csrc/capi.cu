@@ -114,8 +114,7 @@ void Stage1(Ctx& c, double freq, uint64_t kmax, bool minhash, uint64_t ib,
   }
 
   GatherFetch(c);
-  c.st_pile.resize(total_bins);
-  RVN_CUDA(cudaMemcpyAsync(c.st_pile.data(), d_pile, total_bins * sizeof(uint16_t),
+  RVN_CUDA(cudaMemcpyAsync(c.st_pile.reserve(total_bins + 1), d_pile, total_bins * sizeof(uint16_t),
                            cudaMemcpyDeviceToHost, c.stream));
   RVN_CUDA(cudaStreamSynchronize(c.stream));
   TimerCollect(c);
@@ -212,6 +211,7 @@ static void UploadReads(Ctx& c, const uint64_t* words, const uint64_t* word_off,
   c.h_len.assign(lens, lens + n_reads);
   c.h_ids.resize(n_reads);
   c.ids_identity = true;
+  c.ids_ascending = true;
   for (uint32_t i = 0; i < n_reads; ++i) {
     const uint64_t have = c.h_woff[i + 1] - c.h_woff[i];
     if (have < ((static_cast<uint64_t>(lens[i]) + 31) >> 5)) {
@@ -220,6 +220,7 @@ static void UploadReads(Ctx& c, const uint64_t* words, const uint64_t* word_off,
     if (lens[i] >= (1u << 31)) throw LimitError("read of 2^31 or more bases");
     c.h_ids[i] = ids ? ids[i] : i;
     if (c.h_ids[i] != i) c.ids_identity = false;
+    if (i > 0 && c.h_ids[i] < c.h_ids[i - 1]) c.ids_ascending = false;
   }
   c.n_words = c.h_woff[n_reads];
   // one spare slot everywhere: an external query read rides at index n_reads
@@ -450,9 +451,9 @@ RVN_API int rvn_stage1_results(rvn_ctx* ctx, const rvn_overlap** overlaps,
                                const uint64_t** pile_off, uint64_t* n_mapped) {
   return Guard(ctx, [&](Ctx& c) {
     if (!c.st_valid) throw StateError("no stage-1 results");
-    if (overlaps) *overlaps = c.st_ovl.data();
-    if (ovl_off) *ovl_off = c.st_ovl_off.data();
-    if (pile) *pile = c.st_pile.data();
+    if (overlaps) *overlaps = c.st_ovl.get();
+    if (ovl_off) *ovl_off = c.st_ovl_off.get();
+    if (pile) *pile = c.st_pile.get();
     if (pile_off) *pile_off = c.st_pile_off.data();
     if (n_mapped) *n_mapped = c.st_mapped;
   });
@@ -578,6 +579,8 @@ RVN_API int rvn_dist_index(rvn_ctx* ctx, const uint64_t* d_value,
     if (n_records && (!d_value || !d_origin)) throw InvalidArgument("null records");
     c.i_first = c.i_last = 0;
     BuildIndexFrom(c, d_value, d_origin, n_records, index_bases);
+    // (records of a partitioned run arrive in read order: the caller's contract)
+    c.i_sorted_ids = c.ids_ascending;
     RVN_CUDA(cudaStreamSynchronize(c.stream));
   });
 }

@@ -80,8 +80,10 @@ struct Ctx {
   DevBuf<uint64_t> i_val, i_org, i_val_alt, i_org_alt;
   DevBuf<uint32_t> i_bucket;
   int i_bucket_bits = 0;
-  DevBuf<uint32_t> i_run_start;  // first record of every distinct key
+  DevBuf<uint64_t> i_hist;  // run-length histogram of the keys + #keys (index.cu)
   uint32_t occurrence = 0xFFFFFFFFu;
+  bool i_sorted_ids = false;  // postings of a key are in ascending read-id order
+  bool ids_ascending = true;  // read ids never decrease with the read index
   DevBuf<uint8_t> sort_tmp;
 
   // ---- map ----
@@ -146,9 +148,9 @@ struct Ctx {
   bool po_has_cov = false, poa_valid = false;
 
   // ---- stage-1 results ----
-  std::vector<rvn_overlap> st_ovl;
-  std::vector<uint64_t> st_ovl_off;
-  std::vector<uint16_t> st_pile;
+  PinBuf<rvn_overlap> st_ovl;  // pinned: the D2H of the results runs at link speed
+  PinBuf<uint64_t> st_ovl_off;
+  PinBuf<uint16_t> st_pile;
   std::vector<uint64_t> st_pile_off;
   uint64_t st_mapped = 0;
   bool st_valid = false;

@@ -250,13 +250,12 @@ void GatherFlush(Ctx& c, const rvn_overlap* ovl, const uint64_t* q_ovl_off,
 
 void GatherFetch(Ctx& c) {
   const uint32_t n = c.n_reads;
-  c.st_ovl_off.assign(n + 1ULL, 0);
-  c.st_ovl.resize(c.g_total);
-  RVN_CUDA(cudaMemcpyAsync(c.st_ovl_off.data(), c.g_off.get(),
+  c.st_ovl.reserve(c.g_total + 1);
+  RVN_CUDA(cudaMemcpyAsync(c.st_ovl_off.reserve(n + 1ULL), c.g_off.get(),
                            (n + 1ULL) * sizeof(uint64_t), cudaMemcpyDeviceToHost,
                            c.stream));
   if (c.g_total) {
-    RVN_CUDA(cudaMemcpyAsync(c.st_ovl.data(), c.g_list[c.g_cur].get(),
+    RVN_CUDA(cudaMemcpyAsync(c.st_ovl.get(), c.g_list[c.g_cur].get(),
                              c.g_total * sizeof(rvn_overlap),
                              cudaMemcpyDeviceToHost, c.stream));
   }

@@ -24,77 +24,60 @@ namespace {
 
 constexpr int kThreads = 256;
 
-// bucket[b] = index of the first record whose (value >> shift) >= b
-__global__ void BuildBucketTable(const uint64_t* __restrict__ val, uint64_t n,
-                                 int shift, uint32_t n_buckets,
-                                 uint32_t* __restrict__ bucket) {
-  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i > n) return;
-  const uint64_t lo = i == 0 ? 0 : (val[i - 1] >> shift) + 1;
-  const uint64_t hi = i == n ? n_buckets : (val[i] >> shift);
-  // record i is the first one of buckets (prev_bucket, this_bucket]
-  for (uint64_t b = lo; b <= hi; ++b) {
-    bucket[b] = static_cast<uint32_t>(i);
-  }
-}
-
-// flag the first record of every run of equal values
-__global__ void FlagRunStarts(const uint64_t* __restrict__ val, uint64_t n,
-                              uint32_t* __restrict__ flag) {
-  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  flag[i] = (i == 0 || val[i] != val[i - 1]) ? 1u : 0u;
-}
-
-__global__ void ScatterRunStarts(const uint32_t* __restrict__ flag,
-                                 const uint64_t* __restrict__ pos, uint64_t n,
-                                 uint32_t* __restrict__ run_start) {
-  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (flag[i]) run_start[pos[i]] = static_cast<uint32_t>(i);
-}
-
 constexpr uint32_t kHistBins = 1u << 16;
-
-// histogram of run lengths; lengths >= kHistBins-1 land in the last bin.
-// Nearly every run has length 1..3, so short lengths are counted in a
-// shared-memory histogram per CTA (one global atomic per bin per CTA).
 constexpr uint32_t kSmemBins = 1024;
+
+// One pass over the sorted values:
+//   bucket[b] = index of the first record whose (value >> shift) >= b;
+//   hist[len] += 1 for every run of equal values (a key) of that many postings
+//     (lengths >= kHistBins-1 land in the last bin; nearly every run has
+//     length 1..3, so short lengths go through a shared-memory histogram);
+//   hist[kHistBins] = number of keys.
 __global__ void __launch_bounds__(kThreads)
-RunLengthHistogram(const uint32_t* __restrict__ run_start, uint64_t n_keys,
-                   uint64_t n, unsigned long long* __restrict__ hist) {
+IndexTableKernel(const uint64_t* __restrict__ val, uint64_t n, int shift,
+                 uint32_t n_buckets, uint32_t* __restrict__ bucket,
+                 unsigned long long* __restrict__ hist) {
   __shared__ uint32_t sh[kSmemBins];
+  __shared__ uint32_t keys;
   for (uint32_t i = threadIdx.x; i < kSmemBins; i += kThreads) sh[i] = 0;
+  if (threadIdx.x == 0) keys = 0;
   __syncthreads();
-  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kThreads;
-  for (uint64_t j = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
-       j < n_keys; j += stride) {
-    const uint64_t end = j + 1 < n_keys ? run_start[j + 1] : n;
-    uint64_t len = end - run_start[j];
-    if (len > kHistBins - 1) len = kHistBins - 1;
-    if (len < kSmemBins) {
-      atomicAdd(&sh[len], 1u);
-    } else {
-      atomicAdd(&hist[len], 1ULL);
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (i <= n) {
+    const uint64_t prev = i == 0 ? 0 : val[i - 1];
+    const uint64_t cur = i == n ? 0 : val[i];
+    // record i is the first one of buckets (prev_bucket, this_bucket]
+    const uint64_t lo = i == 0 ? 0 : (prev >> shift) + 1;
+    const uint64_t hi = i == n ? n_buckets : (cur >> shift);
+    for (uint64_t b = lo; b <= hi; ++b) bucket[b] = static_cast<uint32_t>(i);
+    if (i < n && (i == 0 || cur != prev)) {  // a run starts here
+      uint32_t len = 1;
+      while (len < kHistBins - 1 && i + len < n && val[i + len] == cur) ++len;
+      if (len < kSmemBins) {
+        atomicAdd(&sh[len], 1u);
+      } else {
+        atomicAdd(&hist[len], 1ULL);
+      }
+      atomicAdd(&keys, 1u);
     }
   }
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < kSmemBins; i += kThreads) {
-    if (sh[i]) atomicAdd(&hist[i], static_cast<unsigned long long>(sh[i]));
+  for (uint32_t b = threadIdx.x; b < kSmemBins; b += kThreads) {
+    if (sh[b]) atomicAdd(&hist[b], static_cast<unsigned long long>(sh[b]));
   }
+  if (threadIdx.x == 0 && keys) atomicAdd(&hist[kHistBins], static_cast<unsigned long long>(keys));
 }
 
-__global__ void CollectLongRuns(const uint32_t* __restrict__ run_start,
-                                uint64_t n_keys, uint64_t n,
+// exact lengths of the runs of kHistBins-1 or more postings (rare)
+__global__ void CollectLongRuns(const uint64_t* __restrict__ val, uint64_t n,
                                 unsigned long long* __restrict__ counter,
                                 uint32_t* __restrict__ out) {
-  const uint64_t j = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (j >= n_keys) return;
-  const uint64_t end = j + 1 < n_keys ? run_start[j + 1] : n;
-  const uint64_t len = end - run_start[j];
-  if (len >= kHistBins - 1) {
-    out[atomicAdd(counter, 1ULL)] = static_cast<uint32_t>(len);
-  }
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n || (i > 0 && val[i] == val[i - 1])) return;
+  if (i + (kHistBins - 2) >= n || val[i + (kHistBins - 2)] != val[i]) return;
+  uint64_t len = kHistBins - 1;
+  while (i + len < n && val[i + len] == val[i]) ++len;
+  out[atomicAdd(counter, 1ULL)] = static_cast<uint32_t>(len);
 }
 
 }  // namespace
@@ -117,11 +100,13 @@ void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash) {
   c.i_first = first;
   c.i_last = last;
   BuildIndexFrom(c, src_val, src_org, n, bases);
+  c.i_sorted_ids = c.ids_ascending;
 }
 
 void BuildIndexFrom(Ctx& c, const uint64_t* src_val, const uint64_t* src_org, uint64_t n,
                     uint64_t index_bases) {
   c.i_valid = false;
+  c.i_sorted_ids = false;
   c.occurrence = 0xFFFFFFFFu;
   if (n >= 0xFFFFFFFFULL) {
     throw LimitError("index batch holds 2^32 or more minimizers");
@@ -164,7 +149,7 @@ void BuildIndexFrom(Ctx& c, const uint64_t* src_val, const uint64_t* src_org, ui
   TimerEnd(c);
 
   TimerBegin(c, "index_table");
-  // bucket table over the top bits of the value
+  // bucket table over the top bits of the value + run-length histogram + #keys
   int bits = 8;
   while (bits < 28 && (1ULL << (bits + 1)) <= n) ++bits;
   bits = std::min<int>(bits, 2 * c.prm.k);
@@ -172,25 +157,14 @@ void BuildIndexFrom(Ctx& c, const uint64_t* src_val, const uint64_t* src_org, ui
   const int shift = static_cast<int>(2 * c.prm.k) - bits;
   const uint32_t n_buckets = 1u << bits;
   uint32_t* bucket = c.i_bucket.reserve(n_buckets + 2ULL);
-  BuildBucketTable<<<CeilDiv(n + 1, kThreads), kThreads, 0, c.stream>>>(
-      kv, n, shift, n_buckets, bucket);
+  static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
+  uint64_t* hist = c.i_hist.reserve(kHistBins + 8);
+  RVN_CUDA(cudaMemsetAsync(hist, 0, (kHistBins + 8) * sizeof(uint64_t), c.stream));
+  IndexTableKernel<<<CeilDiv(n + 1, kThreads), kThreads, 0, c.stream>>>(
+      kv, n, shift, n_buckets, bucket, reinterpret_cast<unsigned long long*>(hist));
   RVN_LAUNCH_CHECK();
   ++c.launches;
-
-  // distinct keys: run starts, compacted
-  if (n > 0) {
-    uint32_t* flag = c.m_cnt.reserve(n);
-    uint64_t* pos = c.m_hit_off.reserve(n + 1);
-    FlagRunStarts<<<CeilDiv(n, kThreads), kThreads, 0, c.stream>>>(kv, n, flag);
-    RVN_LAUNCH_CHECK();
-    ExclusiveScanU32(c, flag, pos, n);
-    c.i_keys = ReadU64(c, pos + n);
-    uint32_t* rs = c.i_run_start.reserve(c.i_keys + 1);
-    ScatterRunStarts<<<CeilDiv(n, kThreads), kThreads, 0, c.stream>>>(flag, pos,
-                                                                      n, rs);
-    RVN_LAUNCH_CHECK();
-    c.launches += 2;
-  }
+  c.i_keys = ReadU64(c, hist + kHistBins);
   TimerEnd(c);
 
   c.stats.index_bases = index_bases;
@@ -199,19 +173,8 @@ void BuildIndexFrom(Ctx& c, const uint64_t* src_val, const uint64_t* src_org, ui
   c.i_valid = true;
 }
 
-uint64_t* IndexHistogram(Ctx& c) {
-  static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
-  uint64_t* hist = c.m_counter.reserve(kHistBins + 8);
-  RVN_CUDA(cudaMemsetAsync(hist, 0, (kHistBins + 8) * sizeof(uint64_t), c.stream));
-  if (c.i_keys) {
-    RunLengthHistogram<<<std::min<unsigned>(CeilDiv(c.i_keys, kThreads), 148 * 16),
-                         kThreads, 0, c.stream>>>(
-        c.i_run_start.get(), c.i_keys, c.i_n,
-        reinterpret_cast<unsigned long long*>(hist));
-    RVN_LAUNCH_CHECK();
-    ++c.launches;
-  }
-  return hist;
+uint64_t* IndexHistogram(Ctx& c) {  // filled by the build
+  return c.i_hist.get();
 }
 
 // same arithmetic as the reference engine: index = (1 - f) * #keys, truncated
@@ -258,10 +221,10 @@ uint32_t FilterIndex(Ctx& c, double frequency) {
     if (rank >= c.i_keys) rank = c.i_keys - 1;
     const uint64_t n_long = h[kHistBins - 1];
     uint32_t* out = c.m_cnt.reserve(n_long + 1);
-    RVN_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint64_t), c.stream));
-    CollectLongRuns<<<CeilDiv(c.i_keys, kThreads), kThreads, 0, c.stream>>>(
-        c.i_run_start.get(), c.i_keys, c.i_n,
-        reinterpret_cast<unsigned long long*>(hist), out);
+    uint64_t* counter = c.m_counter.reserve(8);
+    RVN_CUDA(cudaMemsetAsync(counter, 0, sizeof(uint64_t), c.stream));
+    CollectLongRuns<<<CeilDiv(c.i_n, kThreads), kThreads, 0, c.stream>>>(
+        c.i_val.get(), c.i_n, reinterpret_cast<unsigned long long*>(counter), out);
     RVN_LAUNCH_CHECK();
     ++c.launches;
     std::vector<uint32_t> lens(n_long);

@@ -144,6 +144,95 @@ ExpandKernel(IndexView ix, const uint64_t* __restrict__ q_val,
   }
 }
 
+// ---- fast path of probe + expand -------------------------------------------
+// The postings of a key are in read order (the index sort is stable over
+// records in (read, position) order), so with avoid_equal && avoid_symmetric
+// the kept postings (rhs_id > lhs_id) are a SUFFIX of the run - and with both
+// flags off they are the whole run. The probe then only needs the first kept
+// posting (a binary search in the run), and the expansion can be done by whole
+// warps with fully coalesced stores: hit t of a warp's 32 queries is located
+// by a shuffle search over the 32 exclusive prefixes.
+__global__ void __launch_bounds__(kThreads)
+ProbeSuffixKernel(IndexView ix, const uint64_t* __restrict__ q_val,
+                  const uint64_t* __restrict__ q_org, uint64_t q_begin, uint64_t n_q,
+                  bool strict_above, uint32_t* __restrict__ cnt,
+                  uint32_t* __restrict__ first, uint8_t* __restrict__ filt) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (i >= n_q) return;
+  const uint64_t v = q_val[q_begin + i];
+  uint32_t f, n;
+  Lookup(ix, v, &f, &n);
+  uint8_t over = 0;
+  uint32_t kept = 0, fk = f;
+  if (n > ix.occurrence) {
+    over = 1;
+  } else if (n > 0) {
+    if (strict_above) {
+      const uint32_t lhs_id = static_cast<uint32_t>(q_org[q_begin + i] >> 32);
+      uint32_t lo = f, hi = f + n;  // first posting with rhs_id > lhs_id
+      while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (static_cast<uint32_t>(ix.org[mid] >> 32) <= lhs_id) lo = mid + 1; else hi = mid;
+      }
+      fk = lo;
+    }
+    kept = f + n - fk;
+  }
+  cnt[i] = kept;
+  first[i] = fk;
+  filt[i] = over;
+}
+
+__global__ void __launch_bounds__(kThreads)
+ExpandWarpKernel(IndexView ix, const uint64_t* __restrict__ q_org, uint64_t q_begin,
+                 uint64_t n_q, const uint32_t* __restrict__ cnt,
+                 const uint32_t* __restrict__ first, const uint64_t* __restrict__ hit_off,
+                 uint64_t* __restrict__ h_grp, uint64_t* __restrict__ h_pos) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t i = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x);
+  const bool valid = i < n_q;
+  const uint32_t my_cnt = valid ? cnt[i] : 0;
+  const uint32_t my_first = valid ? first[i] : 0;
+  const uint64_t my_org = valid ? q_org[q_begin + i] : 0;
+  const uint64_t my_off = valid ? hit_off[i] : 0;
+  // exclusive prefix of the warp, relative to its first query (lanes beyond n_q
+  // only occur at the very end: give them the running end)
+  const uint64_t base = __shfl_sync(0xFFFFFFFFu, my_off, 0);
+  uint32_t rel = valid ? static_cast<uint32_t>(my_off - base) : 0;
+  // total and a monotone prefix for the invalid tail lanes
+  uint32_t run = valid ? rel + my_cnt : 0;
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, run, d);
+    if (lane >= d && o > run) run = o;
+  }
+  if (!valid) rel = run;
+  const uint32_t total = __shfl_sync(0xFFFFFFFFu, run, 31);
+  for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+    const uint32_t t = t0 + lane;
+    // largest q with rel[q] <= t
+    uint32_t q = 0;
+#pragma unroll
+    for (uint32_t step = 16; step > 0; step >>= 1) {
+      const uint32_t r = __shfl_sync(0xFFFFFFFFu, rel, q + step);
+      if (r <= t) q += step;
+    }
+    const uint32_t qrel = __shfl_sync(0xFFFFFFFFu, rel, q);
+    const uint32_t qfirst = __shfl_sync(0xFFFFFFFFu, my_first, q);
+    const uint64_t lo = __shfl_sync(0xFFFFFFFFu, my_org, q);
+    if (t < total) {
+      const uint64_t o = ix.org[qfirst + (t - qrel)];
+      const uint64_t lhs_pos = static_cast<uint32_t>(lo) >> 1;
+      const uint64_t rhs_id = o >> 32;
+      const uint64_t strand = (lo & 1) == (o & 1);
+      const uint64_t rhs_pos = static_cast<uint32_t>(o) >> 1;
+      const uint64_t diagonal =
+          !strand ? rhs_pos + lhs_pos : rhs_pos - lhs_pos + (3ULL << 30);
+      h_grp[base + t] = (((rhs_id << 1) | strand) << 32) | diagonal;
+      h_pos[base + t] = (lhs_pos << 32) | rhs_pos;
+    }
+  }
+}
+
 // per-read offsets out of per-record offsets
 __global__ void GatherU64(const uint64_t* __restrict__ src,
                           const uint64_t* __restrict__ idx, uint64_t idx_base,
@@ -1313,9 +1402,17 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
   uint8_t* filt = c.m_filt.reserve(n_q + 1);
   uint64_t* hit_off = c.m_hit_off.reserve(n_q + 2);
   uint64_t n_hits = 0;
+  // kept postings = a suffix of the run (or the whole run): see ProbeSuffixKernel
+  const bool suffix = (avoid_equal && avoid_symmetric && c.i_sorted_ids) ||
+                      (!avoid_equal && !avoid_symmetric);
   if (n_q > 0) {
-    ProbeKernel<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
-        ix, qv, qo, q_begin, n_q, avoid_equal, avoid_symmetric, cnt, frst, filt);
+    if (suffix) {
+      ProbeSuffixKernel<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
+          ix, qv, qo, q_begin, n_q, avoid_equal, cnt, frst, filt);
+    } else {
+      ProbeKernel<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
+          ix, qv, qo, q_begin, n_q, avoid_equal, avoid_symmetric, cnt, frst, filt);
+    }
     RVN_LAUNCH_CHECK();
     ++c.launches;
     ExclusiveScanU32(c, cnt, hit_off, n_q);
@@ -1328,9 +1425,14 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
   uint64_t* hg = c.h_grp.reserve(n_hits + 1);
   uint64_t* hp = c.h_pos.reserve(n_hits + 1);
   if (n_hits > 0) {
-    ExpandKernel<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
-        ix, qv, qo, q_begin, n_q, avoid_equal, avoid_symmetric, cnt, frst,
-        hit_off, hg, hp);
+    if (suffix) {
+      ExpandWarpKernel<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
+          ix, qo, q_begin, n_q, cnt, frst, hit_off, hg, hp);
+    } else {
+      ExpandKernel<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
+          ix, qv, qo, q_begin, n_q, avoid_equal, avoid_symmetric, cnt, frst,
+          hit_off, hg, hp);
+    }
     RVN_LAUNCH_CHECK();
     ++c.launches;
   }
