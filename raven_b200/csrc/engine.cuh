@@ -80,6 +80,7 @@ struct Ctx {
   DevBuf<uint64_t> i_val, i_org, i_val_alt, i_org_alt;
   DevBuf<uint32_t> i_bucket;
   int i_bucket_bits = 0;
+  DevBuf<uint64_t> i_gaps;  // long empty stretches of the bucket table (index.cu)
   DevBuf<uint64_t> i_hist;  // run-length histogram of the keys + #keys (index.cu)
   uint32_t occurrence = 0xFFFFFFFFu;
   bool i_sorted_ids = false;  // postings of a key are in ascending read-id order
@@ -90,6 +91,8 @@ struct Ctx {
   DevBuf<uint32_t> m_cnt, m_first;
   DevBuf<uint8_t> m_filt;
   DevBuf<uint64_t> m_hit_off;  // per query record (+1)
+  DevBuf<uint64_t> m_sq_key, m_sq_key2;  // queries sorted by value (probe order)
+  DevBuf<uint32_t> m_sq_idx, m_sq_idx2;
   DevBuf<uint64_t> h_grp, h_pos;
   DevBuf<uint64_t> m_read_hit_off;  // per query read (+1)
   DevBuf<uint64_t> m_scratch64;     // oversize chain scratch

@@ -27,45 +27,96 @@ constexpr int kThreads = 256;
 constexpr uint32_t kHistBins = 1u << 16;
 constexpr uint32_t kSmemBins = 1024;
 
+__global__ void NarrowKeys(const uint64_t* __restrict__ in, uint64_t n,
+                           uint32_t* __restrict__ out) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = static_cast<uint32_t>(in[i]);
+}
+
+__global__ void WidenKeys(const uint32_t* __restrict__ in, uint64_t n,
+                          uint64_t* __restrict__ out) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
 // One pass over the sorted values:
 //   bucket[b] = index of the first record whose (value >> shift) >= b;
 //   hist[len] += 1 for every run of equal values (a key) of that many postings
 //     (lengths >= kHistBins-1 land in the last bin; nearly every run has
 //     length 1..3, so short lengths go through a shared-memory histogram);
 //   hist[kHistBins] = number of keys.
+// (minimizer values are minima of hashes: the top of the value range is nearly
+// empty, so a few records own millions of buckets - those gaps are handed to
+// FillLongGaps instead of being filled by one thread)
+constexpr uint32_t kShortGap = 64;
+constexpr uint32_t kMaxLongGaps = 1u << 20;
+
 __global__ void __launch_bounds__(kThreads)
 IndexTableKernel(const uint64_t* __restrict__ val, uint64_t n, int shift,
                  uint32_t n_buckets, uint32_t* __restrict__ bucket,
-                 unsigned long long* __restrict__ hist) {
+                 unsigned long long* __restrict__ hist, uint64_t* __restrict__ gaps) {
   __shared__ uint32_t sh[kSmemBins];
   __shared__ uint32_t keys;
   for (uint32_t i = threadIdx.x; i < kSmemBins; i += kThreads) sh[i] = 0;
   if (threadIdx.x == 0) keys = 0;
   __syncthreads();
-  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  // persistent CTAs: the shared histogram is set up and flushed once per CTA
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kThreads;
+  for (uint64_t base = static_cast<uint64_t>(blockIdx.x) * kThreads; base <= n; base += stride) {
+  const uint64_t i = base + threadIdx.x;
+  bool start = false;
+  uint32_t len = 0;
   if (i <= n) {
     const uint64_t prev = i == 0 ? 0 : val[i - 1];
     const uint64_t cur = i == n ? 0 : val[i];
     // record i is the first one of buckets (prev_bucket, this_bucket]
     const uint64_t lo = i == 0 ? 0 : (prev >> shift) + 1;
     const uint64_t hi = i == n ? n_buckets : (cur >> shift);
-    for (uint64_t b = lo; b <= hi; ++b) bucket[b] = static_cast<uint32_t>(i);
-    if (i < n && (i == 0 || cur != prev)) {  // a run starts here
-      uint32_t len = 1;
-      while (len < kHistBins - 1 && i + len < n && val[i + len] == cur) ++len;
-      if (len < kSmemBins) {
-        atomicAdd(&sh[len], 1u);
-      } else {
-        atomicAdd(&hist[len], 1ULL);
+    if (hi + 1 - lo <= kShortGap || hi < lo) {
+      for (uint64_t b = lo; b <= hi; ++b) bucket[b] = static_cast<uint32_t>(i);
+    } else {
+      const unsigned long long g = atomicAdd(&hist[kHistBins + 1], 1ULL);
+      if (g < kMaxLongGaps) {
+        gaps[3 * g] = lo;
+        gaps[3 * g + 1] = hi;
+        gaps[3 * g + 2] = i;
+      } else {  // (never seen: the list holds a million gaps)
+        for (uint64_t b = lo; b <= hi; ++b) bucket[b] = static_cast<uint32_t>(i);
       }
-      atomicAdd(&keys, 1u);
     }
+    if (i < n && (i == 0 || cur != prev)) {  // a run starts here
+      start = true;
+      len = 1;
+      while (len < kHistBins - 1 && i + len < n && val[i + len] == cur) ++len;
+    }
+  }
+  // warp-aggregated: nearly all runs have the same few lengths
+  const uint32_t starts = __ballot_sync(0xFFFFFFFFu, start);
+  if (start) {
+    const uint32_t same = __match_any_sync(starts, len);
+    if ((threadIdx.x & 31) == static_cast<uint32_t>(__ffs(same) - 1)) {
+      if (len < kSmemBins) {
+        atomicAdd(&sh[len], static_cast<uint32_t>(__popc(same)));
+      } else {
+        atomicAdd(&hist[len], static_cast<unsigned long long>(__popc(same)));
+      }
+    }
+  }
+  if ((threadIdx.x & 31) == 0 && starts) atomicAdd(&keys, static_cast<uint32_t>(__popc(starts)));
+
   }
   __syncthreads();
   for (uint32_t b = threadIdx.x; b < kSmemBins; b += kThreads) {
     if (sh[b]) atomicAdd(&hist[b], static_cast<unsigned long long>(sh[b]));
   }
   if (threadIdx.x == 0 && keys) atomicAdd(&hist[kHistBins], static_cast<unsigned long long>(keys));
+}
+
+__global__ void __launch_bounds__(kThreads)
+FillLongGaps(const uint64_t* __restrict__ gaps, uint32_t* __restrict__ bucket) {
+  const uint64_t lo = gaps[3ULL * blockIdx.x], hi = gaps[3ULL * blockIdx.x + 1];
+  const uint32_t v = static_cast<uint32_t>(gaps[3ULL * blockIdx.x + 2]);
+  for (uint64_t b = lo + threadIdx.x; b <= hi; b += kThreads) bucket[b] = v;
 }
 
 // exact lengths of the runs of kHistBins-1 or more postings (rare)
@@ -117,34 +168,33 @@ void BuildIndexFrom(Ctx& c, const uint64_t* src_val, const uint64_t* src_org, ui
   TimerBegin(c, "index_sort");
   uint64_t* kv = c.i_val.reserve(n + 1);
   uint64_t* ko = c.i_org.reserve(n + 1);
-  uint64_t* kv_alt = c.i_val_alt.reserve(n + 1);
-  uint64_t* ko_alt = c.i_org_alt.reserve(n + 1);
   if (n > 0) {
-    // stable LSD radix sort on the 2k value bits; the sketch arrays stay
-    // untouched (they still serve the queries of this batch)
-    RVN_CUDA(cudaMemcpyAsync(kv_alt, src_val, n * sizeof(uint64_t),
-                             cudaMemcpyDeviceToDevice, c.stream));
-    RVN_CUDA(cudaMemcpyAsync(ko_alt, src_org, n * sizeof(uint64_t),
-                             cudaMemcpyDeviceToDevice, c.stream));
-    cub::DoubleBuffer<uint64_t> keys(kv_alt, kv);
-    cub::DoubleBuffer<uint64_t> vals(ko_alt, ko);
+    // stable LSD radix sort on the 2k value bits. The out-of-place API leaves the
+    // sketch arrays untouched (they still serve the queries of this batch) - no
+    // staging copies. Values of up to 32 bits (k <= 16) travel as u32 keys:
+    // 12 instead of 16 bytes per record and pass.
+    const int key_bits = static_cast<int>(2 * c.prm.k);
     size_t tmp_bytes = 0;
-    RVN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, vals, n, 0,
-                                             static_cast<int>(2 * c.prm.k),
-                                             c.stream));
-    void* tmp = c.sort_tmp.reserve(tmp_bytes + 16);
-    RVN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, vals, n, 0,
-                                             static_cast<int>(2 * c.prm.k),
-                                             c.stream));
-    c.launches += 2 * ((2 * c.prm.k + 7) / 8) + 1;
-    if (keys.Current() != kv) {
-      std::swap(c.i_val.p, c.i_val_alt.p);
-      std::swap(c.i_val.cap, c.i_val_alt.cap);
-      std::swap(c.i_org.p, c.i_org_alt.p);
-      std::swap(c.i_org.cap, c.i_org_alt.cap);
-      kv = c.i_val.get();
-      ko = c.i_org.get();
+    if (key_bits <= 32) {
+      uint32_t* k32_in = reinterpret_cast<uint32_t*>(c.i_val_alt.reserve(n / 2 + 2));
+      uint32_t* k32_out = reinterpret_cast<uint32_t*>(c.i_org_alt.reserve(n / 2 + 2));
+      NarrowKeys<<<CeilDiv(n, kThreads), kThreads, 0, c.stream>>>(src_val, n, k32_in);
+      RVN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k32_in, k32_out, src_org, ko,
+                                               n, 0, key_bits, c.stream));
+      void* tmp = c.sort_tmp.reserve(tmp_bytes + 16);
+      RVN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k32_in, k32_out, src_org, ko, n,
+                                               0, key_bits, c.stream));
+      WidenKeys<<<CeilDiv(n, kThreads), kThreads, 0, c.stream>>>(k32_out, n, kv);
+      RVN_LAUNCH_CHECK();
+      c.launches += 2;
+    } else {
+      RVN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, src_val, kv, src_org, ko, n,
+                                               0, key_bits, c.stream));
+      void* tmp = c.sort_tmp.reserve(tmp_bytes + 16);
+      RVN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, src_val, kv, src_org, ko, n, 0,
+                                               key_bits, c.stream));
     }
+    c.launches += (key_bits + 7) / 8 + 2;
   }
   TimerEnd(c);
 
@@ -160,11 +210,22 @@ void BuildIndexFrom(Ctx& c, const uint64_t* src_val, const uint64_t* src_org, ui
   static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
   uint64_t* hist = c.i_hist.reserve(kHistBins + 8);
   RVN_CUDA(cudaMemsetAsync(hist, 0, (kHistBins + 8) * sizeof(uint64_t), c.stream));
-  IndexTableKernel<<<CeilDiv(n + 1, kThreads), kThreads, 0, c.stream>>>(
-      kv, n, shift, n_buckets, bucket, reinterpret_cast<unsigned long long*>(hist));
+  uint64_t* gaps = c.i_gaps.reserve(3ULL * kMaxLongGaps);
+  IndexTableKernel<<<std::min<unsigned>(CeilDiv(n + 1, kThreads), 148 * 8), kThreads, 0, c.stream>>>(
+      kv, n, shift, n_buckets, bucket, reinterpret_cast<unsigned long long*>(hist), gaps);
   RVN_LAUNCH_CHECK();
   ++c.launches;
-  c.i_keys = ReadU64(c, hist + kHistBins);
+  uint64_t* hk = c.pin64.reserve(8);
+  RVN_CUDA(cudaMemcpyAsync(hk, hist + kHistBins, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                           c.stream));
+  RVN_CUDA(cudaStreamSynchronize(c.stream));
+  c.i_keys = hk[0];
+  const uint64_t n_long = std::min<uint64_t>(hk[1], kMaxLongGaps);
+  if (n_long) {
+    FillLongGaps<<<static_cast<unsigned>(n_long), kThreads, 0, c.stream>>>(gaps, bucket);
+    RVN_LAUNCH_CHECK();
+    ++c.launches;
+  }
   TimerEnd(c);
 
   c.stats.index_bases = index_bases;

@@ -183,6 +183,53 @@ ProbeSuffixKernel(IndexView ix, const uint64_t* __restrict__ q_val,
   filt[i] = over;
 }
 
+// the same probe over queries sorted by value: neighbouring threads walk
+// neighbouring parts of the bucket table and of the postings (coalesced,
+// TLB-friendly) instead of 67 M independent random probes into 12 GB
+__global__ void __launch_bounds__(kThreads)
+ProbeSortedKernel(IndexView ix, const uint64_t* __restrict__ sorted_val,
+                  const uint32_t* __restrict__ sorted_idx,
+                  const uint64_t* __restrict__ q_org, uint64_t q_begin, uint64_t n_q,
+                  bool strict_above, uint64_t* __restrict__ packed) {
+  const uint64_t t = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (t >= n_q) return;
+  const uint64_t v = sorted_val[t];
+  const uint32_t i = sorted_idx[t];
+  uint32_t f, n;
+  Lookup(ix, v, &f, &n);
+  uint8_t over = 0;
+  uint32_t kept = 0, fk = f;
+  if (n > ix.occurrence) {
+    over = 1;
+  } else if (n > 0) {
+    if (strict_above) {
+      const uint32_t lhs_id = static_cast<uint32_t>(q_org[q_begin + i] >> 32);
+      uint32_t lo = f, hi = f + n;
+      while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (static_cast<uint32_t>(ix.org[mid] >> 32) <= lhs_id) lo = mid + 1; else hi = mid;
+      }
+      fk = lo;
+    }
+    kept = f + n - fk;
+  }
+  // ONE scattered store per query (a partial-sector write costs a read-modify-
+  // write in HBM): first kept posting | over-threshold flag | kept count
+  packed[i] = (static_cast<uint64_t>(fk) << 32) | (static_cast<uint64_t>(over) << 31) | kept;
+}
+
+__global__ void UnpackProbe(const uint64_t* __restrict__ packed, uint64_t n,
+                            uint32_t* __restrict__ cnt, uint32_t* __restrict__ first,
+                            uint8_t* __restrict__ filt) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t p = packed[i];
+  cnt[i] = static_cast<uint32_t>(p) & 0x7FFFFFFFu;
+  first[i] = static_cast<uint32_t>(p >> 32);
+  filt[i] = static_cast<uint8_t>((p >> 31) & 1);
+}
+
+
 __global__ void __launch_bounds__(kThreads)
 ExpandWarpKernel(IndexView ix, const uint64_t* __restrict__ q_org, uint64_t q_begin,
                  uint64_t n_q, const uint32_t* __restrict__ cnt,
@@ -1406,7 +1453,30 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
   const bool suffix = (avoid_equal && avoid_symmetric && c.i_sorted_ids) ||
                       (!avoid_equal && !avoid_symmetric);
   if (n_q > 0) {
-    if (suffix) {
+    if (suffix && n_q >= (1u << 16) && n_q < 0xFFFFFFFFULL) {
+      // sort the queries by value, probe in that order, results back by index
+      uint64_t* k1 = c.m_sq_key.reserve(n_q);
+      uint64_t* k2 = c.m_sq_key2.reserve(n_q);
+      uint32_t* v1 = c.m_sq_idx.reserve(n_q);
+      uint32_t* v2 = c.m_sq_idx2.reserve(n_q);
+      RVN_CUDA(cudaMemcpyAsync(k1, qv + q_begin, n_q * sizeof(uint64_t),
+                               cudaMemcpyDeviceToDevice, c.stream));
+      IotaU32<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(v1, n_q);
+      cub::DoubleBuffer<uint64_t> dk(k1, k2);
+      cub::DoubleBuffer<uint32_t> dv(v1, v2);
+      size_t tmp_bytes = 0;
+      RVN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, n_q, 0,
+                                               static_cast<int>(2 * c.prm.k), c.stream));
+      void* tmp = c.sort_tmp.reserve(tmp_bytes + 16);
+      RVN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, n_q, 0,
+                                               static_cast<int>(2 * c.prm.k), c.stream));
+      // (the spare key buffer of the sort receives the packed results)
+      uint64_t* packed = dk.Current() == k1 ? k2 : k1;
+      ProbeSortedKernel<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
+          ix, dk.Current(), dv.Current(), qo, q_begin, n_q, avoid_equal, packed);
+      UnpackProbe<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(packed, n_q, cnt, frst, filt);
+      c.launches += (2 * c.prm.k + 7) / 8 + 5;
+    } else if (suffix) {
       ProbeSuffixKernel<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
           ix, qv, qo, q_begin, n_q, avoid_equal, cnt, frst, filt);
     } else {

@@ -43,21 +43,6 @@ __device__ __forceinline__ uint64_t ReverseGroups(uint64_t x) {
   return ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
 }
 
-// read index of tile t: last r with tile_off[r] <= t
-__device__ __forceinline__ uint32_t FindRead(const uint64_t* __restrict__ tile_off,
-                                             uint32_t lo, uint32_t hi, uint64_t t) {
-  // invariant: tile_off[lo] <= t < tile_off[hi]
-  while (hi - lo > 1) {
-    uint32_t mid = lo + (hi - lo) / 2;
-    if (tile_off[mid] <= t) {
-      lo = mid;
-    } else {
-      hi = mid;
-    }
-  }
-  return lo;
-}
-
 __device__ __forceinline__ uint32_t MixHash32(uint32_t key, uint32_t mask) {
   // the same mix on 32-bit registers; exact for 2k <= 30 bits because every
   // step is masked to 2k bits and wrap-around above bit 31 never reaches them
@@ -74,6 +59,60 @@ __device__ __forceinline__ uint32_t MixHash32(uint32_t key, uint32_t mask) {
 __device__ __forceinline__ uint32_t ReverseGroups32(uint32_t x) {
   x = __brev(x);
   return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+}
+
+// Window-minimum selection for a compile-time w <= 8, branch-free and in
+// registers: the 8 positions of a thread need the hashes of 8 + 2(w-1)
+// positions. Window minima come from a sparse table (widths 1, 2, 4, 8);
+// position q is a minimizer iff it equals the minimum of one of the (valid)
+// windows that contain it - the same set as "left run + right run >= w-1",
+// ties included.
+template <typename HashT, int W>
+__device__ __forceinline__ uint32_t SelectFixedW(const HashT* __restrict__ sh_hash,
+                                                 uint32_t hs, uint32_t he, uint32_t qa,
+                                                 uint32_t q1, uint32_t L) {
+  constexpr HashT kBad = static_cast<HashT>(~static_cast<HashT>(0));
+  constexpr int H = W - 1;        // halo
+  constexpr int N = 8 + 2 * H;    // slots; slot j = position qa - H + j
+  constexpr int P = W >= 8 ? 8 : W >= 4 ? 4 : W >= 2 ? 2 : 1;  // largest power of two <= W
+  const int64_t origin = static_cast<int64_t>(qa) - H;
+  HashT h[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const int64_t p = origin + j;
+    h[j] = (p >= static_cast<int64_t>(hs) && p < static_cast<int64_t>(he)) ? sh_hash[p - hs] : kBad;
+  }
+  // m[j] = min of slots j .. j + P - 1
+  HashT m[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    HashT v = h[j];
+#pragma unroll
+    for (int t = 1; t < P; ++t) {
+      if (j + t < N) v = h[j + t] < v ? h[j + t] : v;
+    }
+    m[j] = v;
+  }
+  // minimum of the window starting at slot j, j = 0 .. 7 + H; kBad if the window
+  // leaves the read's k-mer positions [0, L)
+  HashT wm[8 + H];
+#pragma unroll
+  for (int j = 0; j < 8 + H; ++j) {
+    HashT v = m[j];
+    if (W > P) v = m[j + W - P] < v ? m[j + W - P] : v;
+    const int64_t p = origin + j;
+    wm[j] = (p >= 0 && p + W <= static_cast<int64_t>(L)) ? v : kBad;
+  }
+  uint32_t flags = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const HashT hq = h[H + i];
+    bool is_min = false;
+#pragma unroll
+    for (int d = 0; d <= H; ++d) is_min = is_min || wm[i + d] == hq;
+    if (is_min && hq != kBad && qa + i < q1) flags |= 1u << i;
+  }
+  return flags;
 }
 
 // decoupled look-back status word: state in the top two bits
@@ -110,10 +149,28 @@ SketchKernel(const uint64_t* __restrict__ words,
   __shared__ uint32_t sh_read, sh_tile;
   __shared__ uint64_t sh_excl;
 
-  if (threadIdx.x == 0) {
-    const uint32_t tk = atomicAdd(ticket, 1u);
-    sh_tile = tk;
-    sh_read = FindRead(tile_off, first_read, last_read, tile_off[first_read] + tk);
+  if (threadIdx.x < 32) {
+    // ticket, then the read of this tile by a 32-ary search of the first warp
+    // (4 rounds of one load instead of 17 dependent ones)
+    uint32_t tk = 0;
+    if (threadIdx.x == 0) tk = atomicAdd(ticket, 1u);
+    tk = __shfl_sync(0xFFFFFFFFu, tk, 0);
+    const uint64_t want = tile_off[first_read] + tk;
+    uint32_t lo = first_read, hi = last_read;  // tile_off[lo] <= want < tile_off[hi]
+    while (hi - lo > 1) {
+      const uint32_t step = (hi - lo + 31) / 32;
+      const uint64_t probe = static_cast<uint64_t>(lo) + (threadIdx.x + 1ULL) * step;
+      const bool le = probe < hi && tile_off[probe] <= want;
+      const uint32_t cnt = __popc(__ballot_sync(0xFFFFFFFFu, le));
+      const uint64_t nlo = static_cast<uint64_t>(lo) + static_cast<uint64_t>(cnt) * step;
+      const uint64_t nhi = nlo + step;
+      lo = static_cast<uint32_t>(nlo);
+      if (nhi < hi) hi = static_cast<uint32_t>(nhi);
+    }
+    if (threadIdx.x == 0) {
+      sh_tile = tk;
+      sh_read = lo;
+    }
   }
   __syncthreads();
   const uint32_t tile = sh_tile;
@@ -174,12 +231,16 @@ SketchKernel(const uint64_t* __restrict__ words,
 
   // ---- select: each thread owns ITEMS consecutive positions ----
   constexpr uint32_t ITEMS = kSketchTile / kSketchThreads;
+  static_assert(ITEMS == 8, "SelectFixedW handles 8 positions per thread");
   uint32_t flags = 0;
   const uint32_t qa = q0 + threadIdx.x * ITEMS;
+  if (w == 5) {  // raven's default window
+    if (qa < q1) flags = SelectFixedW<HashT, 5>(sh_hash, hs, he, qa, q1, L);
+  }
 #pragma unroll
   for (uint32_t i = 0; i < ITEMS; ++i) {
     const uint32_t q = qa + i;
-    if (q >= q1) break;
+    if (q >= q1 || w == 5) break;
     const HashT h = sh_hash[q - hs];
     if (h == kBad) continue;
     // consecutive left neighbours with hash >= h (capped)
@@ -199,27 +260,42 @@ SketchKernel(const uint64_t* __restrict__ words,
       __popc(flags), sh_scan, &total);
 
   // ---- output offset: running prefix of the tiles before this one ----
-  if (threadIdx.x == 0) {
+  // decoupled look-back by the first warp: 32 predecessors per step
+  if (threadIdx.x < 32) {
+    const uint32_t lane = threadIdx.x;
     uint64_t excl = 0;
     volatile uint64_t* st = status;
     if (tile > 0) {
-      st[tile] = kStAggregate | total;
-      __threadfence();
-      uint64_t idx = tile;
-      while (idx > 0) {
-        --idx;
-        uint64_t v;
-        do {
-          v = st[idx];
-        } while ((v & kStMask) == 0);
-        excl += v & ~kStMask;
-        if ((v & kStMask) == kStPrefix) break;
+      if (lane == 0) {
+        st[tile] = kStAggregate | total;
+        __threadfence();
+      }
+      __syncwarp();
+      int64_t idx = static_cast<int64_t>(tile) - 1;  // lane 0 looks at the nearest tile
+      while (true) {
+        const int64_t mine = idx - lane;
+        uint64_t v = kStPrefix;  // before tile 0: an empty prefix
+        if (mine >= 0) {
+          do {
+            v = st[mine];
+          } while ((v & kStMask) == 0);
+        }
+        const uint32_t pm = __ballot_sync(0xFFFFFFFFu, (v & kStMask) == kStPrefix);
+        const int firstp = __ffs(pm) - 1;  // nearest tile that already knows its prefix
+        uint64_t part = (firstp < 0 || static_cast<int>(lane) <= firstp) ? (v & ~kStMask) : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, d);
+        excl += part;
+        if (firstp >= 0) break;
+        idx -= 32;
       }
     }
-    st[tile] = kStPrefix | (excl + total);
-    tile_out[tile] = excl;
-    if (tile + 1 == n_tiles) tile_out[n_tiles] = excl + total;
-    sh_excl = excl;
+    if (lane == 0) {
+      st[tile] = kStPrefix | (excl + total);
+      tile_out[tile] = excl;
+      if (tile + 1 == n_tiles) tile_out[n_tiles] = excl + total;
+      sh_excl = excl;
+    }
   }
   __syncthreads();
   uint64_t dst = sh_excl + ex;
