@@ -48,7 +48,7 @@ __global__ void WidenKeys(const uint32_t* __restrict__ in, uint64_t n,
 // (minimizer values are minima of hashes: the top of the value range is nearly
 // empty, so a few records own millions of buckets - those gaps are handed to
 // FillLongGaps instead of being filled by one thread)
-constexpr uint32_t kShortGap = 64;
+constexpr uint32_t kShortGap = 1024;
 constexpr uint32_t kMaxLongGaps = 1u << 20;
 
 __global__ void __launch_bounds__(kThreads)
@@ -57,6 +57,7 @@ IndexTableKernel(const uint64_t* __restrict__ val, uint64_t n, int shift,
                  unsigned long long* __restrict__ hist, uint64_t* __restrict__ gaps) {
   __shared__ uint32_t sh[kSmemBins];
   __shared__ uint32_t keys;
+  __shared__ uint32_t warp_first[kThreads / 32];
   for (uint32_t i = threadIdx.x; i < kSmemBins; i += kThreads) sh[i] = 0;
   if (threadIdx.x == 0) keys = 0;
   __syncthreads();
@@ -66,28 +67,91 @@ IndexTableKernel(const uint64_t* __restrict__ val, uint64_t n, int shift,
   const uint64_t i = base + threadIdx.x;
   bool start = false;
   uint32_t len = 0;
+  uint64_t fill_lo = 0, mine = 0;
+  uint32_t fill_cnt = 0;  // buckets (prev_bucket, this_bucket] this record owns
   if (i <= n) {
     const uint64_t prev = i == 0 ? 0 : val[i - 1];
     const uint64_t cur = i == n ? 0 : val[i];
     // record i is the first one of buckets (prev_bucket, this_bucket]
     const uint64_t lo = i == 0 ? 0 : (prev >> shift) + 1;
     const uint64_t hi = i == n ? n_buckets : (cur >> shift);
-    if (hi + 1 - lo <= kShortGap || hi < lo) {
-      for (uint64_t b = lo; b <= hi; ++b) bucket[b] = static_cast<uint32_t>(i);
-    } else {
-      const unsigned long long g = atomicAdd(&hist[kHistBins + 1], 1ULL);
-      if (g < kMaxLongGaps) {
-        gaps[3 * g] = lo;
-        gaps[3 * g + 1] = hi;
-        gaps[3 * g + 2] = i;
-      } else {  // (never seen: the list holds a million gaps)
-        for (uint64_t b = lo; b <= hi; ++b) bucket[b] = static_cast<uint32_t>(i);
+    if (hi >= lo) {
+      if (hi + 1 - lo <= kShortGap) {
+        fill_lo = lo;
+        fill_cnt = static_cast<uint32_t>(hi + 1 - lo);
+      } else {
+        const unsigned long long g = atomicAdd(&hist[kHistBins + 1], 1ULL);
+        if (g < kMaxLongGaps) {
+          gaps[3 * g] = lo;
+          gaps[3 * g + 1] = hi;
+          gaps[3 * g + 2] = i;
+        } else {  // (never seen: the list holds a million gaps)
+          for (uint64_t b = lo; b <= hi; ++b) bucket[b] = static_cast<uint32_t>(i);
+        }
       }
     }
-    if (i < n && (i == 0 || cur != prev)) {  // a run starts here
-      start = true;
-      len = 1;
-      while (len < kHistBins - 1 && i + len < n && val[i + len] == cur) ++len;
+    start = i < n && (i == 0 || cur != prev);  // a run starts here
+    mine = cur;
+  }
+  // Run length = distance to the next run start: found in the warp's ballot, else
+  // in the following warps of this tile (shared memory), else - the run crosses
+  // the tile end - by scanning on from there. (A per-thread forward scan costs
+  // every warp its longest run in dependent loads.) The virtual record n ends
+  // the last run.
+  {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t marks = __ballot_sync(0xFFFFFFFFu, start || i == n);
+    if (lane == 0) warp_first[wid] = marks ? static_cast<uint32_t>(__ffs(marks) - 1) : 32u;
+    __syncthreads();
+    if (start) {
+      const uint32_t above = lane == 31 ? 0u : (marks & ~((2u << lane) - 1u));
+      if (above) {
+        len = static_cast<uint32_t>(__ffs(above) - 1) - lane;
+      } else {
+        len = 32 - lane;
+        uint32_t w2 = wid + 1;
+        while (w2 < kThreads / 32 && warp_first[w2] == 32u) {
+          len += 32;
+          ++w2;
+        }
+        if (w2 < kThreads / 32) {
+          len += warp_first[w2];
+        } else {
+          uint64_t pos = base + kThreads;
+          while (len < kHistBins - 1 && pos < n && val[pos] == mine) {
+            ++pos;
+            ++len;
+          }
+        }
+      }
+      if (len > kHistBins - 1) len = kHistBins - 1;
+    }
+    __syncthreads();
+  }
+  // the warp fills its records' buckets together (a per-thread loop would run
+  // as long as the widest gap among the 32 records): slot t of the warp's
+  // total belongs to the lane found by a shuffle search over the prefixes
+  {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t incl = fill_cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= static_cast<uint32_t>(d)) incl += o;
+    }
+    const uint32_t rel = incl - fill_cnt;
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+      const uint32_t t = t0 + lane;
+      uint32_t q = 0;
+#pragma unroll
+      for (uint32_t step = 16; step > 0; step >>= 1) {
+        const uint32_t r = __shfl_sync(0xFFFFFFFFu, rel, q + step);
+        if (r <= t) q += step;
+      }
+      const uint32_t qrel = __shfl_sync(0xFFFFFFFFu, rel, q);
+      const uint64_t qlo = __shfl_sync(0xFFFFFFFFu, fill_lo, q);
+      if (t < total) bucket[qlo + (t - qrel)] = static_cast<uint32_t>(base + (threadIdx.x & ~31u) + q);
     }
   }
   // warp-aggregated: nearly all runs have the same few lengths
