@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libraven_b200.so")
+# (RVN_LIB: a differently tuned build of the same library, development only)
+LIB_PATH = os.environ.get("RVN_LIB") or os.path.join(HERE, "libraven_b200.so")
 
 U64P = C.POINTER(C.c_uint64)
 U32P = C.POINTER(C.c_uint32)

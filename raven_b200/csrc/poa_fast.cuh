@@ -352,7 +352,13 @@ __device__ __forceinline__ void StoreRow(int16_t* row, uint32_t lane, const int 
 
 constexpr int kNegInf = -1000000;
 
-__global__ void __launch_bounds__(32)
+// one warp per CTA; the register cap decides how many windows an SM holds at
+// once (the kernel is bound by the latency of lane 0's graph surgery, so more
+// resident windows = more throughput until the DP spills)
+#ifndef RVN_POA_BLOCKS
+#define RVN_POA_BLOCKS 16
+#endif
+__global__ void __launch_bounds__(32, RVN_POA_BLOCKS)
 PoaKernelFast(uint32_t n_windows, const uint32_t* __restrict__ win_list,
               const uint32_t* __restrict__ win_first,
               const uint64_t* __restrict__ seq_off, const uint8_t* __restrict__ bases,
