@@ -247,6 +247,94 @@ ExpandOwned(IndexView2 ix, const uint64_t* __restrict__ q_val,
   }
 }
 
+// the same two steps for the stage-1 flags (avoid_equal && avoid_symmetric): the
+// kept postings are a suffix of the run (see map.cu: ProbeSuffixKernel), the
+// expansion is done by whole warps with coalesced stores
+__global__ void __launch_bounds__(kThreads)
+ProbeOwnedSuffix(IndexView2 ix, const uint64_t* __restrict__ q_val,
+                 const uint64_t* __restrict__ q_org, uint64_t n_q,
+                 uint32_t* __restrict__ cnt, uint32_t* __restrict__ first) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (i >= n_q) return;
+  const uint64_t v = q_val[i];
+  const uint32_t lhs_id = static_cast<uint32_t>(q_org[i] >> 32);
+  uint32_t f, n;
+  Lookup2(ix, v, &f, &n);
+  uint32_t kept = 0, fk = f;
+  if (n <= ix.occurrence && n > 0) {
+    uint32_t lo = f, hi = f + n;  // first posting with rhs_id > lhs_id
+    while (lo < hi) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      if (static_cast<uint32_t>(ix.org[mid] >> 32) <= lhs_id) lo = mid + 1; else hi = mid;
+    }
+    fk = lo;
+    kept = f + n - fk;
+  }
+  cnt[i] = kept;
+  first[i] = fk;
+}
+
+__global__ void __launch_bounds__(kThreads)
+ExpandOwnedWarp(IndexView2 ix, const uint64_t* __restrict__ q_org, uint64_t n_q,
+                const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ first,
+                const uint64_t* __restrict__ hit_off, const uint64_t* __restrict__ start,
+                const uint64_t* __restrict__ read_base, uint32_t n_reads, uint32_t parts,
+                uint32_t per_part, uint64_t* __restrict__ h_grp, uint64_t* __restrict__ h_pos,
+                uint32_t* __restrict__ h_lhs, uint32_t* __restrict__ bad) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  bool valid = i < n_q;
+  uint32_t my_cnt = 0, my_first = 0;
+  uint64_t my_org = 0, my_dst = 0;
+  if (valid) {
+    my_org = q_org[i];
+    const uint32_t lhs_id = static_cast<uint32_t>(my_org >> 32);
+    if (lhs_id >= n_reads || i < start[lhs_id] || i >= start[lhs_id + 1]) {
+      *bad = 2;  // query records not sorted by read (or a read out of range)
+      valid = false;
+    } else {
+      my_cnt = cnt[i];
+      my_first = first[i];
+      my_dst = read_base[Slot(lhs_id, parts, per_part)] + (hit_off[i] - hit_off[start[lhs_id]]);
+    }
+  }
+  // exclusive prefix of the 32 counts
+  uint32_t incl = my_cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if (lane >= static_cast<uint32_t>(d)) incl += o;
+  }
+  const uint32_t rel = incl - my_cnt;
+  const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+    const uint32_t t = t0 + lane;
+    uint32_t q = 0;  // largest q with rel[q] <= t
+#pragma unroll
+    for (uint32_t step = 16; step > 0; step >>= 1) {
+      const uint32_t r = __shfl_sync(0xFFFFFFFFu, rel, q + step);
+      if (r <= t) q += step;
+    }
+    const uint32_t qrel = __shfl_sync(0xFFFFFFFFu, rel, q);
+    const uint32_t qfirst = __shfl_sync(0xFFFFFFFFu, my_first, q);
+    const uint64_t lo = __shfl_sync(0xFFFFFFFFu, my_org, q);
+    const uint64_t qdst = __shfl_sync(0xFFFFFFFFu, my_dst, q);
+    if (t < total) {
+      const uint64_t o = ix.org[qfirst + (t - qrel)];
+      const uint64_t lhs_pos = static_cast<uint32_t>(lo) >> 1;
+      const uint64_t rhs_id = o >> 32;
+      const uint64_t strand = (lo & 1) == (o & 1);
+      const uint64_t rhs_pos = static_cast<uint32_t>(o) >> 1;
+      const uint64_t diagonal =
+          !strand ? rhs_pos + lhs_pos : rhs_pos - lhs_pos + (3ULL << 30);
+      const uint64_t dst = qdst + (t - qrel);
+      h_grp[dst] = (((rhs_id << 1) | strand) << 32) | diagonal;
+      h_pos[dst] = (lhs_pos << 32) | rhs_pos;
+      h_lhs[dst] = static_cast<uint32_t>(lo >> 32);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // k-way merge of runs sorted by a u32 key (stride = u32 words per record)
 // start[p * (nk + 1) + k] = first record of run p with key / div >= k
@@ -495,9 +583,15 @@ void DistHitsSplit(Ctx& c, const uint64_t* d_qval, const uint64_t* d_qorg, uint6
   RVN_CUDA(cudaMemsetAsync(bad, 0, 4, c.stream));
   RVN_CUDA(cudaMemsetAsync(tot, 0, (slots + 1) * 4, c.stream));
   TimerBegin(c, "probe");
+  const bool suffix = ae && as && c.i_sorted_ids;  // kept postings = a suffix of the run
   if (n_q) {
-    ProbeOwned<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(ix, d_qval, d_qorg, n_q, ae, as,
-                                                                 cnt, frst);
+    if (suffix) {
+      ProbeOwnedSuffix<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(ix, d_qval, d_qorg, n_q,
+                                                                         cnt, frst);
+    } else {
+      ProbeOwned<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(ix, d_qval, d_qorg, n_q, ae,
+                                                                   as, cnt, frst);
+    }
     RVN_LAUNCH_CHECK();
     ++c.launches;
   }
@@ -522,9 +616,14 @@ void DistHitsSplit(Ctx& c, const uint64_t* d_qval, const uint64_t* d_qorg, uint6
   uint64_t* hp = c.h_pos.reserve(n_hits + 1);
   uint32_t* hl = c.ds_hit_lhs.reserve(n_hits + 1);
   if (n_q) {
-    ExpandOwned<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
-        ix, d_qval, d_qorg, n_q, ae, as, cnt, frst, off, start, rbase, n_query, parts, per_part,
-        hg, hp, hl, bad);
+    if (suffix) {
+      ExpandOwnedWarp<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
+          ix, d_qorg, n_q, cnt, frst, off, start, rbase, n_query, parts, per_part, hg, hp, hl, bad);
+    } else {
+      ExpandOwned<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
+          ix, d_qval, d_qorg, n_q, ae, as, cnt, frst, off, start, rbase, n_query, parts,
+          per_part, hg, hp, hl, bad);
+    }
     RVN_LAUNCH_CHECK();
     ++c.launches;
   }
