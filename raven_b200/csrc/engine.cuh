@@ -211,7 +211,7 @@ void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash);
 // index from device records already in (read, position) order
 void BuildIndexFrom(Ctx& c, const uint64_t* src_val, const uint64_t* src_org, uint64_t n,
                     uint64_t index_bases);
-// run-length histogram of the index keys into c.m_counter (65536 u64 bins)
+// run-length histogram of the index keys (c.i_hist: 65536 u64 bins + #keys), filled by the build
 uint64_t* IndexHistogram(Ctx& c);
 uint32_t ThresholdFromHistogram(Ctx& c, const uint64_t* h_hist, uint64_t n_keys,
                                 double frequency, bool* needs_long_runs);

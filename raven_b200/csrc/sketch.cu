@@ -24,7 +24,6 @@ namespace rvn {
 
 namespace {
 
-constexpr uint64_t kInvalid = ~0ULL;
 
 __device__ __forceinline__ uint64_t MixHash(uint64_t key, uint64_t mask) {
   key = ((~key) + (key << 21)) & mask;
