@@ -345,6 +345,7 @@ def main_ours(a):
             "gpu_launches": int(launches_step),
             "phases_ms": {k: round(v, 3) for k, v in sorted(phases.items())},
             "query_mbases_per_s": st["query_bases"] / 1e6 / (ms_total / a.steps * 1e-3),
+            "index_mbases_per_s": st["index_bases"] / 1e6 / (ms_total / a.steps * 1e-3),
             "roofline": {"kernel": dom + (" (cub::DeviceRadixSort, library)"
                                           if dom == "index_sort" else ""), "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
@@ -430,6 +431,10 @@ def bench_poa(eng, a, peak, with_cpu):
     }
     if out["roofline"]["achieved"]:
         out["roofline"]["frac"] = out["roofline"]["achieved"] / peak
+    if out["gcups"]:
+        # integer-issue ceiling of a packed int16 DP on 148 SMs, ~10 TCUPS
+        out["issue_bound"] = {"ceiling_gcups": 10000.0, "frac": out["gcups"] / 10000.0,
+                              "ncu": "profiles/r01_poa_ncu.txt"}
     if with_cpu:
         import oracle_lib
         O = oracle_lib.Oracle()
