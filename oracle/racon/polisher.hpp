@@ -60,6 +60,8 @@ class Polisher {
 // only), 'D' (target only) per alignment column
 std::string GlobalAlignmentPath(const std::string& query, const std::string& target);
 
+std::int64_t GlobalDistance(const std::string& query, const std::string& target);
+
 // (target, query) breaking points of an alignment cut at multiples of `w`
 std::vector<std::pair<std::uint32_t, std::uint32_t>> BreakingPoints(
     const std::string& path, std::uint32_t q_begin, std::uint32_t t_begin,

@@ -191,6 +191,7 @@ RVN_API int rvn_engine_configure(rvn_ctx* ctx, uint32_t k, uint32_t w,
     c.prm.matches = matches;
     c.prm.gap = gap;
     c.s_valid = c.q_valid = c.i_valid = c.r_valid = false;
+    c.tiles_k = 0;  // the tile table depends on (k, w)
     c.occurrence = 0xFFFFFFFFu;
   });
 }
@@ -311,20 +312,29 @@ RVN_API int rvn_map_external(rvn_ctx* ctx, const uint64_t* words, uint32_t len,
     c.h_tile_off.push_back(tile_tail[1]);
     c.n_reads = n + 1;
     c.s_valid = c.q_valid = false;
-    try {
-      MapRange(c, n, n + 1, avoid_equal != 0, avoid_symmetric != 0, minhash != 0,
-               want_filtered != 0);
-    } catch (...) {
+    // the rider's bases are resident for the duration of the call (EnsureSketch
+    // refuses reads outside [res_first, res_last))
+    const uint32_t res_first0 = c.res_first, res_last0 = c.res_last;
+    c.res_first = n;
+    c.res_last = n + 1;
+    auto restore = [&]() {
+      c.res_first = res_first0;
+      c.res_last = res_last0;
       c.n_reads = n;
       c.h_woff.pop_back(); c.h_len.pop_back(); c.h_ids.pop_back();
       c.h_tile_off.pop_back();
       c.s_valid = c.q_valid = false;
+    };
+    try {
+      // an id below an indexed id breaks the "kept postings are a suffix" shortcut
+      // only through avoid_symmetric, which compares ids, not indices: fine
+      MapRange(c, n, n + 1, avoid_equal != 0, avoid_symmetric != 0, minhash != 0,
+               want_filtered != 0);
+    } catch (...) {
+      restore();
       throw;
     }
-    c.n_reads = n;
-    c.h_woff.pop_back(); c.h_len.pop_back(); c.h_ids.pop_back();
-    c.h_tile_off.pop_back();
-    c.s_valid = c.q_valid = false;
+    restore();
     TimerCollect(c);
   });
 }

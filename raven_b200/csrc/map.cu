@@ -1272,6 +1272,8 @@ uint64_t ChainGroupedHits(Ctx& c, const uint64_t* hg, const uint64_t* hp,
         big.insert(big.end(), fb.begin(), fb.end());
       }
       if (n_groups >= 0xFFFFFFFFULL) throw LimitError("2^32 or more seed pairs");
+      // GroupDesc::hit_off is 32 bits wide
+      if (hpin[2] >= 0xFFFFFFFFULL) throw LimitError("2^32 or more chained seed hits in one flush");
 
       if (n_groups) {
         // largest pairs first: lanes of a warp get pairs of similar size

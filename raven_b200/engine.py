@@ -106,6 +106,22 @@ class Engine:
         res["filtered"] = _arr(f, int(fo[-1]) if want_filtered else 0, np.uint32)
         return res
 
+    def map_external(self, words, length, read_id, avoid_equal=True, avoid_symmetric=True,
+                     minhash=False, want_filtered=False):
+        """Map one read that is not part of the uploaded set (construct.cc:59 with more
+        than one index batch; assemble.cc:757,780) against the current index."""
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        self._check(self.lib.rvn_map_external(
+            self.h, w.ctypes.data_as(U64P), int(length), int(read_id), int(avoid_equal),
+            int(avoid_symmetric), int(minhash), int(want_filtered)))
+        o, off, n = OVLP(), U64P(), C.c_uint64(0)
+        f, foff = U32P(), U64P()
+        self._check(self.lib.rvn_map_results(self.h, C.byref(o), C.byref(off),
+                                             C.byref(n), C.byref(f), C.byref(foff)))
+        fo = _arr(foff, 2, np.uint64)
+        return dict(overlaps=_arr(o, n.value * 8, np.uint32).reshape(-1, 8),
+                    filtered=_arr(f, int(fo[-1]) if want_filtered else 0, np.uint32))
+
     def map_hits(self, nr):
         g, p, off, n = U64P(), U64P(), U64P(), C.c_uint64(0)
         self._check(self.lib.rvn_map_hits(self.h, C.byref(g), C.byref(p),

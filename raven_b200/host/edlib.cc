@@ -1,11 +1,27 @@
 // raven-b200 host-side implementation of the `edlib` C surface the reference
-// calls (include/edlib.h). Exact global (NW) edit distance by Myers/Hyyro
-// bit-vector blocks (only the NW mode is on the reference's path and only NW
-// is served). The edit distance is unique, so any exact algorithm is
-// bit-identical with upstream edlib on `editDistance` (reference use:
-// construct.cc:190-199,407-416 - identity = 1 - ed/max(len)). EDLIB_TASK_PATH
-// (used by the polisher for the read-to-unitig alignment) walks back over the
-// stored vertical deltas.
+// calls (include/edlib.h). Only the global (NW) mode is on the reference's path
+// and only NW is served.
+//
+//  * EDLIB_TASK_DISTANCE (construct.cc:190-199,407-416: identity = 1 - ed/max):
+//    Myers/Hyyro bit-vector blocks inside an Ukkonen band that doubles until the
+//    distance fits. The distance is unique, so this is bit-identical with
+//    upstream edlib.
+//  * EDLIB_TASK_PATH (racon's read-to-unitig alignment, polish.cc:43-51): among
+//    the equally optimal paths upstream edlib returns ONE, fixed by two rules of
+//    edlib.cpp that are restated here:
+//      - obtainAlignmentTraceback: from the end cell, a move up (query symbol
+//        alone, EDLIB_EDOP_INSERT) is taken if it is optimal, else a move left
+//        (target symbol alone, EDLIB_EDOP_DELETE), else the diagonal;
+//      - obtainAlignment: that traceback is only used while its alignment data,
+//        (2*8+4) * ceil(|query|/64) * |target| + 8 * |target| bytes, stays below
+//        1 MiB. Larger problems are split Hirschberg-style at target column
+//        |target|/2: the path crosses that column at the SMALLEST query row r in
+//        [1, |query|-1] with forward[r] + backward[r] == distance (then r = 0,
+//        then r = |query|), and both halves are solved recursively.
+//    With these two rules RavenTest.Assemble reproduces the reference's golden
+//    value (1137, RavenTest/src/raven_test.cpp:66); any single fixed preference
+//    order without the split does not. Memory is O(|query| + |target|) above
+//    the 1 MiB base case.
 #include "edlib.h"
 
 #include <algorithm>
@@ -49,47 +65,51 @@ inline int Step(std::uint64_t eq, int hin, std::uint64_t high,
   return hout;
 }
 
-// Column-wise state kept for the traceback: vertical deltas of every block and
-// the cell value at the bottom of every block, after each target column.
+// match masks of the query: peq[symbol * blocks + block]
+struct Peq {
+  int blocks = 0;
+  std::vector<std::uint64_t> bits;
+  Peq(const unsigned char* q, int m) : blocks(CeilDiv(m, kWord)) {
+    bits.assign(static_cast<std::size_t>(256) * std::max(blocks, 1), 0);
+    for (int i = 0; i < m; ++i) {
+      bits[static_cast<std::size_t>(q[i]) * blocks + i / kWord] |= 1ULL << (i % kWord);
+    }
+  }
+  const std::uint64_t* of(unsigned char c) const {
+    return bits.data() + static_cast<std::size_t>(c) * blocks;
+  }
+};
+
+// Column-wise state of the full matrix, for the traceback of small problems:
+// vertical deltas of every block and the value at the bottom of every block.
 struct Trace {
   int blocks = 0;
   std::vector<std::uint64_t> pv, mv;  // [column][block]
   std::vector<std::int32_t> bottom;   // [column][block] = D[last row of block][column]
 };
 
-// Global distance between query (rows) and target (columns).
-int GlobalDistance(const unsigned char* q, int m, const unsigned char* t,
-                   int n, Trace* trace = nullptr) {
-  if (m == 0) {
-    return n;
-  }
-  if (n == 0) {
-    return m;
-  }
+// Whole matrix, no band: distance of query (rows) and the first `cols` target
+// columns. scores (optional): D[r][cols] for r = 0..m.
+int FullColumns(const unsigned char* q, int m, const unsigned char* t, int cols,
+                Trace* trace, std::vector<std::int32_t>* scores) {
   const int blocks = CeilDiv(m, kWord);
-  std::vector<std::uint64_t> peq(static_cast<std::size_t>(256) * blocks, 0);
-  for (int i = 0; i < m; ++i) {
-    peq[static_cast<std::size_t>(q[i]) * blocks + i / kWord] |=
-        1ULL << (i % kWord);
-  }
+  const Peq peq(q, m);
   const int last_bits = m - (blocks - 1) * kWord;
   const std::uint64_t last_high = 1ULL << (last_bits - 1);
-
   std::vector<std::uint64_t> pv(blocks, ~0ULL), mv(blocks, 0);
   std::vector<std::int32_t> bottom(blocks);
   for (int b = 0; b < blocks; ++b) bottom[b] = std::min(m, (b + 1) * kWord);
   if (trace) {
     trace->blocks = blocks;
-    trace->pv.resize(static_cast<std::size_t>(n) * blocks);
-    trace->mv.resize(static_cast<std::size_t>(n) * blocks);
-    trace->bottom.resize(static_cast<std::size_t>(n) * blocks);
+    trace->pv.resize(static_cast<std::size_t>(cols) * blocks);
+    trace->mv.resize(static_cast<std::size_t>(cols) * blocks);
+    trace->bottom.resize(static_cast<std::size_t>(cols) * blocks);
   }
-  for (int j = 0; j < n; ++j) {
-    const std::uint64_t* eq = peq.data() + static_cast<std::size_t>(t[j]) * blocks;
+  for (int j = 0; j < cols; ++j) {
+    const std::uint64_t* eq = peq.of(t[j]);
     int h = 1;  // D[0][j] - D[0][j-1] = +1 in global mode
     for (int b = 0; b < blocks; ++b) {
-      h = Step(eq[b], h, b == blocks - 1 ? last_high : (1ULL << 63), pv[b],
-               mv[b]);
+      h = Step(eq[b], h, b == blocks - 1 ? last_high : (1ULL << 63), pv[b], mv[b]);
       bottom[b] += h;
     }
     if (trace) {
@@ -99,7 +119,164 @@ int GlobalDistance(const unsigned char* q, int m, const unsigned char* t,
       std::copy(bottom.begin(), bottom.end(), trace->bottom.begin() + at);
     }
   }
+  if (scores) {
+    scores->resize(static_cast<std::size_t>(m) + 1);
+    std::int32_t v = cols;  // D[0][cols]
+    (*scores)[0] = v;
+    for (int r = 1; r <= m; ++r) {
+      const int b = (r - 1) / kWord, bit = (r - 1) % kWord;
+      v += static_cast<std::int32_t>((pv[b] >> bit) & 1) -
+           static_cast<std::int32_t>((mv[b] >> bit) & 1);
+      (*scores)[r] = v;
+    }
+  }
   return bottom[blocks - 1];
+}
+
+// Global distance if it is <= k, else -1. Ukkonen band |row - column| <= k at
+// block granularity: cells outside are never better than k, cells inside hold
+// upper bounds that are exact wherever the true value is <= k.
+int BandedDistance(const unsigned char* q, int m, const unsigned char* t, int n,
+                   const Peq& peq, int k) {
+  if (std::abs(m - n) > k) return -1;
+  const int blocks = peq.blocks;
+  const int last_bits = m - (blocks - 1) * kWord;
+  const std::uint64_t last_high = 1ULL << (last_bits - 1);
+  std::vector<std::uint64_t> pv(blocks), mv(blocks);
+  std::vector<std::int32_t> bottom(blocks);
+  auto rows_of = [&](int b) { return b == blocks - 1 ? last_bits : kWord; };
+  int lo = 0;
+  int hi = (std::min(m, std::max(1, k)) - 1) / kWord;  // column 0: rows 1..k
+  for (int b = 0; b <= hi; ++b) {
+    pv[b] = ~0ULL;
+    mv[b] = 0;
+    bottom[b] = std::min(m, (b + 1) * kWord);
+  }
+  for (int j = 1; j <= n; ++j) {
+    // band rows of column j: [j - k, j + k] (1-based cells)
+    const int want_hi = (std::min(m, j + k) - 1) / kWord;
+    while (hi < want_hi) {  // a block enters the band: all vertical deltas +1
+      ++hi;
+      pv[hi] = ~0ULL;
+      mv[hi] = 0;
+      bottom[hi] = bottom[hi - 1] + rows_of(hi);
+    }
+    const int want_lo = (std::max(1, j - k) - 1) / kWord;
+    if (want_lo > lo) lo = want_lo;
+    const std::uint64_t* eq = peq.of(t[j - 1]);
+    int h = 1;  // row 0 for lo == 0; an upper bound for a band that left row 0
+    for (int b = lo; b <= hi; ++b) {
+      h = Step(eq[b], h, b == blocks - 1 ? last_high : (1ULL << 63), pv[b], mv[b]);
+      bottom[b] += h;
+    }
+  }
+  if (hi != blocks - 1) return -1;
+  const int d = bottom[blocks - 1];
+  return d <= k ? d : -1;
+}
+
+int GlobalDistance(const unsigned char* q, int m, const unsigned char* t, int n,
+                   int k_limit) {
+  if (m == 0) return (k_limit < 0 || n <= k_limit) ? n : -1;
+  if (n == 0) return (k_limit < 0 || m <= k_limit) ? m : -1;
+  const Peq peq(q, m);
+  if (k_limit >= 0) return BandedDistance(q, m, t, n, peq, k_limit);
+  for (long long k = std::max(kWord, std::abs(m - n));; k *= 2) {
+    const int kk = static_cast<int>(std::min<long long>(k, m + n));
+    const int d = BandedDistance(q, m, t, n, peq, kk);
+    if (d >= 0) return d;
+  }
+}
+
+// edlib's obtainAlignmentTraceback over the stored columns of a small problem.
+void Traceback(const unsigned char* q, int m, const unsigned char* t, int n,
+               std::vector<unsigned char>* out) {
+  Trace trace;
+  const int d = FullColumns(q, m, t, n, &trace, nullptr);
+  auto cell = [&](int i, int j) -> int {  // D[i][j], i rows of query, j columns
+    if (j == 0) return i;
+    if (i == 0) return j;
+    const int b = (i - 1) / kWord;
+    const std::size_t at = static_cast<std::size_t>(j - 1) * trace.blocks + b;
+    const int last_row = std::min(m, (b + 1) * kWord);  // 1-based row of the block bottom
+    const int below = last_row - i;  // rows i+1 .. last_row lie below cell i
+    int v = trace.bottom[at];
+    if (below > 0) {
+      const int lo_bit = (i - 1) % kWord + 1;  // first bit below row i
+      const std::uint64_t mask = (below >= 64 ? ~0ULL : ((1ULL << below) - 1)) << lo_bit;
+      v -= __builtin_popcountll(trace.pv[at] & mask);
+      v += __builtin_popcountll(trace.mv[at] & mask);
+    }
+    return v;
+  };
+  std::vector<unsigned char> ops;
+  ops.reserve(static_cast<std::size_t>(m) + n);
+  int i = m, j = n, cur = d;
+  while (i > 0 || j > 0) {
+    if (i > 0 && cell(i - 1, j) + 1 == cur) {
+      ops.push_back(EDLIB_EDOP_INSERT);
+      --i;
+      --cur;
+    } else if (j > 0 && cell(i, j - 1) + 1 == cur) {
+      ops.push_back(EDLIB_EDOP_DELETE);
+      --j;
+      --cur;
+    } else {
+      const bool eq = q[i - 1] == t[j - 1];
+      ops.push_back(eq ? EDLIB_EDOP_MATCH : EDLIB_EDOP_MISMATCH);
+      --i;
+      --j;
+      if (!eq) --cur;
+    }
+  }
+  out->insert(out->end(), ops.rbegin(), ops.rend());
+}
+
+// edlib's obtainAlignment (see the header comment)
+void ObtainAlignment(const unsigned char* q, int m, const unsigned char* t, int n,
+                     int best, std::vector<unsigned char>* out) {
+  if (m == 0) {
+    out->insert(out->end(), n, EDLIB_EDOP_DELETE);
+    return;
+  }
+  if (n == 0) {
+    out->insert(out->end(), m, EDLIB_EDOP_INSERT);
+    return;
+  }
+  const long long blocks = CeilDiv(m, kWord);
+  const long long data_size = (2ll * 8 + 4) * blocks * n + 2ll * 4 * n;
+  if (data_size < 1024 * 1024) {
+    Traceback(q, m, t, n, out);
+    return;
+  }
+  const int left = n / 2, right = n - left;
+  std::vector<std::int32_t> fw, bw;
+  FullColumns(q, m, t, left, nullptr, &fw);
+  {
+    std::vector<unsigned char> rq(q, q + m), rt(t + left, t + n);
+    std::reverse(rq.begin(), rq.end());
+    std::reverse(rt.begin(), rt.end());
+    FullColumns(rq.data(), m, rt.data(), right, nullptr, &bw);
+  }
+  // bw[m - r] = distance of q[r, m) and t[left, n)
+  int split = -1;
+  for (int r = 1; r <= m - 1; ++r) {
+    if (fw[r] + bw[m - r] == best) {
+      split = r;
+      break;
+    }
+  }
+  if (split < 0 && fw[0] + bw[m] == best) split = 0;
+  if (split < 0 && fw[m] + bw[0] == best) split = m;
+  if (split < 0) {  // (unreachable: some row of the column lies on an optimal path)
+    Traceback(q, m, t, n, out);
+    return;
+  }
+  const int left_score = fw[split], right_score = bw[m - split];
+  std::vector<std::int32_t>().swap(fw);
+  std::vector<std::int32_t>().swap(bw);
+  ObtainAlignment(q, split, t, left, left_score, out);
+  ObtainAlignment(q + split, m - split, t + left, right, right_score, out);
 }
 
 }  // namespace
@@ -145,10 +322,8 @@ EdlibAlignResult edlibAlign(const char* query, int queryLength,
     for (bool s : seen) r.alphabetLength += s;
   }
 
-  const bool want_path = config.task == EDLIB_TASK_PATH;
-  Trace trace;
-  int d = GlobalDistance(q, queryLength, t, targetLength, want_path ? &trace : nullptr);
-  if (config.k >= 0 && d > config.k) {
+  const int d = GlobalDistance(q, queryLength, t, targetLength, config.k);
+  if (d < 0) {
     return r;  // editDistance stays -1
   }
   r.editDistance = d;
@@ -158,50 +333,10 @@ EdlibAlignResult edlibAlign(const char* query, int queryLength,
   r.endLocations[0] = targetLength - 1;
   r.startLocations[0] = 0;
 
-  if (want_path) {
-    // Walk back from (m, n). Among equally good moves: up (a query symbol
-    // alone, EDLIB_EDOP_INSERT), then left (a target symbol alone,
-    // EDLIB_EDOP_DELETE), then the diagonal - the order we recall of edlib's
-    // own traceback (upstream's choice is not pinned by the reference tree).
-    const int m = queryLength, n = targetLength;
-    auto cell = [&](int i, int j) -> int {  // D[i][j], i rows of query, j columns
-      if (j == 0) return i;
-      if (i == 0) return j;
-      const int b = (i - 1) / kWord;
-      const std::size_t at = static_cast<std::size_t>(j - 1) * trace.blocks + b;
-      const int last_row = std::min(m, (b + 1) * kWord);  // 1-based row of the block bottom
-      // rows i+1 .. last_row lie below cell i inside the block
-      const int below = last_row - i;
-      int v = trace.bottom[at];
-      if (below > 0) {
-        const int lo_bit = (i - 1) % kWord + 1;  // first bit below row i
-        const std::uint64_t mask = (below >= 64 ? ~0ULL : ((1ULL << below) - 1)) << lo_bit;
-        v -= __builtin_popcountll(trace.pv[at] & mask);
-        v += __builtin_popcountll(trace.mv[at] & mask);
-      }
-      return v;
-    };
+  if (config.task == EDLIB_TASK_PATH) {
     std::vector<unsigned char> ops;
-    ops.reserve(static_cast<std::size_t>(m) + n);
-    int i = m, j = n, cur = d;
-    while (i > 0 || j > 0) {
-      if (i > 0 && cell(i - 1, j) + 1 == cur) {
-        ops.push_back(EDLIB_EDOP_INSERT);
-        --i;
-        --cur;
-      } else if (j > 0 && cell(i, j - 1) + 1 == cur) {
-        ops.push_back(EDLIB_EDOP_DELETE);
-        --j;
-        --cur;
-      } else {
-        const bool eq = q[i - 1] == t[j - 1];
-        ops.push_back(eq ? EDLIB_EDOP_MATCH : EDLIB_EDOP_MISMATCH);
-        --i;
-        --j;
-        if (!eq) --cur;
-      }
-    }
-    std::reverse(ops.begin(), ops.end());
+    ops.reserve(static_cast<std::size_t>(queryLength) + targetLength);
+    ObtainAlignment(q, queryLength, t, targetLength, d, &ops);
     r.alignmentLength = static_cast<int>(ops.size());
     r.alignment = static_cast<unsigned char*>(std::malloc(ops.size() + 1));
     std::memcpy(r.alignment, ops.data(), ops.size());

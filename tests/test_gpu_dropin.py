@@ -69,7 +69,8 @@ def test_dropin_synthetic_small_kmax(tmp_path, oracle):
 def test_full_pipeline_on_b200_equals_oracle_pipeline(tmp_path, oracle, reference, lambda_reads):
     """RavenTest.Assemble with the reference's own sources on the B200 facades
     (ram::MinimizerEngine, racon::Polisher incl. GPU POA) == the same sources over
-    the CPU oracle: identical polished unitig, 1141 edits to NC_001416 (golden 1137)."""
+    the CPU oracle: identical polished unitig, and the reference's golden value:
+    1137 edits to NC_001416 (RavenTest/src/raven_test.cpp:66)."""
     import oracle_lib
     from raven_b200 import seqio
     binary = os.path.join(HERE, "cpp", "_build", "assemble_test")
@@ -91,4 +92,4 @@ def test_full_pipeline_on_b200_equals_oracle_pipeline(tmp_path, oracle, referenc
     assert seqs == want_seqs
     genome = seqio.ReadSet.load(os.path.join(HERE, "golden", "lambda_genome.npz")).ascii(0)
     rc = seqs[0].translate(bytes.maketrans(b"ACGT", b"TGCA"))[::-1]
-    assert oracle.edit_distance(rc, genome) == 1141
+    assert oracle.edit_distance(rc, genome) == 1137   # EXPECT_EQ(1137, ...) raven_test.cpp:66

@@ -154,6 +154,41 @@ def test_map_edge_cases_and_repeats(gpu_engine, oracle):
                [(0, rs.n, True, True, False)])
 
 
+def test_map_external_read(gpu_engine, oracle, lambda_reads):
+    """ram::MinimizerEngine::Map for a read outside the indexed/uploaded set
+    (construct.cc:59-62 with several index batches; assemble.cc:757,780)."""
+    n = lambda_reads.n
+    n_idx = n - 6
+    sub = lambda_reads.subset(range(n_idx))
+    gpu_engine.configure(15, 5)
+    gpu_engine.upload(sub)
+    gpu_engine.minimize(0, n_idx, False)
+    occ = gpu_engine.filter(0.001)
+    eng = oracle.engine(15, 5, threads=4)
+    reads = oracle.reads(lambda_reads)
+    oracle.minimize(eng, reads, 0, n_idx, False)
+    assert occ == oracle.filter(eng, 0.001)
+    rs = lambda_reads
+    for j in range(n_idx, n):
+        w = rs.words[int(rs.word_off[j]):int(rs.word_off[j + 1])]
+        for (ae, asym, mh) in ((True, True, True), (False, False, False), (True, False, True),
+                               (True, True, False)):
+            got = gpu_engine.map_external(w, int(rs.lens[j]), j, ae, asym, mh,
+                                          want_filtered=True)
+            want = oracle.map(eng, reads, j, j + 1, ae, asym, mh)
+            assert np.array_equal(got["overlaps"], want["overlaps"]), (j, ae, asym, mh)
+            assert np.array_equal(got["filtered"], want["filtered"]), (j, ae, asym, mh)
+    # an id BELOW the indexed ids: avoid_symmetric keeps every posting
+    j = n - 1
+    w = rs.words[int(rs.word_off[j]):int(rs.word_off[j + 1])]
+    got = gpu_engine.map_external(w, int(rs.lens[j]), j, False, False, True)
+    assert got["overlaps"].shape[0] > 0
+    # the uploaded set is intact afterwards
+    again = gpu_engine.map(0, 20, True, True, True)
+    want = oracle.map(eng, reads, 0, 20, True, True, True)
+    assert np.array_equal(again["overlaps"], want["overlaps"])
+
+
 def test_empty_inputs(gpu_engine, oracle):
     rs = seqio.pack_codes([])
     gpu_engine.configure(15, 5)

@@ -231,17 +231,16 @@ def test_end_to_end_pin_against_reference_golden(oracle, reference, lambda_reads
     """RavenTest.Assemble (RavenTest/src/raven_test.cpp:50-67), the reference's ONLY
     golden value: the reference's own construct/assemble/polish/common sources
     (compiled in place) over the oracle restatements of ram, racon, spoa and the
-    edlib path. Upstream expects 1137; the restatement lands at 1141 (4 edits
-    over 48.5 kb). The residue sits in tie-breaks no file of the reference tree
-    pins (alignment path among equal optima, layer order): the six fixed path
-    preferences give 1131..1166."""
+    edlib path. Upstream expects 1137 and the restatement reproduces it exactly;
+    what decides the last edits is edlib's Hirschberg split of alignments whose
+    traceback data would exceed 1 MiB (oracle/nw_path.cpp) - without it the six
+    fixed traceback preferences give 1131..1166."""
     import oracle_lib
     genome = seqio.ReadSet.load(os.path.join(HERE, "golden", "lambda_genome.npz")).ascii(0)
     names, seqs = oracle_lib.ref_assemble(reference, lambda_reads, True, 2, 8)
     assert len(seqs) == 1 and names[0].startswith("Utg")
     ed = oracle.edit_distance(_revcomp(seqs[0]), genome)
-    assert ed == 1141                 # regression pin of OUR oracle
-    assert abs(ed - 1137) <= 5        # distance to the upstream golden value
+    assert ed == 1137                 # EXPECT_EQ(1137, ...) raven_test.cpp:66
     # unpolished assembly for scale
     names0, seqs0 = oracle_lib.ref_assemble(reference, lambda_reads, True, 0, 8)
     assert oracle.edit_distance(_revcomp(seqs0[0]), genome) > 5 * ed
@@ -272,3 +271,74 @@ def test_nw_path_is_optimal_and_deterministic(oracle):
             else:
                 cost += 1; j += 1
         assert cost == oracle.edit_distance(a, b)
+
+
+def _host_edlib():
+    """The PRODUCT's host edlib (raven_b200/host/edlib.cc) as a library of its own."""
+    import ctypes as C
+    import subprocess
+    subprocess.run(["make", "-C", os.path.join(HERE, "cpp"), "host"], check=True,
+                   stdout=subprocess.DEVNULL)
+    lib = C.CDLL(os.path.join(HERE, "cpp", "_build", "libhost_edlib.so"))
+
+    class Cfg(C.Structure):
+        _fields_ = [("k", C.c_int), ("mode", C.c_int), ("task", C.c_int),
+                    ("eq", C.c_void_p), ("n_eq", C.c_int)]
+
+    class Res(C.Structure):
+        _fields_ = [("status", C.c_int), ("editDistance", C.c_int),
+                    ("endLocations", C.POINTER(C.c_int)), ("startLocations", C.POINTER(C.c_int)),
+                    ("numLocations", C.c_int), ("alignment", C.POINTER(C.c_ubyte)),
+                    ("alignmentLength", C.c_int), ("alphabetLength", C.c_int)]
+
+    lib.edlibAlign.restype = Res
+    lib.edlibAlign.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, Cfg]
+    lib.edlibFreeAlignResult.argtypes = [Res]
+
+    def align(a, b, task, k=-1):
+        r = lib.edlibAlign(a, len(a), b, len(b), Cfg(k, 0, task, None, 0))
+        assert r.status == 0
+        path = bytes(r.alignment[i] for i in range(r.alignmentLength)) if task == 2 else b""
+        d = r.editDistance
+        lib.edlibFreeAlignResult(r)
+        return d, path
+
+    return align
+
+
+def test_product_edlib_equals_oracle(oracle):
+    """raven_b200/host/edlib.cc (bit-vector blocks, band doubling, traceback below
+    1 MiB, Hirschberg split above) against the oracle's plain dynamic programmes:
+    distance AND the one path upstream edlib would return, incl. 10 kb ONT pairs."""
+    import ctypes as C
+    align = _host_edlib()
+    oracle.lib.orc_nw_path.restype = C.c_int64
+    oracle.lib.orc_nw_path.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p]
+    rng = np.random.default_rng(11)
+    letters = np.frombuffer(b"ACGT", np.uint8)
+    cases = [(0, 0.1), (1, 0.1), (2, 0.5), (63, 0.1), (64, 0.1), (65, 0.2), (130, 0.0),
+             (700, 0.3), (1500, 0.15), (3000, 0.1), (4100, 0.02), (6000, 0.12),
+             (10000, 0.1), (12000, 0.01), (11000, 0.15)]
+    cases += [(int(rng.integers(1, 900)), float(rng.uniform(0, 0.4))) for _ in range(30)]
+    for n, err in cases:
+        a = rng.integers(0, 4, n, dtype=np.uint8)
+        b = synth.mutate(a, rng, err / 3, err / 3, err / 3) if n else a
+        if n and rng.random() < 0.3:   # unequal ends
+            b = np.concatenate([rng.integers(0, 4, int(rng.integers(0, 40)), dtype=np.uint8), b])
+        sa, sb = letters[a].tobytes(), letters[np.asarray(b, dtype=np.uint8)].tobytes()
+        d, path = align(sa, sb, 2)
+        d0, _ = align(sa, sb, 0)
+        assert d == d0
+        if max(len(sa), len(sb)) <= 3000:
+            assert d == oracle.edit_distance(sa, sb), (n, err)
+        buf = C.create_string_buffer(len(sa) + len(sb) + 1)
+        ln = oracle.lib.orc_nw_path(sa, len(sa), sb, len(sb), buf)
+        want = buf.raw[:ln]
+        got = path.translate(bytes.maketrans(bytes([0, 1, 2, 3]), b"MIDM"))
+        assert got == want, (n, err)
+        assert d == want.count(b"I") + want.count(b"D") + sum(
+            1 for op in path if op == 3), (n, err)
+        # bounded calls: k below the distance -> -1, k at the distance -> found
+        if d > 0:
+            assert align(sa, sb, 0, d - 1)[0] == -1
+        assert align(sa, sb, 0, d)[0] == d
