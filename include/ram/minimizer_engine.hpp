@@ -67,6 +67,9 @@ class MinimizerEngine {
   // the whole read set on the device (ids must equal positions); lets stage 1
   // run without per-batch uploads
   void Upload(const std::vector<std::unique_ptr<biosoup::NucleicAcid>>& sequences);
+  // any range, with its own ids (stage 2: the valid reads, sorted by id)
+  void Upload(std::vector<std::unique_ptr<biosoup::NucleicAcid>>::const_iterator first,
+              std::vector<std::unique_ptr<biosoup::NucleicAcid>>::const_iterator last);
   rvn_ctx* context() const { return ctx_; }
   std::mutex& mutex() const { return *mutex_; }
   std::uint32_t occurrence() const { return occurrence_; }

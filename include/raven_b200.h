@@ -15,6 +15,10 @@
  *   rvn_kmer_complexity    raven::Pile::AddKmers       RavenLib/src/pile.cc:64-120
  *   rvn_poa_batch          racon::Polisher::Polish (window consensus: racon::Window +
  *                          spoa)                       RavenLib/src/polish.cc:43-51
+ *   rvn_edit_distance_batch
+ *                          edlibAlign(lhs, rhs, edlibDefaultAlignConfig()) of the
+ *                          identity filter      RavenLib/src/construct.cc:176-199,
+ *                                                                        :393-416
  *   rvn_find_overlaps_and_create_piles
  *                          raven::FindOverlapsAndCreatePiles
  *                                                      RavenLib/src/construct.cc:14-121
@@ -150,6 +154,20 @@ int rvn_kmer_complexity(rvn_ctx* ctx, const uint32_t* read_index,
                         const uint32_t* positions, uint64_t n, uint32_t kmer_len,
                         uint8_t* keep);
 
+/* The identity filter's edlibAlign(lhs, rhs, edlibDefaultAlignConfig()).editDistance
+ * (RavenLib/src/construct.cc:176-199 and :393-416) for n_pairs overlaps at once:
+ * pair i aligns bases [lhs_begin, +lhs_len) of uploaded read lhs_read[i] with
+ * [rhs_begin, +rhs_len) of read rhs_read[i], the latter reverse complemented when
+ * strand[i] == 0 (construct.cc:184-188). Reads are addressed by their index in
+ * the uploaded set. limit (may be NULL): limit[i] >= 0 bounds the search -
+ * distance[i] = -1 if the distance exceeds it (the filter only needs to know that
+ * 1 - ed/max(len) < identity); limit[i] < 0: exact distance, whatever it takes. */
+int rvn_edit_distance_batch(rvn_ctx* ctx, uint64_t n_pairs, const uint32_t* lhs_read,
+                            const uint32_t* lhs_begin, const uint32_t* lhs_len,
+                            const uint32_t* rhs_read, const uint32_t* rhs_begin,
+                            const uint32_t* rhs_len, const uint8_t* strand,
+                            const int32_t* limit, int32_t* distance);
+
 /* raven::FindOverlapsAndCreatePiles over the uploaded read set: index batches
  * of >= index_batch_bases (reference: 1<<32), query flushes of >=
  * query_batch_bases (reference: 1<<30); pass 0 for the reference values.
@@ -203,6 +221,14 @@ int rvn_index_records(rvn_ctx* ctx, const uint64_t** value,
 int rvn_map_hits(rvn_ctx* ctx, const uint64_t** group,
                  const uint64_t** positions, const uint64_t** hit_off,
                  uint64_t* n_hits);
+
+/* The engine's stable LSD radix sort (raven_b200/csrc/radix.cu - it orders the
+ * minimizer index, construct.cc:42-43) on host arrays, in place: keys of 4 or 8
+ * bytes, values of 0 (u32 keys only), 4 or 8 bytes, key bits [begin_bit,
+ * end_bit); equal keys keep their input order. */
+int rvn_debug_sort_pairs(rvn_ctx* ctx, int key_bytes, int val_bytes, void* keys,
+                         void* vals, uint64_t n, int begin_bit, int end_bit,
+                         int descending);
 
 int rvn_get_stats(rvn_ctx* ctx, rvn_stats* out);
 

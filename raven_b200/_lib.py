@@ -70,6 +70,11 @@ SIGNATURES = {
                                     U64P, U64P]),
     "rvn_map_hits": (C.c_int, [C.c_void_p, C.POINTER(U64P), C.POINTER(U64P),
                                C.POINTER(U64P), U64P]),
+    "rvn_edit_distance_batch": (C.c_int, [C.c_void_p, C.c_uint64, U32P, U32P, U32P, U32P, U32P,
+                                          U32P, C.POINTER(C.c_uint8), C.POINTER(C.c_int32),
+                                          C.POINTER(C.c_int32)]),
+    "rvn_debug_sort_pairs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_uint64, C.c_int, C.c_int, C.c_int]),
     "rvn_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "rvn_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "rvn_get_timings": (C.c_int, [C.c_void_p, C.POINTER(C.POINTER(C.c_char_p)),

@@ -494,10 +494,15 @@ RVN_API int rvn_sketch(rvn_ctx* ctx, uint32_t first, uint32_t last, int minhash,
     uint64_t* hv = c.x_val.reserve(total + 1);
     uint64_t* ho = c.x_org.reserve(total + 1);
     uint64_t* hf = c.x_off.reserve(nr + 2ULL);
-    RVN_CUDA(cudaMemcpyAsync(hv, dv, total * 8, cudaMemcpyDeviceToHost, c.stream));
+    const bool v32 = !minhash && c.s_is32;  // full sketches of k <= 15 hold u32 values
+    RVN_CUDA(cudaMemcpyAsync(hv, dv, total * (v32 ? 4 : 8), cudaMemcpyDeviceToHost, c.stream));
     RVN_CUDA(cudaMemcpyAsync(ho, dorg, total * 8, cudaMemcpyDeviceToHost, c.stream));
     for (uint32_t i = 0; i <= nr; ++i) hf[i] = (*hoff)[i];
     RVN_CUDA(cudaStreamSynchronize(c.stream));
+    if (v32) {  // widen in place, back to front
+      const uint32_t* h32 = reinterpret_cast<const uint32_t*>(hv);
+      for (uint64_t i = total; i-- > 0;) hv[i] = h32[i];
+    }
     TimerCollect(c);
     if (value) *value = hv;
     if (origin) *origin = ho;
@@ -513,11 +518,15 @@ RVN_API int rvn_index_records(rvn_ctx* ctx, const uint64_t** value,
     if (!c.i_valid) throw StateError("no index");
     uint64_t* hv = c.x_val.reserve(c.i_n + 1);
     uint64_t* ho = c.x_org.reserve(c.i_n + 1);
-    RVN_CUDA(cudaMemcpyAsync(hv, c.i_val.get(), c.i_n * 8, cudaMemcpyDeviceToHost,
-                             c.stream));
+    RVN_CUDA(cudaMemcpyAsync(hv, c.i_val.get(), c.i_n * (c.i_is32 ? 4 : 8),
+                             cudaMemcpyDeviceToHost, c.stream));
     RVN_CUDA(cudaMemcpyAsync(ho, c.i_org.get(), c.i_n * 8, cudaMemcpyDeviceToHost,
                              c.stream));
     RVN_CUDA(cudaStreamSynchronize(c.stream));
+    if (c.i_is32) {  // widen in place, back to front
+      const uint32_t* h32 = reinterpret_cast<const uint32_t*>(hv);
+      for (uint64_t i = c.i_n; i-- > 0;) hv[i] = h32[i];
+    }
     if (value) *value = hv;
     if (origin) *origin = ho;
     if (n_records) *n_records = c.i_n;
@@ -534,6 +543,75 @@ RVN_API int rvn_map_hits(rvn_ctx* ctx, const uint64_t** group,
     if (positions) *positions = c.r_hit_pos.get();
     if (hit_off) *hit_off = c.r_hit_off.get();
     if (n_hits) *n_hits = c.r_n_hits;
+  });
+}
+
+RVN_API int rvn_edit_distance_batch(rvn_ctx* ctx, uint64_t n_pairs, const uint32_t* lhs_read,
+                                    const uint32_t* lhs_begin, const uint32_t* lhs_len,
+                                    const uint32_t* rhs_read, const uint32_t* rhs_begin,
+                                    const uint32_t* rhs_len, const uint8_t* strand,
+                                    const int32_t* limit, int32_t* distance) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (n_pairs && (!lhs_read || !lhs_begin || !lhs_len || !rhs_read || !rhs_begin || !rhs_len ||
+                    !strand || !distance)) {
+      throw InvalidArgument("null argument");
+    }
+    EditDistanceBatch(c, n_pairs, lhs_read, lhs_begin, lhs_len, rhs_read, rhs_begin, rhs_len,
+                      strand, limit, distance);
+    TimerCollect(c);
+  });
+}
+
+// the engine's radix sort on host arrays (parity tests of radix.cu)
+RVN_API int rvn_debug_sort_pairs(rvn_ctx* ctx, int key_bytes, int val_bytes, void* keys,
+                                 void* vals, uint64_t n, int begin_bit, int end_bit,
+                                 int descending) {
+  return Guard(ctx, [&](Ctx& c) {
+    if ((key_bytes != 4 && key_bytes != 8) || (val_bytes != 0 && val_bytes != 4 && val_bytes != 8)) {
+      throw InvalidArgument("key of 4 or 8 bytes, value of 0, 4 or 8 bytes");
+    }
+    if (val_bytes == 0 && key_bytes != 4) throw InvalidArgument("keys-only sort takes u32 keys");
+    if (begin_bit < 0 || end_bit > 8 * key_bytes || begin_bit > end_bit) {
+      throw InvalidArgument("bit range out of bounds");
+    }
+    if (n && (!keys || (val_bytes && !vals))) throw InvalidArgument("null arrays");
+    DevBuf<uint8_t> ks, ka, kb, vs, va, vb;
+    const size_t kb_ = static_cast<size_t>(key_bytes) * n + 16, vb_ = static_cast<size_t>(val_bytes) * n + 16;
+    ks.reserve(kb_); ka.reserve(kb_); kb.reserve(kb_);
+    vs.reserve(vb_); va.reserve(vb_); vb.reserve(vb_);
+    RVN_CUDA(cudaMemcpyAsync(ks.get(), keys, static_cast<size_t>(key_bytes) * n, cudaMemcpyHostToDevice, c.stream));
+    if (val_bytes) {
+      RVN_CUDA(cudaMemcpyAsync(vs.get(), vals, static_cast<size_t>(val_bytes) * n, cudaMemcpyHostToDevice, c.stream));
+    }
+    int where;
+    const bool desc = descending != 0;
+    if (val_bytes == 0) {
+      where = RadixSortKeys(c, (const uint32_t*)ks.get(), (uint32_t*)ka.get(), (uint32_t*)kb.get(), n,
+                            begin_bit, end_bit);
+    } else if (key_bytes == 4 && val_bytes == 8) {
+      where = RadixSortPairs(c, (const uint32_t*)ks.get(), (uint32_t*)ka.get(), (uint32_t*)kb.get(),
+                             (const uint64_t*)vs.get(), (uint64_t*)va.get(), (uint64_t*)vb.get(), n,
+                             begin_bit, end_bit, desc);
+    } else if (key_bytes == 8 && val_bytes == 8) {
+      where = RadixSortPairs(c, (const uint64_t*)ks.get(), (uint64_t*)ka.get(), (uint64_t*)kb.get(),
+                             (const uint64_t*)vs.get(), (uint64_t*)va.get(), (uint64_t*)vb.get(), n,
+                             begin_bit, end_bit, desc);
+    } else if (key_bytes == 4 && val_bytes == 4) {
+      where = RadixSortPairs(c, (const uint32_t*)ks.get(), (uint32_t*)ka.get(), (uint32_t*)kb.get(),
+                             (const uint32_t*)vs.get(), (uint32_t*)va.get(), (uint32_t*)vb.get(), n,
+                             begin_bit, end_bit, desc);
+    } else {
+      where = RadixSortPairs(c, (const uint64_t*)ks.get(), (uint64_t*)ka.get(), (uint64_t*)kb.get(),
+                             (const uint32_t*)vs.get(), (uint32_t*)va.get(), (uint32_t*)vb.get(), n,
+                             begin_bit, end_bit, desc);
+    }
+    const uint8_t* rk = where < 0 ? ks.get() : (where == 0 ? ka.get() : kb.get());
+    const uint8_t* rv = where < 0 ? vs.get() : (where == 0 ? va.get() : vb.get());
+    RVN_CUDA(cudaMemcpyAsync(keys, rk, static_cast<size_t>(key_bytes) * n, cudaMemcpyDeviceToHost, c.stream));
+    if (val_bytes) {
+      RVN_CUDA(cudaMemcpyAsync(vals, rv, static_cast<size_t>(val_bytes) * n, cudaMemcpyDeviceToHost, c.stream));
+    }
+    RVN_CUDA(cudaStreamSynchronize(c.stream));
   });
 }
 
@@ -588,7 +666,7 @@ RVN_API int rvn_dist_index(rvn_ctx* ctx, const uint64_t* d_value,
   return Guard(ctx, [&](Ctx& c) {
     if (n_records && (!d_value || !d_origin)) throw InvalidArgument("null records");
     c.i_first = c.i_last = 0;
-    BuildIndexFrom(c, d_value, d_origin, n_records, index_bases);
+    BuildIndexFrom(c, ValView{d_value, 0}, d_origin, n_records, index_bases);
     // (records of a partitioned run arrive in read order: the caller's contract)
     c.i_sorted_ids = c.ids_ascending;
     RVN_CUDA(cudaStreamSynchronize(c.stream));

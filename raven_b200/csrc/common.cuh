@@ -80,6 +80,23 @@ struct DevBuf {
     return p;
   }
   T* get() const { return p; }
+  void swap(DevBuf& o) {
+    std::swap(p, o.p);
+    std::swap(cap, o.cap);
+  }
+};
+
+// Minimizer values travel as u32 when 2k <= 30 bits (k <= 15: raven's default)
+// and as u64 otherwise; kernels that only read them take this view.
+struct ValView {
+  const void* p;
+  int is32;
+#ifdef __CUDACC__
+  __device__ __forceinline__ uint64_t operator[](uint64_t i) const {
+    return is32 ? static_cast<uint64_t>(static_cast<const uint32_t*>(p)[i])
+                : static_cast<const uint64_t*>(p)[i];
+  }
+#endif
 };
 
 // Grow-only pinned host buffer (D2H results, H2D staging).

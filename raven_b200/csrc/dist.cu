@@ -45,7 +45,7 @@ constexpr uint32_t kPartRounds = 8;
 constexpr uint32_t kPartTile = kThreads * kPartRounds;
 
 __global__ void __launch_bounds__(kThreads)
-PartitionCount(const uint64_t* __restrict__ val, uint64_t n, uint32_t parts,
+PartitionCount(ValView val, uint64_t n, uint32_t parts,
                uint64_t n_tiles, uint32_t* __restrict__ hist) {
   __shared__ uint32_t cnt[kMaxParts];
   if (threadIdx.x < kMaxParts) cnt[threadIdx.x] = 0;
@@ -65,7 +65,7 @@ PartitionCount(const uint64_t* __restrict__ val, uint64_t n, uint32_t parts,
 }
 
 __global__ void __launch_bounds__(kThreads)
-PartitionScatter(const uint64_t* __restrict__ val, const uint64_t* __restrict__ org,
+PartitionScatter(ValView val, const uint64_t* __restrict__ org,
                  uint64_t n, uint32_t parts, uint64_t n_tiles,
                  const uint64_t* __restrict__ tile_base, uint64_t* __restrict__ out_val,
                  uint64_t* __restrict__ out_org) {
@@ -121,7 +121,7 @@ __global__ void GatherBoundaries(const uint64_t* __restrict__ src, uint64_t stri
 // seed lookup of received queries, hits written into per-destination runs
 // ---------------------------------------------------------------------------
 struct IndexView2 {
-  const uint64_t* val;
+  ValView val;
   const uint64_t* org;
   const uint32_t* bucket;
   uint64_t n;
@@ -518,22 +518,24 @@ void DistSketchSplit(Ctx& c, uint32_t first, uint32_t last, int which, uint32_t 
                      const uint64_t** d_val, const uint64_t** d_org, uint64_t* counts) {
   CheckParts(parts, 0);
   EnsureSketch(c, first, last);
-  const uint64_t* sv = c.s_val.get();
+  ValView sv{c.s_val.get(), c.s_is32 ? 1 : 0};
   const uint64_t* so = c.s_org.get();
   uint64_t n = c.s_n;
   if (which == 1) {
     EnsureMicromizers(c, first, last);
-    sv = c.q_val.get();
+    sv = ValView{c.q_val.get(), 0};
     so = c.q_org.get();
     n = c.q_n;
   }
-  if (parts == 1 || n == 0) {  // nothing to move
+  if ((parts == 1 && !sv.is32) || n == 0) {  // nothing to move
     for (uint32_t p = 0; p < parts; ++p) counts[p] = 0;
     counts[0] = n;
-    *d_val = sv;
+    *d_val = static_cast<const uint64_t*>(sv.p);
     *d_org = so;
     return;
   }
+  // (one part with u32 sketch values: the partition below is the widening copy
+  //  to the 16-byte exchange format)
   DevBuf<uint64_t>& ov = which == 1 ? c.ds_qsplit_val : c.ds_split_val;
   DevBuf<uint64_t>& oo = which == 1 ? c.ds_qsplit_org : c.ds_split_org;
   uint64_t* out_val = ov.reserve(n + 1);
@@ -568,7 +570,7 @@ void DistHitsSplit(Ctx& c, const uint64_t* d_qval, const uint64_t* d_qorg, uint6
   if (!c.i_valid) throw StateError("no index");
   CheckParts(parts, 0);
   if (n_query > c.n_reads) throw InvalidArgument("query range out of bounds");
-  IndexView2 ix{c.i_val.get(), c.i_org.get(), c.i_bucket.get(), c.i_n,
+  IndexView2 ix{ValView{c.i_val.get(), c.i_is32 ? 1 : 0}, c.i_org.get(), c.i_bucket.get(), c.i_n,
                 static_cast<int>(2 * c.prm.k) - c.i_bucket_bits, c.occurrence};
   const uint32_t per_part = CeilDiv(n_query, parts);
   const uint64_t slots = static_cast<uint64_t>(per_part) * parts;

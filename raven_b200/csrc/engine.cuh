@@ -62,6 +62,7 @@ struct Ctx {
   uint32_t s_first = 0, s_last = 0;
   uint64_t s_n = 0;
   DevBuf<uint64_t> s_val, s_org, s_off;  // s_off: (s_last-s_first)+1
+  bool s_is32 = false;  // s_val holds u32 values (2k <= 30 bits)
   std::vector<uint64_t> h_s_off;
   DevBuf<uint32_t> tile_cnt;
   DevBuf<uint64_t> tile_out, tile_status;
@@ -78,6 +79,7 @@ struct Ctx {
   uint32_t i_first = 0, i_last = 0;
   uint64_t i_n = 0, i_keys = 0;
   DevBuf<uint64_t> i_val, i_org, i_val_alt, i_org_alt;
+  bool i_is32 = false;  // i_val holds u32 values
   DevBuf<uint32_t> i_bucket;
   int i_bucket_bits = 0;
   DevBuf<uint64_t> i_gaps;  // long empty stretches of the bucket table (index.cu)
@@ -208,9 +210,29 @@ void EnsureMicromizers(Ctx& c, uint32_t first, uint32_t last);
 
 // ---- index.cu ----
 void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash);
-// index from device records already in (read, position) order
-void BuildIndexFrom(Ctx& c, const uint64_t* src_val, const uint64_t* src_org, uint64_t n,
+// index from device records already in (read, position) order (values as u32
+// or u64, see ValView)
+void BuildIndexFrom(Ctx& c, ValView src_val, const uint64_t* src_org, uint64_t n,
                     uint64_t index_bases);
+
+// ---- radix.cu ---- stable LSD radix sort on key bits [begin_bit, end_bit).
+// The source arrays are only read (src may alias buffer b: it is dead once the
+// first pass is through); the result lands in buffer a (return 0) or b (return
+// 1); -1 = nothing to do, the source order is the result.
+int RadixSortPairs(Ctx& c, const uint32_t* src_keys, uint32_t* keys_a, uint32_t* keys_b,
+                   const uint64_t* src_vals, uint64_t* vals_a, uint64_t* vals_b, uint64_t n,
+                   int begin_bit, int end_bit, bool descending = false);
+int RadixSortPairs(Ctx& c, const uint64_t* src_keys, uint64_t* keys_a, uint64_t* keys_b,
+                   const uint64_t* src_vals, uint64_t* vals_a, uint64_t* vals_b, uint64_t n,
+                   int begin_bit, int end_bit, bool descending = false);
+int RadixSortPairs(Ctx& c, const uint32_t* src_keys, uint32_t* keys_a, uint32_t* keys_b,
+                   const uint32_t* src_vals, uint32_t* vals_a, uint32_t* vals_b, uint64_t n,
+                   int begin_bit, int end_bit, bool descending = false);
+int RadixSortPairs(Ctx& c, const uint64_t* src_keys, uint64_t* keys_a, uint64_t* keys_b,
+                   const uint32_t* src_vals, uint32_t* vals_a, uint32_t* vals_b, uint64_t n,
+                   int begin_bit, int end_bit, bool descending = false);
+int RadixSortKeys(Ctx& c, const uint32_t* src_keys, uint32_t* keys_a, uint32_t* keys_b,
+                  uint64_t n, int begin_bit, int end_bit);
 // run-length histogram of the index keys (c.i_hist: 65536 u64 bins + #keys), filled by the build
 uint64_t* IndexHistogram(Ctx& c);
 uint32_t ThresholdFromHistogram(Ctx& c, const uint64_t* h_hist, uint64_t n_keys,
@@ -262,6 +284,12 @@ void ArenaImport(Ctx& c, uint32_t parts, uint32_t rank, const void* handles);
 void ArenaPut(Ctx& c, uint32_t dest, uint64_t dst_off, const void* d_src, uint64_t bytes);
 void ArenaFlush(Ctx& c);
 void ArenaRelease(Ctx& c);
+
+// ---- editdist.cu ---- batched global edit distance of read substrings
+void EditDistanceBatch(Ctx& c, uint64_t n, const uint32_t* lhs_read, const uint32_t* lhs_begin,
+                       const uint32_t* lhs_len, const uint32_t* rhs_read,
+                       const uint32_t* rhs_begin, const uint32_t* rhs_len,
+                       const uint8_t* strand, const int32_t* limit, int32_t* out);
 
 // ---- pile.cu ----
 // data: device u16 bins, off: device u64 offsets (n_piles + 1)

@@ -12,7 +12,6 @@
 // read's own query block. A stable radix sort of overlap indices by rhs_id
 // gives the first part, the block offset the second. The truncation replays
 // libstdc++'s std::sort (introsort.cuh), one thread per read.
-#include <cub/device/device_radix_sort.cuh>
 
 #include "engine.cuh"
 #include "introsort.cuh"
@@ -194,14 +193,9 @@ void GatherFlush(Ctx& c, const rvn_overlap* ovl, const uint64_t* q_ovl_off,
   ++c.launches;
   int bits = 1;
   while ((1ULL << bits) < n) ++bits;
-  cub::DoubleBuffer<uint32_t> dk(key, key2), dv(idx, idx2);
-  size_t tmp_bytes = 0;
-  RVN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, m, 0, bits,
-                                           c.stream));
-  void* tmp = c.sort_tmp.reserve(tmp_bytes + 16);
-  RVN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, m, 0, bits,
-                                           c.stream));
-  const uint32_t* sorted_idx = dv.Current();
+  // stable: records of one rhs read keep their overlap-index order (radix.cu)
+  const int w_rhs = RadixSortPairs(c, key, key2, key, idx, idx2, idx, m, 0, bits);
+  const uint32_t* sorted_idx = w_rhs == 0 ? idx2 : idx;
   ExclusiveScanU32(c, rhs_cnt, rhs_off, n);
 
   // staging list: kept records + new records per read

@@ -6,13 +6,11 @@
 //
 // The reference keeps 2^14 hash buckets, radix-sorts each bucket by value and
 // fills an unordered_map per bucket. On B200 the whole batch is ONE stable
-// radix sort of the (value, origin) records by value — the input is already
+// radix sort (radix.cu) of the (value, origin) records by value — the input is already
 // in (read, position) order, so equal values keep exactly the reference's
 // posting order — plus a direct-address bucket table over the top bits of
 // the (uniformly mixed) value: a probe is one table read and one short scan
 // of a sorted run, no hashing, no pointer chasing.
-#include <cub/device/device_radix_sort.cuh>
-
 #include <algorithm>
 #include <cmath>
 
@@ -27,18 +25,6 @@ constexpr int kThreads = 256;
 constexpr uint32_t kHistBins = 1u << 16;
 constexpr uint32_t kSmemBins = 1024;
 
-__global__ void NarrowKeys(const uint64_t* __restrict__ in, uint64_t n,
-                           uint32_t* __restrict__ out) {
-  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = static_cast<uint32_t>(in[i]);
-}
-
-__global__ void WidenKeys(const uint32_t* __restrict__ in, uint64_t n,
-                          uint64_t* __restrict__ out) {
-  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = in[i];
-}
-
 // One pass over the sorted values:
 //   bucket[b] = index of the first record whose (value >> shift) >= b;
 //   hist[len] += 1 for every run of equal values (a key) of that many postings
@@ -51,8 +37,9 @@ __global__ void WidenKeys(const uint32_t* __restrict__ in, uint64_t n,
 constexpr uint32_t kShortGap = 1024;
 constexpr uint32_t kMaxLongGaps = 1u << 20;
 
+template <typename ValT>
 __global__ void __launch_bounds__(kThreads)
-IndexTableKernel(const uint64_t* __restrict__ val, uint64_t n, int shift,
+IndexTableKernel(const ValT* __restrict__ val, uint64_t n, int shift,
                  uint32_t n_buckets, uint32_t* __restrict__ bucket,
                  unsigned long long* __restrict__ hist, uint64_t* __restrict__ gaps) {
   __shared__ uint32_t sh[kSmemBins];
@@ -184,7 +171,8 @@ FillLongGaps(const uint64_t* __restrict__ gaps, uint32_t* __restrict__ bucket) {
 }
 
 // exact lengths of the runs of kHistBins-1 or more postings (rare)
-__global__ void CollectLongRuns(const uint64_t* __restrict__ val, uint64_t n,
+template <typename ValT>
+__global__ void CollectLongRuns(const ValT* __restrict__ val, uint64_t n,
                                 unsigned long long* __restrict__ counter,
                                 uint32_t* __restrict__ out) {
   const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -201,12 +189,12 @@ void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash) {
   c.i_valid = false;
   c.occurrence = 0xFFFFFFFFu;
   EnsureSketch(c, first, last);
-  const uint64_t* src_val = c.s_val.get();
+  ValView src_val{c.s_val.get(), c.s_is32 ? 1 : 0};
   const uint64_t* src_org = c.s_org.get();
   uint64_t n = c.s_n;
   if (minhash) {
     EnsureMicromizers(c, first, last);
-    src_val = c.q_val.get();
+    src_val = ValView{c.q_val.get(), 0};
     src_org = c.q_org.get();
     n = c.q_n;
   }
@@ -218,7 +206,7 @@ void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash) {
   c.i_sorted_ids = c.ids_ascending;
 }
 
-void BuildIndexFrom(Ctx& c, const uint64_t* src_val, const uint64_t* src_org, uint64_t n,
+void BuildIndexFrom(Ctx& c, ValView src_val, const uint64_t* src_org, uint64_t n,
                     uint64_t index_bases) {
   c.i_valid = false;
   c.i_sorted_ids = false;
@@ -228,39 +216,39 @@ void BuildIndexFrom(Ctx& c, const uint64_t* src_val, const uint64_t* src_org, ui
   }
   c.i_n = n;
   c.i_keys = 0;
+  const bool is32 = src_val.is32 != 0;
+  c.i_is32 = is32;
 
   TimerBegin(c, "index_sort");
-  uint64_t* kv = c.i_val.reserve(n + 1);
-  uint64_t* ko = c.i_org.reserve(n + 1);
+  // stable LSD radix sort on the 2k value bits (radix.cu). The sketch arrays are
+  // only read (they still serve the queries of this batch); values of up to 30
+  // bits (k <= 15) are u32 keys straight from the sketch kernel: 12 instead of
+  // 16 bytes per record and pass, three 10-bit passes at k = 15.
+  const int key_bits = static_cast<int>(2 * c.prm.k);
+  const uint64_t val_elems = is32 ? n / 2 + 2 : n + 1;
+  c.i_val.reserve(val_elems);
+  c.i_val_alt.reserve(val_elems);
+  c.i_org.reserve(n + 1);
+  c.i_org_alt.reserve(n + 1);
   if (n > 0) {
-    // stable LSD radix sort on the 2k value bits. The out-of-place API leaves the
-    // sketch arrays untouched (they still serve the queries of this batch) - no
-    // staging copies. Values of up to 32 bits (k <= 16) travel as u32 keys:
-    // 12 instead of 16 bytes per record and pass.
-    const int key_bits = static_cast<int>(2 * c.prm.k);
-    size_t tmp_bytes = 0;
-    if (key_bits <= 32) {
-      uint32_t* k32_in = reinterpret_cast<uint32_t*>(c.i_val_alt.reserve(n / 2 + 2));
-      uint32_t* k32_out = reinterpret_cast<uint32_t*>(c.i_org_alt.reserve(n / 2 + 2));
-      NarrowKeys<<<CeilDiv(n, kThreads), kThreads, 0, c.stream>>>(src_val, n, k32_in);
-      RVN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k32_in, k32_out, src_org, ko,
-                                               n, 0, key_bits, c.stream));
-      void* tmp = c.sort_tmp.reserve(tmp_bytes + 16);
-      RVN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k32_in, k32_out, src_org, ko, n,
-                                               0, key_bits, c.stream));
-      WidenKeys<<<CeilDiv(n, kThreads), kThreads, 0, c.stream>>>(k32_out, n, kv);
-      RVN_LAUNCH_CHECK();
-      c.launches += 2;
+    int where;
+    if (is32) {
+      where = RadixSortPairs(c, static_cast<const uint32_t*>(src_val.p),
+                             reinterpret_cast<uint32_t*>(c.i_val.get()),
+                             reinterpret_cast<uint32_t*>(c.i_val_alt.get()), src_org,
+                             c.i_org.get(), c.i_org_alt.get(), n, 0, key_bits);
     } else {
-      RVN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, src_val, kv, src_org, ko, n,
-                                               0, key_bits, c.stream));
-      void* tmp = c.sort_tmp.reserve(tmp_bytes + 16);
-      RVN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, src_val, kv, src_org, ko, n, 0,
-                                               key_bits, c.stream));
+      where = RadixSortPairs(c, static_cast<const uint64_t*>(src_val.p), c.i_val.get(),
+                             c.i_val_alt.get(), src_org, c.i_org.get(), c.i_org_alt.get(), n, 0,
+                             key_bits);
     }
-    c.launches += (key_bits + 7) / 8 + 2;
+    if (where == 1) {
+      c.i_val.swap(c.i_val_alt);
+      c.i_org.swap(c.i_org_alt);
+    }
   }
   TimerEnd(c);
+  const uint64_t* kv = c.i_val.get();
 
   TimerBegin(c, "index_table");
   // bucket table over the top bits of the value + run-length histogram + #keys
@@ -275,8 +263,15 @@ void BuildIndexFrom(Ctx& c, const uint64_t* src_val, const uint64_t* src_org, ui
   uint64_t* hist = c.i_hist.reserve(kHistBins + 8);
   RVN_CUDA(cudaMemsetAsync(hist, 0, (kHistBins + 8) * sizeof(uint64_t), c.stream));
   uint64_t* gaps = c.i_gaps.reserve(3ULL * kMaxLongGaps);
-  IndexTableKernel<<<std::min<unsigned>(CeilDiv(n + 1, kThreads), 148 * 8), kThreads, 0, c.stream>>>(
-      kv, n, shift, n_buckets, bucket, reinterpret_cast<unsigned long long*>(hist), gaps);
+  const unsigned grid = std::min<unsigned>(CeilDiv(n + 1, kThreads), 148 * 8);
+  if (is32) {
+    IndexTableKernel<uint32_t><<<grid, kThreads, 0, c.stream>>>(
+        reinterpret_cast<const uint32_t*>(kv), n, shift, n_buckets, bucket,
+        reinterpret_cast<unsigned long long*>(hist), gaps);
+  } else {
+    IndexTableKernel<uint64_t><<<grid, kThreads, 0, c.stream>>>(
+        kv, n, shift, n_buckets, bucket, reinterpret_cast<unsigned long long*>(hist), gaps);
+  }
   RVN_LAUNCH_CHECK();
   ++c.launches;
   uint64_t* hk = c.pin64.reserve(8);
@@ -330,9 +325,7 @@ uint32_t FilterIndex(Ctx& c, double frequency) {
     c.occurrence = 0xFFFFFFFFu;
     return c.occurrence;
   }
-  TimerBegin(c, "filter");
-  uint64_t* hist = IndexHistogram(c);
-  TimerEnd(c);
+  uint64_t* hist = IndexHistogram(c);  // (filled by the index table pass)
   std::vector<uint64_t> h(kHistBins);
   RVN_CUDA(cudaMemcpyAsync(h.data(), hist, kHistBins * sizeof(uint64_t),
                            cudaMemcpyDeviceToHost, c.stream));
@@ -348,8 +341,14 @@ uint32_t FilterIndex(Ctx& c, double frequency) {
     uint32_t* out = c.m_cnt.reserve(n_long + 1);
     uint64_t* counter = c.m_counter.reserve(8);
     RVN_CUDA(cudaMemsetAsync(counter, 0, sizeof(uint64_t), c.stream));
-    CollectLongRuns<<<CeilDiv(c.i_n, kThreads), kThreads, 0, c.stream>>>(
-        c.i_val.get(), c.i_n, reinterpret_cast<unsigned long long*>(counter), out);
+    if (c.i_is32) {
+      CollectLongRuns<uint32_t><<<CeilDiv(c.i_n, kThreads), kThreads, 0, c.stream>>>(
+          reinterpret_cast<const uint32_t*>(c.i_val.get()), c.i_n,
+          reinterpret_cast<unsigned long long*>(counter), out);
+    } else {
+      CollectLongRuns<uint64_t><<<CeilDiv(c.i_n, kThreads), kThreads, 0, c.stream>>>(
+          c.i_val.get(), c.i_n, reinterpret_cast<unsigned long long*>(counter), out);
+    }
     RVN_LAUNCH_CHECK();
     ++c.launches;
     std::vector<uint32_t> lens(n_long);

@@ -21,8 +21,6 @@
 // The chain result is a pure function of the MULTISET of hits of a query
 // (both reference sorts are total orders here: equal (group, positions)
 // pairs cannot occur), so hit generation order is free.
-#include <cub/device/device_radix_sort.cuh>
-
 #include <algorithm>
 
 #include "engine.cuh"
@@ -34,7 +32,7 @@ namespace {
 constexpr int kThreads = 256;
 
 struct IndexView {
-  const uint64_t* val;
+  ValView val;  // sorted values, u32 or u64
   const uint64_t* org;
   const uint32_t* bucket;
   uint64_t n;
@@ -1277,13 +1275,11 @@ uint64_t ChainGroupedHits(Ctx& c, const uint64_t* hg, const uint64_t* hp,
 
       if (n_groups) {
         // largest pairs first: lanes of a warp get pairs of similar size
-        cub::DoubleBuffer<uint32_t> kk(dcnt, dcnt2), vv(didx, didx2);
-        size_t tmp_bytes = 0;
-        RVN_CUDA(cub::DeviceRadixSort::SortPairsDescending(
-            nullptr, tmp_bytes, kk, vv, n_groups, 0, 12, c.stream));
-        void* tmp = c.sort_tmp.reserve(tmp_bytes + 16);
-        RVN_CUDA(cub::DeviceRadixSort::SortPairsDescending(
-            tmp, tmp_bytes, kk, vv, n_groups, 0, 12, c.stream));
+        // (stable descending radix sort on the 12 count bits, radix.cu)
+        const int w_desc = RadixSortPairs(c, dcnt, dcnt2, dcnt, didx, didx2, didx, n_groups, 0, 12,
+                                          /*descending=*/true);
+        const uint32_t* sorted_cnt = w_desc == 0 ? dcnt2 : dcnt;
+        const uint32_t* sorted_idx = w_desc == 0 ? didx2 : didx;
         rvn_overlap* tmp_ovl = c.m_ovl_tmp.reserve(ovl_cap);
         uint64_t* key = c.m_okey.reserve(ovl_cap);
         uint64_t* key2 = c.m_okey2.reserve(ovl_cap);
@@ -1297,8 +1293,7 @@ uint64_t ChainGroupedHits(Ctx& c, const uint64_t* hg, const uint64_t* hp,
         uint64_t* d_starts = c.m_starts.reserve(kNB + 1);
         RVN_CUDA(cudaMemcpyAsync(d_bounds, kGB, sizeof(kGB), cudaMemcpyHostToDevice,
                                  c.stream));
-        SizeClassStarts<<<1, 32, 0, c.stream>>>(kk.Current(), n_groups, d_bounds, kNB,
-                                                d_starts);
+        SizeClassStarts<<<1, 32, 0, c.stream>>>(sorted_cnt, n_groups, d_bounds, kNB, d_starts);
         uint64_t h_starts[kNB + 1];
         RVN_CUDA(cudaMemcpyAsync(h_starts, d_starts, kNB * sizeof(uint64_t),
                                  cudaMemcpyDeviceToHost, c.stream));
@@ -1315,8 +1310,8 @@ uint64_t ChainGroupedHits(Ctx& c, const uint64_t* hg, const uint64_t* hp,
           while (threads > 8 && 12ULL * kGB[b] * threads > 196 * 1024) threads >>= 1;
           const size_t smem = 12ULL * kGB[b] * threads;
           GroupChainKernel<<<CeilDiv(hi - lo, threads), threads, smem, c.stream>>>(
-              desc, vv.Current(), lo, hi, kGB[b], g_diag, g_pos, cp, tmp_ovl, key,
-              ctr + 3, ovl_cap);
+              desc, sorted_idx, lo, hi, kGB[b], g_diag, g_pos, cp, tmp_ovl, key, ctr + 3,
+              ovl_cap);
           RVN_LAUNCH_CHECK();
           ++c.launches;
         }
@@ -1329,17 +1324,14 @@ uint64_t ChainGroupedHits(Ctx& c, const uint64_t* hg, const uint64_t* hp,
               oidx, n_fast_ovl);
           int key_bits = 17;
           while (key_bits < 64 && (1ULL << (key_bits - 16)) < n_groups) ++key_bits;
-          cub::DoubleBuffer<uint64_t> ok(key, key2);
-          cub::DoubleBuffer<uint32_t> ov(oidx, oidx2);
-          RVN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ok, ov,
-                                                   n_fast_ovl, 0, key_bits, c.stream));
-          tmp = c.sort_tmp.reserve(tmp_bytes + 16);
-          RVN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, ok, ov, n_fast_ovl,
-                                                   0, key_bits, c.stream));
+          const int w_ovl = RadixSortPairs(c, key, key2, key, oidx, oidx2, oidx, n_fast_ovl, 0,
+                                           key_bits);
+          const uint64_t* sorted_key = w_ovl == 0 ? key2 : key;
+          const uint32_t* sorted_oidx = w_ovl == 0 ? oidx2 : oidx;
           GatherOverlapsByIndex<<<CeilDiv(n_fast_ovl * 2, kThreads), kThreads, 0,
-                                  c.stream>>>(tmp_ovl, ov.Current(), n_fast_ovl, raw);
+                                  c.stream>>>(tmp_ovl, sorted_oidx, n_fast_ovl, raw);
           LocateReadOverlaps<<<CeilDiv(total, kThreads), kThreads, 0, c.stream>>>(
-              ok.Current(), n_fast_ovl, d_list, static_cast<uint32_t>(total),
+              sorted_key, n_fast_ovl, d_list, static_cast<uint32_t>(total),
               group_loc, 0, loc);
           RVN_LAUNCH_CHECK();
           c.launches += 3;
@@ -1441,7 +1433,7 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
   const uint64_t q_begin = (*h_read_off)[off_base_read];
   const uint64_t n_q = (*h_read_off)[off_base_read + nr] - q_begin;
 
-  IndexView ix{c.i_val.get(), c.i_org.get(), c.i_bucket.get(), c.i_n,
+  IndexView ix{ValView{c.i_val.get(), c.i_is32 ? 1 : 0}, c.i_org.get(), c.i_bucket.get(), c.i_n,
                static_cast<int>(2 * c.prm.k) - c.i_bucket_bits, c.occurrence};
 
   // ---- probe + expand ----
@@ -1461,25 +1453,18 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
       uint64_t* k2 = c.m_sq_key2.reserve(n_q);
       uint32_t* v1 = c.m_sq_idx.reserve(n_q);
       uint32_t* v2 = c.m_sq_idx2.reserve(n_q);
-      RVN_CUDA(cudaMemcpyAsync(k1, qv + q_begin, n_q * sizeof(uint64_t),
-                               cudaMemcpyDeviceToDevice, c.stream));
       IotaU32<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(v1, n_q);
-      cub::DoubleBuffer<uint64_t> dk(k1, k2);
-      cub::DoubleBuffer<uint32_t> dv(v1, v2);
-      size_t tmp_bytes = 0;
       // (only locality matters: the top 16 value bits put neighbours within
       //  ~10 k index records of each other, at half the passes of a full sort)
       const int hi_bit = static_cast<int>(2 * c.prm.k);
       const int lo_bit = std::max(0, hi_bit - 16);
-      RVN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, n_q, lo_bit, hi_bit,
-                                               c.stream));
-      void* tmp = c.sort_tmp.reserve(tmp_bytes + 16);
-      RVN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, n_q, lo_bit, hi_bit,
-                                               c.stream));
-      // (the spare key buffer of the sort receives the packed results)
-      uint64_t* packed = dk.Current() == k1 ? k2 : k1;
+      const int w_q = RadixSortPairs(c, qv + q_begin, k1, k2, v1, v2, v1, n_q, lo_bit, hi_bit);
+      const uint64_t* sorted_qv = w_q < 0 ? qv + q_begin : (w_q == 0 ? k1 : k2);
+      const uint32_t* sorted_qi = w_q == 0 ? v2 : v1;
+      // (the key buffer the sort did not end in receives the packed results)
+      uint64_t* packed = w_q == 0 ? k2 : k1;
       ProbeSortedKernel<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
-          ix, dk.Current(), dv.Current(), qo, q_begin, n_q, avoid_equal, packed);
+          ix, sorted_qv, sorted_qi, qo, q_begin, n_q, avoid_equal, packed);
       UnpackProbe<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(packed, n_q, cnt, frst, filt);
       c.launches += (2 * c.prm.k + 7) / 8 + 5;
     } else if (suffix) {

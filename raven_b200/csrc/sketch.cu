@@ -133,7 +133,7 @@ SketchKernel(const uint64_t* __restrict__ words,
              uint32_t last_read, uint32_t k, uint32_t w,
              unsigned int* __restrict__ ticket, uint64_t* __restrict__ status,
              uint64_t* __restrict__ tile_out, uint64_t n_tiles, uint64_t out_cap,
-             uint64_t* __restrict__ out_val, uint64_t* __restrict__ out_org) {
+             HashT* __restrict__ out_val, uint64_t* __restrict__ out_org) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr HashT kBad = static_cast<HashT>(~static_cast<HashT>(0));
   const uint32_t halo = w - 1;
@@ -304,7 +304,7 @@ SketchKernel(const uint64_t* __restrict__ words,
     flags &= flags - 1;
     const uint32_t q = qa + i;
     if (dst < out_cap) {
-      out_val[dst] = static_cast<uint64_t>(sh_hash[q - hs]);
+      out_val[dst] = sh_hash[q - hs];  // u32 values when 2k <= 30: no narrowing pass later
       out_org[dst] = id | (static_cast<uint64_t>(q) << 1) | sh_strand[q - hs];
     }
     ++dst;
@@ -325,8 +325,9 @@ __global__ void GatherReadOffsets(const uint64_t* __restrict__ tile_off,
 // position, back in position order ("minhash") ----
 constexpr int kMicroThreads = 256;
 
+template <typename ValT>
 __global__ void __launch_bounds__(kMicroThreads)
-MicromizeKernel(const uint64_t* __restrict__ s_val,
+MicromizeKernel(const ValT* __restrict__ s_val,
                 const uint64_t* __restrict__ s_org,
                 const uint64_t* __restrict__ s_off,  // per read of the sketch
                 uint32_t s_first, const uint64_t* __restrict__ q_off,
@@ -341,7 +342,7 @@ MicromizeKernel(const uint64_t* __restrict__ s_val,
   const uint32_t cnt = static_cast<uint32_t>(s_off[r - s_first + 1] - b);
   const uint64_t ob = q_off[blockIdx.x];
   const uint32_t m = static_cast<uint32_t>(q_off[blockIdx.x + 1] - ob);
-  const uint64_t* val = s_val + b;
+  const ValT* val = s_val + b;
   const uint64_t* org = s_org + b;
   if (m == 0) return;
   if (m >= cnt) {  // keep everything
@@ -475,12 +476,13 @@ void EnsureSketch(Ctx& c, uint32_t first, uint32_t last) {
     uint64_t cap = static_cast<uint64_t>(
                        static_cast<double>(positions) *
                        std::min(1.0, 2.2 / (c.prm.w + 1.0))) + 4096;
-    cap = std::max<uint64_t>(cap, std::min<uint64_t>(c.s_val.cap, c.s_org.cap));
+    // (u32 values: two per element of the u64-typed buffer)
+    cap = std::max<uint64_t>(cap, std::min<uint64_t>(c.s_val.cap * (k32 ? 2 : 1), c.s_org.cap));
     uint64_t* tout = c.tile_out.reserve(n_tiles + 1);
     uint64_t* status = c.tile_status.reserve(n_tiles + 2);
     unsigned int* ticket = reinterpret_cast<unsigned int*>(status + n_tiles);
     for (int attempt = 0; attempt < 2; ++attempt) {
-      uint64_t* val = c.s_val.reserve(cap);
+      uint64_t* val = c.s_val.reserve(k32 ? cap / 2 + 1 : cap);
       uint64_t* org = c.s_org.reserve(cap);
       RVN_CUDA(cudaMemsetAsync(status, 0, (n_tiles + 2) * sizeof(uint64_t), c.stream));
       if (k32) {
@@ -488,7 +490,7 @@ void EnsureSketch(Ctx& c, uint32_t first, uint32_t last) {
                                  c.stream>>>(
             c.d_words.get(), c.d_woff.get(), c.d_len.get(), c.d_ids.get(),
             c.d_tile_off.get(), first, last, c.prm.k, c.prm.w, ticket, status, tout,
-            n_tiles, cap, val, org);
+            n_tiles, cap, reinterpret_cast<uint32_t*>(val), org);
       } else {
         SketchKernel<uint64_t><<<static_cast<unsigned>(n_tiles), kSketchThreads, smem,
                                  c.stream>>>(
@@ -518,6 +520,7 @@ void EnsureSketch(Ctx& c, uint32_t first, uint32_t last) {
   c.s_first = first;
   c.s_last = last;
   c.s_n = total;
+  c.s_is32 = 2 * c.prm.k <= 30;
   c.s_valid = true;
 }
 
@@ -544,9 +547,15 @@ void EnsureMicromizers(Ctx& c, uint32_t first, uint32_t last) {
   uint64_t* qo = c.q_org.reserve(total);
   if (nr > 0 && total > 0) {
     TimerBegin(c, "micromize");
-    MicromizeKernel<<<nr, kMicroThreads, 0, c.stream>>>(
-        c.s_val.get(), c.s_org.get(), c.s_off.get(), c.s_first, qoff, first,
-        c.prm.k, qv, qo);
+    if (c.s_is32) {
+      MicromizeKernel<uint32_t><<<nr, kMicroThreads, 0, c.stream>>>(
+          reinterpret_cast<const uint32_t*>(c.s_val.get()), c.s_org.get(), c.s_off.get(),
+          c.s_first, qoff, first, c.prm.k, qv, qo);
+    } else {
+      MicromizeKernel<uint64_t><<<nr, kMicroThreads, 0, c.stream>>>(
+          c.s_val.get(), c.s_org.get(), c.s_off.get(), c.s_first, qoff, first, c.prm.k, qv,
+          qo);
+    }
     RVN_LAUNCH_CHECK();
     ++c.launches;
     TimerEnd(c);

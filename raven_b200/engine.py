@@ -213,6 +213,34 @@ class Engine:
                     ovl_off=ovl_off, pile=_arr(p, int(pile_off[-1]), np.uint16),
                     pile_off=pile_off, num_mapped=nm.value)
 
+    # ---- edlibAlign(..., edlibDefaultAlignConfig()) of the identity filter ----
+    def edit_distance_batch(self, lhs_read, lhs_begin, lhs_len, rhs_read, rhs_begin, rhs_len,
+                            strand, limit=None):
+        """Global edit distances of substring pairs of the uploaded reads
+        (construct.cc:176-199): -1 where the distance exceeds limit[i] >= 0."""
+        a = [np.ascontiguousarray(x, dtype=np.uint32)
+             for x in (lhs_read, lhs_begin, lhs_len, rhs_read, rhs_begin, rhs_len)]
+        st = np.ascontiguousarray(strand, dtype=np.uint8)
+        lim = None if limit is None else np.ascontiguousarray(limit, dtype=np.int32)
+        out = np.zeros(a[0].size, dtype=np.int32)
+        self._check(self.lib.rvn_edit_distance_batch(
+            self.h, a[0].size, *[x.ctypes.data_as(U32P) for x in a],
+            st.ctypes.data_as(C.POINTER(C.c_uint8)),
+            None if lim is None else lim.ctypes.data_as(C.POINTER(C.c_int32)),
+            out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def debug_sort_pairs(self, keys, vals=None, begin_bit=0, end_bit=None, descending=False):
+        """The engine's stable radix sort (csrc/radix.cu) on host arrays; returns copies."""
+        k = np.ascontiguousarray(keys).copy()
+        v = None if vals is None else np.ascontiguousarray(vals).copy()
+        end_bit = 8 * k.itemsize if end_bit is None else end_bit
+        self._check(self.lib.rvn_debug_sort_pairs(
+            self.h, k.itemsize, 0 if v is None else v.itemsize, k.ctypes.data_as(C.c_void_p),
+            None if v is None else v.ctypes.data_as(C.c_void_p), k.size, begin_bit, end_bit,
+            int(descending)))
+        return k, v
+
     # ---- bookkeeping ----
     def set_option(self, name, value):
         self._check(self.lib.rvn_set_option(self.h, name.encode(), int(value)))

@@ -70,6 +70,17 @@ MinimizerEngine::~MinimizerEngine() {
 void MinimizerEngine::UploadRange(
     std::vector<std::unique_ptr<biosoup::NucleicAcid>>::const_iterator first,
     std::vector<std::unique_ptr<biosoup::NucleicAcid>>::const_iterator last) {
+  // the same objects as last time (stage 1 -> identity filter): nothing to move
+  {
+    const std::size_t n = static_cast<std::size_t>(last - first);
+    bool same = n > 0 && n == uploaded_.size();
+    std::uint32_t pos = 0;
+    for (auto it = first; same && it != last; ++it, ++pos) {
+      const auto f = uploaded_.find((*it)->id);
+      same = f != uploaded_.end() && f->second.first == pos && f->second.second == it->get();
+    }
+    if (same) return;
+  }
   // deflated_data is already the device format: concatenate, never repack
   std::vector<std::uint64_t> words, off{0};
   std::vector<std::uint32_t> lens, ids;
@@ -97,6 +108,13 @@ void MinimizerEngine::Upload(
     const std::vector<std::unique_ptr<biosoup::NucleicAcid>>& sequences) {
   std::lock_guard<std::mutex> lock(*mutex_);
   UploadRange(sequences.begin(), sequences.end());
+}
+
+void MinimizerEngine::Upload(
+    std::vector<std::unique_ptr<biosoup::NucleicAcid>>::const_iterator first,
+    std::vector<std::unique_ptr<biosoup::NucleicAcid>>::const_iterator last) {
+  std::lock_guard<std::mutex> lock(*mutex_);
+  UploadRange(first, last);
 }
 
 void MinimizerEngine::Minimize(

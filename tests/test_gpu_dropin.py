@@ -93,3 +93,32 @@ def test_full_pipeline_on_b200_equals_oracle_pipeline(tmp_path, oracle, referenc
     genome = seqio.ReadSet.load(os.path.join(HERE, "golden", "lambda_genome.npz")).ascii(0)
     rc = seqs[0].translate(bytes.maketrans(b"ACGT", b"TGCA"))[::-1]
     assert oracle.edit_distance(rc, genome) == 1137   # EXPECT_EQ(1137, ...) raven_test.cpp:66
+
+
+@pytest.mark.parametrize("identity", [0.0, 0.8, 0.9])
+def test_stage2_and_identity_filter_batched_equals_reference(tmp_path, lambda_reads, identity):
+    """raven::ResolveContainedReads + raven::FindOverlapsAndRepetetiveRegions
+    (construct.cc:154-246, 316-491): the reference's own functions over the facade
+    (per-read Map, host edlibAlign per overlap) vs the batched B200 replacements
+    (one device map per batch, rvn_edit_distance_batch): identical overlap lists
+    and identical piles, field by field."""
+    binary = os.path.join(HERE, "cpp", "_build", "stage2_test")
+    if not os.path.exists(binary):
+        pytest.skip("tests/cpp/_build/stage2_test not built")
+    inp, out = str(tmp_path / "reads.bin"), str(tmp_path / "out.bin")
+    with open(inp, "wb") as f:
+        write_vec(f, lambda_reads.words.astype(np.uint64))
+        write_vec(f, lambda_reads.word_off.astype(np.uint64))
+        write_vec(f, lambda_reads.lens.astype(np.uint32))
+    subprocess.run([binary, inp, out, "15", "5", "0.001", str(identity)], check=True,
+                   stderr=subprocess.DEVNULL, timeout=900)
+    with open(out, "rb") as f:
+        a = [read_vec(f, np.uint32), read_vec(f, np.uint64), read_vec(f, np.uint32),
+             read_vec(f, np.uint32)]
+        b = [read_vec(f, np.uint32), read_vec(f, np.uint64), read_vec(f, np.uint32),
+             read_vec(f, np.uint32)]
+    for x, y, name in zip(a, b, ("overlaps", "offsets", "piles", "sequence order")):
+        assert np.array_equal(x, y), name
+    assert a[0].size > 0                       # something survived the stage
+    if identity > 0.85:                        # and the filter bit on 10 % error reads
+        assert a[0].size < 8 * 50_000
