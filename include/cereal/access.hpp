@@ -1,6 +1,7 @@
-// raven-b200: minimal stand-in for cereal (v1.3.0 in the reference,
-// Raven.deps.cmake:21-26). Only what RavenLib's public headers need to
-// compile: `friend cereal::access` (raven/pile.h:114) and CEREAL_NVP.
+// raven-b200: cereal::access of our own small cereal (cereal/cereal.hpp):
+// the door RavenLib's classes open with `friend cereal::access`
+// (RavenLib/include/raven/pile.h:114) - private serialize() members and private
+// default constructors (unique_ptr loading).
 #ifndef CEREAL_ACCESS_HPP_
 #define CEREAL_ACCESS_HPP_
 namespace cereal {
@@ -9,7 +10,9 @@ class access {
   template <class T>
   static T* construct() { return new T(); }
   template <class Archive, class T>
-  static void member_serialize(Archive& ar, T& t) { t.serialize(ar); }
+  static auto member_serialize(Archive& ar, T& t) -> decltype(t.serialize(ar)) {
+    return t.serialize(ar);
+  }
 };
 }  // namespace cereal
 #endif  // CEREAL_ACCESS_HPP_

@@ -1,5 +1,5 @@
-// raven-b200: stand-in for cereal/types/string.hpp — container support lives in
-// the archive classes of our mini-cereal (cereal/archives/binary.hpp).
+// raven-b200: cereal/types/string.hpp - the container support lives in the
+// archive classes of our own small cereal (cereal/archives/*.hpp).
 #ifndef CEREAL_TYPES_STRING_HPP_
 #define CEREAL_TYPES_STRING_HPP_
 #include "cereal/cereal.hpp"

@@ -1,5 +1,5 @@
-// raven-b200: stand-in for cereal/types/unordered_set.hpp — container support lives in
-// the archive classes of our mini-cereal (cereal/archives/binary.hpp).
+// raven-b200: cereal/types/unordered_set.hpp - the container support lives in the
+// archive classes of our own small cereal (cereal/archives/*.hpp).
 #ifndef CEREAL_TYPES_UNORDERED_SET_HPP_
 #define CEREAL_TYPES_UNORDERED_SET_HPP_
 #include "cereal/cereal.hpp"

@@ -88,7 +88,8 @@ inline void FindOverlapsAndCreatePiles(
                        o[e].rhs_begin, o[e].rhs_end, o[e].score, o[e].strand != 0);
     }
     detail::PileDoor door{pile + poff[i], static_cast<std::size_t>(poff[i + 1] - poff[i])};
-    cereal::access::member_serialize(door, *piles[i]);
+    auto visit = cereal::fields(door);
+    cereal::access::member_serialize(visit, *piles[i]);
   }
   std::cerr << "[raven::Graph::Construct] minimized + mapped sequences (B200) "
             << std::fixed << timer.Stop() << "s" << std::endl;

@@ -85,7 +85,8 @@ ORC_EXPORT orc_bag* ref_stage1(orc_reads* r, std::uint32_t k, std::uint32_t w,
     }
     ovl_off.emplace_back(ovl.size() / 8);
     PileProbe probe;
-    cereal::access::member_serialize(probe, *piles[i]);
+    auto visit = cereal::fields(probe);
+    cereal::access::member_serialize(visit, *piles[i]);
     pile.insert(pile.end(), probe.data.begin(), probe.data.end());
     pile_off.emplace_back(pile.size());
   }
@@ -114,7 +115,8 @@ ORC_EXPORT orc_bag* ref_pile_add_layers(std::uint32_t id, std::uint32_t len,
     p.AddLayers(v.begin(), v.end());
   }
   PileProbe probe;
-  cereal::access::member_serialize(probe, p);
+  auto visit = cereal::fields(probe);
+  cereal::access::member_serialize(visit, p);
   auto* bag = new orc_bag();
   bag->Put("pile", probe.data);
   return bag;
@@ -130,7 +132,8 @@ ORC_EXPORT void ref_kmer_complexity(orc_reads* r, const std::uint32_t* read_inde
     raven::Pile p(seq->id, seq->inflated_len);
     p.AddKmers(std::vector<std::uint32_t>{pos[t]}, k, seq);
     KmerProbe probe;
-    cereal::access::member_serialize(probe, p);
+    auto visit = cereal::fields(probe);
+    cereal::access::member_serialize(visit, p);
     keep[t] = probe.any;
   }
 }

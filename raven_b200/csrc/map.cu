@@ -83,7 +83,7 @@ __device__ __forceinline__ bool KeepPosting(uint32_t lhs_id, uint64_t origin,
 }
 
 __global__ void __launch_bounds__(kThreads)
-ProbeKernel(IndexView ix, const uint64_t* __restrict__ q_val,
+ProbeKernel(IndexView ix, ValView q_val,
             const uint64_t* __restrict__ q_org, uint64_t q_begin, uint64_t n_q,
             bool avoid_equal, bool avoid_symmetric,
             uint32_t* __restrict__ cnt, uint32_t* __restrict__ first,
@@ -111,7 +111,7 @@ ProbeKernel(IndexView ix, const uint64_t* __restrict__ q_val,
 }
 
 __global__ void __launch_bounds__(kThreads)
-ExpandKernel(IndexView ix, const uint64_t* __restrict__ q_val,
+ExpandKernel(IndexView ix, ValView q_val,
              const uint64_t* __restrict__ q_org, uint64_t q_begin, uint64_t n_q,
              bool avoid_equal, bool avoid_symmetric,
              const uint32_t* __restrict__ cnt,
@@ -151,7 +151,7 @@ ExpandKernel(IndexView ix, const uint64_t* __restrict__ q_val,
 // warps with fully coalesced stores: hit t of a warp's 32 queries is located
 // by a shuffle search over the 32 exclusive prefixes.
 __global__ void __launch_bounds__(kThreads)
-ProbeSuffixKernel(IndexView ix, const uint64_t* __restrict__ q_val,
+ProbeSuffixKernel(IndexView ix, ValView q_val,
                   const uint64_t* __restrict__ q_org, uint64_t q_begin, uint64_t n_q,
                   bool strict_above, uint32_t* __restrict__ cnt,
                   uint32_t* __restrict__ first, uint8_t* __restrict__ filt) {
@@ -185,7 +185,7 @@ ProbeSuffixKernel(IndexView ix, const uint64_t* __restrict__ q_val,
 // neighbouring parts of the bucket table and of the postings (coalesced,
 // TLB-friendly) instead of 67 M independent random probes into 12 GB
 __global__ void __launch_bounds__(kThreads)
-ProbeSortedKernel(IndexView ix, const uint64_t* __restrict__ sorted_val,
+ProbeSortedKernel(IndexView ix, ValView sorted_val,
                   const uint32_t* __restrict__ sorted_idx,
                   const uint64_t* __restrict__ q_org, uint64_t q_begin, uint64_t n_q,
                   bool strict_above, uint64_t* __restrict__ packed) {
@@ -1408,14 +1408,15 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
   const uint32_t nr = last - first;
 
   // ---- query records ----
-  const uint64_t *qv, *qo, *d_read_off;
+  const uint64_t *qo, *d_read_off;
+  ValView qv;  // query values: u32 for full sketches of k <= 15, else u64
   const std::vector<uint64_t>* h_read_off;
   uint64_t off_base_read;  // index of `first` inside the offsets arrays
   if (minhash) {
     if (!(c.q_valid && c.q_first <= first && last <= c.q_last)) {
       EnsureMicromizers(c, first, last);
     }
-    qv = c.q_val.get();
+    qv = ValView{c.q_val.get(), 0};
     qo = c.q_org.get();
     d_read_off = c.q_off.get();
     h_read_off = &c.h_q_off;
@@ -1424,7 +1425,7 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
     if (!(c.s_valid && c.s_first <= first && last <= c.s_last)) {
       EnsureSketch(c, first, last);
     }
-    qv = c.s_val.get();
+    qv = ValView{c.s_val.get(), c.s_is32 ? 1 : 0};
     qo = c.s_org.get();
     d_read_off = c.s_off.get();
     h_read_off = &c.h_s_off;
@@ -1449,20 +1450,31 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
   if (n_q > 0) {
     if (suffix && n_q >= (1u << 16) && n_q < 0xFFFFFFFFULL) {
       // sort the queries by value, probe in that order, results back by index
-      uint64_t* k1 = c.m_sq_key.reserve(n_q);
+      uint64_t* k1 = c.m_sq_key.reserve(n_q + 2);
       uint64_t* k2 = c.m_sq_key2.reserve(n_q);
       uint32_t* v1 = c.m_sq_idx.reserve(n_q);
       uint32_t* v2 = c.m_sq_idx2.reserve(n_q);
       IotaU32<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(v1, n_q);
-      // (only locality matters: the top 16 value bits put neighbours within
-      //  ~10 k index records of each other, at half the passes of a full sort)
+      // FULL value order: consecutive probes then walk consecutive buckets, values
+      // and postings (the reads of a warp fall into a few hundred bytes instead of
+      // one 32-byte sector per probe per array)
       const int hi_bit = static_cast<int>(2 * c.prm.k);
-      const int lo_bit = std::max(0, hi_bit - 16);
-      const int w_q = RadixSortPairs(c, qv + q_begin, k1, k2, v1, v2, v1, n_q, lo_bit, hi_bit);
-      const uint64_t* sorted_qv = w_q < 0 ? qv + q_begin : (w_q == 0 ? k1 : k2);
+      int w_q;
+      ValView sorted_qv;
+      if (qv.is32) {
+        const uint32_t* src = static_cast<const uint32_t*>(qv.p) + q_begin;
+        uint32_t* a32 = reinterpret_cast<uint32_t*>(k1);
+        uint32_t* b32 = a32 + n_q + (n_q & 1);  // second half of k1 (8-byte aligned)
+        w_q = RadixSortPairs(c, src, a32, b32, v1, v2, v1, n_q, 0, hi_bit);
+        sorted_qv = ValView{w_q < 0 ? src : (w_q == 0 ? a32 : b32), 1};
+      } else {
+        const uint64_t* src = static_cast<const uint64_t*>(qv.p) + q_begin;
+        w_q = RadixSortPairs(c, src, k1, k2, v1, v2, v1, n_q, 0, hi_bit);
+        sorted_qv = ValView{w_q < 0 ? src : (w_q == 0 ? k1 : k2), 0};
+      }
       const uint32_t* sorted_qi = w_q == 0 ? v2 : v1;
-      // (the key buffer the sort did not end in receives the packed results)
-      uint64_t* packed = w_q == 0 ? k2 : k1;
+      // (a key buffer the sort did not end in receives the packed results)
+      uint64_t* packed = (qv.is32 || w_q == 0) ? k2 : k1;
       ProbeSortedKernel<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
           ix, sorted_qv, sorted_qi, qo, q_begin, n_q, avoid_equal, packed);
       UnpackProbe<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(packed, n_q, cnt, frst, filt);

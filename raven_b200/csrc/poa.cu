@@ -800,22 +800,24 @@ void PoaBatch(Ctx& c, uint32_t n_windows, const uint32_t* h_win_first,
 
   // output slots: a consensus never has more bases than the window holds
   c.po_cons_off.assign(n_windows + 1ULL, 0);
-  uint32_t lmax = 1, bb_max = 1;
-  uint64_t total_max = 1;
+  // per window: longest layer, backbone length, all bases - the kernel is chosen
+  // PER WINDOW (one long layer must not send a whole batch to the generic kernel)
+  std::vector<uint32_t> w_lmax(n_windows, 1), w_bb(n_windows, 1);
+  std::vector<uint64_t> w_tot(n_windows, 1);
   for (uint32_t w = 0; w < n_windows; ++w) {
     const uint32_t s0 = h_win_first[w], s1 = h_win_first[w + 1];
     uint64_t tot = 0;
     for (uint32_t s = s0; s < s1; ++s) {
       const uint64_t len = h_seq_off[s + 1] - h_seq_off[s];
       tot += len;
-      if (s > s0) lmax = std::max<uint32_t>(lmax, static_cast<uint32_t>(len));
-      else bb_max = std::max<uint32_t>(bb_max, static_cast<uint32_t>(len));
+      if (s > s0) w_lmax[w] = std::max<uint32_t>(w_lmax[w], static_cast<uint32_t>(len));
+      else w_bb[w] = std::max<uint32_t>(w_bb[w], static_cast<uint32_t>(len));
     }
-    total_max = std::max(total_max, tot);
+    w_tot[w] = std::max<uint64_t>(tot, 1);
+    if (tot > 65000 || w_lmax[w] > 32000) {
+      throw LimitError("a POA window holds more than 65000 bases");
+    }
     c.po_cons_off[w + 1] = c.po_cons_off[w] + tot;
-  }
-  if (total_max > 65000 || lmax > 32000) {
-    throw LimitError("a POA window holds more than 65000 bases");
   }
   const uint64_t out_total = c.po_cons_off[n_windows];
   uint64_t* d_coff = c.po_d_cons_off.reserve(n_windows + 2ULL);
@@ -826,58 +828,71 @@ void PoaBatch(Ctx& c, uint32_t n_windows, const uint32_t* h_win_first,
   uint8_t* d_status = c.po_status.reserve(n_windows + 2ULL);
   uint64_t* d_cells = c.m_counter.reserve((1u << 16) + 8);
   RVN_CUDA(cudaMemsetAsync(d_cells, 0, 8, c.stream));
+  RVN_CUDA(cudaMemsetAsync(d_status, 0, n_windows + 1ULL, c.stream));
 
   c.po_h_status.assign(n_windows, 0);
-  std::vector<uint32_t> todo(n_windows);
-  for (uint32_t w = 0; w < n_windows; ++w) todo[w] = w;
   TimerBegin(c, "poa");
-  for (int tier = 0; tier < 2 && !todo.empty(); ++tier) {
-    PoaShape shape;
-    shape.lmax = lmax;
-    shape.ncap = tier == 0 ? std::min<uint64_t>(total_max, 3ULL * bb_max + lmax + 64)
-                           : static_cast<uint32_t>(total_max);
-    shape.ncap = std::min<uint32_t>(shape.ncap, 65000);
-    shape.ecap = std::min<uint32_t>(3 * shape.ncap, 65000);
-    shape.rows = shape.ncap + 1;
-    shape.width = (lmax + 1 + 31) & ~31u;
-    const bool fast = lmax + 1 <= kFastCols;  // the register-row kernel
-    const size_t stride = ((fast ? MakeFastLayout(shape).bytes : MakePoaLayout(shape).bytes) +
-                           255) & ~size_t(255);
-    const size_t fast_smem = ((shape.ncap + 15) & ~15u) + 4ULL * shape.ncap + 16;
-    if (fast) {
-      RVN_CUDA(cudaFuncSetAttribute(PoaKernelFast,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(std::min<size_t>(fast_smem, 220 * 1024))));
+  // group 0: every layer fits the register-row kernel; group 1: the generic kernel
+  for (int group = 0; group < 2; ++group) {
+    std::vector<uint32_t> todo;
+    for (uint32_t w = 0; w < n_windows; ++w) {
+      if ((w_lmax[w] + 1 <= kFastCols) == (group == 0)) todo.push_back(w);
     }
-    const size_t budget = 48ULL << 30;  // scratch budget per batch
-    const uint32_t batch = static_cast<uint32_t>(
-        std::max<size_t>(1, std::min<size_t>(todo.size(), budget / stride)));
-    uint8_t* scratch = c.po_scratch.reserve(stride * batch);
-    uint32_t* d_list = c.po_list.reserve(todo.size() + 1);
-    RVN_CUDA(cudaMemcpyAsync(d_list, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, c.stream));
-    for (size_t b0 = 0; b0 < todo.size(); b0 += batch) {
-      const uint32_t nb = static_cast<uint32_t>(std::min<size_t>(batch, todo.size() - b0));
-      if (fast && fast_smem <= 220 * 1024) {
-        PoaKernelFast<<<nb, 32, fast_smem, c.stream>>>(
-            nb, d_list + b0, d_wf, d_so, d_bases, d_quals, d_sb, d_se, m, n, gap, trim,
-            tgs, shape, scratch, stride, d_cons, d_coff, d_clen, d_cov, d_status,
-            reinterpret_cast<unsigned long long*>(d_cells));
-      } else {
-        PoaKernel<<<nb, 32, 0, c.stream>>>(
-            nb, d_list + b0, d_wf, d_so, d_bases, d_quals, d_sb, d_se, m, n, gap, trim,
-            tgs, shape, scratch, stride, d_cons, d_coff, d_clen, d_cov, d_status,
-            reinterpret_cast<unsigned long long*>(d_cells));
+    for (int tier = 0; tier < 2 && !todo.empty(); ++tier) {
+      uint32_t lmax = 1, bb_max = 1;
+      uint64_t total_max = 1;
+      for (uint32_t w : todo) {
+        lmax = std::max(lmax, w_lmax[w]);
+        bb_max = std::max(bb_max, w_bb[w]);
+        total_max = std::max(total_max, w_tot[w]);
       }
-      RVN_LAUNCH_CHECK();
-      ++c.launches;
+      PoaShape shape;
+      shape.lmax = lmax;
+      shape.ncap = tier == 0 ? std::min<uint64_t>(total_max, 3ULL * bb_max + lmax + 64)
+                             : static_cast<uint32_t>(total_max);
+      shape.ncap = std::min<uint32_t>(shape.ncap, 65000);
+      shape.ecap = std::min<uint32_t>(3 * shape.ncap, 65000);
+      shape.rows = shape.ncap + 1;
+      shape.width = (lmax + 1 + 31) & ~31u;
+      const size_t fast_smem = ((shape.ncap + 15) & ~15u) + 4ULL * shape.ncap + 16;
+      const bool fast = group == 0 && fast_smem <= 220 * 1024;  // the register-row kernel
+      const size_t stride = ((fast ? MakeFastLayout(shape).bytes : MakePoaLayout(shape).bytes) +
+                             255) & ~size_t(255);
+      if (fast) {
+        RVN_CUDA(cudaFuncSetAttribute(PoaKernelFast,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(fast_smem)));
+      }
+      const size_t budget = 48ULL << 30;  // scratch budget per batch
+      const uint32_t batch = static_cast<uint32_t>(
+          std::max<size_t>(1, std::min<size_t>(todo.size(), budget / stride)));
+      uint8_t* scratch = c.po_scratch.reserve(stride * batch);
+      uint32_t* d_list = c.po_list.reserve(n_windows + 1ULL);
+      RVN_CUDA(cudaMemcpyAsync(d_list, todo.data(), todo.size() * 4, cudaMemcpyHostToDevice, c.stream));
+      for (size_t b0 = 0; b0 < todo.size(); b0 += batch) {
+        const uint32_t nb = static_cast<uint32_t>(std::min<size_t>(batch, todo.size() - b0));
+        if (fast) {
+          PoaKernelFast<<<nb, 32, fast_smem, c.stream>>>(
+              nb, d_list + b0, d_wf, d_so, d_bases, d_quals, d_sb, d_se, m, n, gap, trim,
+              tgs, shape, scratch, stride, d_cons, d_coff, d_clen, d_cov, d_status,
+              reinterpret_cast<unsigned long long*>(d_cells));
+        } else {
+          PoaKernel<<<nb, 32, 0, c.stream>>>(
+              nb, d_list + b0, d_wf, d_so, d_bases, d_quals, d_sb, d_se, m, n, gap, trim,
+              tgs, shape, scratch, stride, d_cons, d_coff, d_clen, d_cov, d_status,
+              reinterpret_cast<unsigned long long*>(d_cells));
+        }
+        RVN_LAUNCH_CHECK();
+        ++c.launches;
+      }
+      RVN_CUDA(cudaMemcpyAsync(c.po_h_status.data(), d_status, n_windows, cudaMemcpyDeviceToHost, c.stream));
+      RVN_CUDA(cudaStreamSynchronize(c.stream));  // (also: todo / d_list are reusable)
+      std::vector<uint32_t> again;
+      for (uint32_t w : todo) {
+        if (c.po_h_status[w] == kPoaStatusCapacity) again.push_back(w);
+      }
+      todo.swap(again);
     }
-    RVN_CUDA(cudaMemcpyAsync(c.po_h_status.data(), d_status, n_windows, cudaMemcpyDeviceToHost, c.stream));
-    RVN_CUDA(cudaStreamSynchronize(c.stream));
-    std::vector<uint32_t> again;
-    for (uint32_t w : todo) {
-      if (c.po_h_status[w] == kPoaStatusCapacity) again.push_back(w);
-    }
-    todo.swap(again);
   }
   TimerEnd(c);
   for (uint32_t w = 0; w < n_windows; ++w) {

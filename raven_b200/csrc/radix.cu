@@ -199,35 +199,62 @@ OnesweepPass(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
   }
 
   // ---- chain the tile's bin counts to the tiles before it (decoupled look-back) ----
+  // A thread owns 4 neighbouring bins = ONE 16-byte status word per tile: all four
+  // aggregates are published in one store before any waiting, and one 16-byte load
+  // per step walks the four chains back together (a per-bin walk would put up to
+  // #resident-tiles dependent L2 round trips in series, four times over).
   {
-    volatile uint32_t* st = status;
+    uint4* st4 = reinterpret_cast<uint4*>(status);
+    const uint64_t my4 = static_cast<uint64_t>(tile) * (kBins / 4) + threadIdx.x;
+    uint32_t excl[kBinsPerThread] = {0, 0, 0, 0};
+    static_assert(kBinsPerThread == 4, "one uint4 of status words per thread");
+    if (tile > 0) {
+      uint4 agg;
+      agg.x = kFlagAggregate | cnt[0];
+      agg.y = kFlagAggregate | cnt[1];
+      agg.z = kFlagAggregate | cnt[2];
+      agg.w = kFlagAggregate | cnt[3];
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(st4 + my4),
+                   "r"(agg.x), "r"(agg.y), "r"(agg.z), "r"(agg.w)
+                   : "memory");
+      uint32_t open = 0xF;  // chains still walking
+      int64_t p = static_cast<int64_t>(tile) - 1;
+      while (open) {
+        uint4 v;
+        const uint4* src = st4 + static_cast<uint64_t>(p) * (kBins / 4) + threadIdx.x;
+        do {  // every status word of the tile must have been written
+          asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                       : "l"(src)
+                       : "memory");
+        } while (((v.x & kFlagMask) == 0) || ((v.y & kFlagMask) == 0) ||
+                 ((v.z & kFlagMask) == 0) || ((v.w & kFlagMask) == 0));
+        const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < kBinsPerThread; ++j) {
+          if (open & (1u << j)) {
+            excl[j] += vv[j] & kValueMask;
+            if ((vv[j] & kFlagMask) == kFlagPrefix) open &= ~(1u << j);
+          }
+        }
+        --p;  // (tile 0 publishes prefixes only: every chain ends there at the latest)
+      }
+    }
+    uint4 pre;
+    pre.x = kFlagPrefix | (excl[0] + cnt[0]);
+    pre.y = kFlagPrefix | (excl[1] + cnt[1]);
+    pre.z = kFlagPrefix | (excl[2] + cnt[2]);
+    pre.w = kFlagPrefix | (excl[3] + cnt[3]);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(st4 + my4), "r"(pre.x),
+                 "r"(pre.y), "r"(pre.z), "r"(pre.w)
+                 : "memory");
 #pragma unroll
     for (int j = 0; j < kBinsPerThread; ++j) {
       const uint32_t b = threadIdx.x * kBinsPerThread + j;
-      if (b > dmask) {  // bins beyond this pass's digit range are empty
-        sm.bin_dst[b] = 0;
-        continue;
-      }
-      const uint64_t at = static_cast<uint64_t>(tile) * kBins + b;
-      uint32_t excl = 0;
-      if (tile > 0) {
-        st[at] = kFlagAggregate | cnt[j];
-        int64_t p = static_cast<int64_t>(tile) - 1;
-        while (true) {
-          uint32_t v;
-          do {
-            v = st[static_cast<uint64_t>(p) * kBins + b];
-          } while ((v & kFlagMask) == 0);
-          excl += v & kValueMask;
-          if ((v & kFlagMask) == kFlagPrefix) break;
-          --p;  // (tile 0 always publishes a prefix)
-        }
-      }
-      st[at] = kFlagPrefix | (excl + cnt[j]);
-      const uint32_t base = bin_base[b];
-      sm.bin_dst[b] = base + excl - sm.bin_off[b];
+      const uint32_t base = bin_base[b];  // (bins beyond the digit range: zero counts)
+      sm.bin_dst[b] = base + excl[j] - sm.bin_off[b];
       // the last tile leaves the running end of every bin for the next portion
-      if (tile == gridDim.x - 1) bin_next[b] = base + excl + cnt[j];
+      if (tile == gridDim.x - 1) bin_next[b] = base + excl[j] + cnt[j];
     }
   }
   __syncthreads();

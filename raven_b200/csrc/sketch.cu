@@ -311,6 +311,222 @@ SketchKernel(const uint64_t* __restrict__ words,
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fast path: 2k <= 30 (u32 hashes) and a compile-time window W <= 8.
+// A thread owns 8 CONSECUTIVE k-mer positions: their 2-bit codes come out of one
+// 64-bit funnel of the staged words (8 + k - 1 <= 22 bases), the eight k-mers
+// are shifts of it, canonical strand and hash are branch-free, and the window
+// minima are two sparse tables in registers over the thread's 8 + 2(W-1)
+// neighbouring hashes (shared memory, padded with "no k-mer" outside the read).
+// Position q is a minimizer iff its hash equals the LARGEST of the minima of the
+// valid windows that contain it (every such minimum is <= hash(q)). About a
+// quarter of the instructions of the generic kernel; same tiles, same look-back,
+// same output order.
+// ---------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(kSketchThreads)
+SketchFastKernel(const uint64_t* __restrict__ words, const uint64_t* __restrict__ woff,
+                 const uint32_t* __restrict__ lens, const uint32_t* __restrict__ ids,
+                 const uint64_t* __restrict__ tile_off, uint32_t first_read,
+                 uint32_t last_read, uint32_t k, unsigned int* __restrict__ ticket,
+                 uint64_t* __restrict__ status, uint64_t* __restrict__ tile_out,
+                 uint64_t n_tiles, uint64_t out_cap, uint32_t* __restrict__ out_val,
+                 uint64_t* __restrict__ out_org) {
+  constexpr uint32_t kBad = 0xFFFFFFFFu;
+  constexpr int H = W - 1;
+  constexpr int ITEMS = 8;
+  constexpr int N = ITEMS + 2 * H;  // hashes a thread looks at
+  constexpr int kSlots = kSketchTile + 2 * H;
+  static_assert(kSketchTile == ITEMS * kSketchThreads, "8 positions per thread");
+  static_assert(W >= 2 && W <= 8, "window of 2..8 k-mers");
+  __shared__ uint64_t sh_words[(kSlots + 31 + 31) / 32 + 3];
+  __shared__ __align__(16) uint32_t sh_hash[kSlots + 8];  // slot j = position q0 - H + j
+  __shared__ uint32_t sh_scan[34];
+  __shared__ uint32_t sh_read, sh_tile;
+  __shared__ uint64_t sh_excl;
+
+  if (threadIdx.x < 32) {
+    uint32_t tk = 0;
+    if (threadIdx.x == 0) tk = atomicAdd(ticket, 1u);
+    tk = __shfl_sync(0xFFFFFFFFu, tk, 0);
+    const uint64_t want = tile_off[first_read] + tk;
+    uint32_t lo = first_read, hi = last_read;  // tile_off[lo] <= want < tile_off[hi]
+    while (hi - lo > 1) {
+      const uint32_t step = (hi - lo + 31) / 32;
+      const uint64_t probe = static_cast<uint64_t>(lo) + (threadIdx.x + 1ULL) * step;
+      const bool le = probe < hi && tile_off[probe] <= want;
+      const uint32_t cnt = __popc(__ballot_sync(0xFFFFFFFFu, le));
+      const uint64_t nlo = static_cast<uint64_t>(lo) + static_cast<uint64_t>(cnt) * step;
+      const uint64_t nhi = nlo + step;
+      lo = static_cast<uint32_t>(nlo);
+      if (nhi < hi) hi = static_cast<uint32_t>(nhi);
+    }
+    if (threadIdx.x == 0) {
+      sh_tile = tk;
+      sh_read = lo;
+    }
+  }
+  __syncthreads();
+  const uint32_t tile = sh_tile;
+  const uint32_t r = sh_read;
+  const int32_t L = static_cast<int32_t>(lens[r] - k + 1);  // k-mer positions, >= W
+  const int32_t q0 =
+      static_cast<int32_t>((tile_off[first_read] + tile - tile_off[r]) * kSketchTile);
+  const int32_t q1 = min(q0 + static_cast<int32_t>(kSketchTile), L);
+
+  // ---- stage the packed words of positions [q0 - H, q1 + H) (+ k - 1 bases) ----
+  const uint64_t* rw = words + woff[r];
+  const uint32_t nwords = static_cast<uint32_t>(woff[r + 1] - woff[r]);
+  const int32_t p_lo = max(q0 - H, 0);
+  const uint32_t w_lo = static_cast<uint32_t>(p_lo) >> 5;
+  const uint32_t w_hi = ((static_cast<uint32_t>(min(q1 + H, L)) - 1 + k - 1) >> 5) + 2;
+  for (uint32_t i = w_lo + threadIdx.x; i < w_hi; i += kSketchThreads) {
+    sh_words[i - w_lo] = i < nwords ? __ldg(rw + i) : 0ULL;
+  }
+  __syncthreads();
+
+  const uint32_t mask = (1u << (2 * k)) - 1u;
+  const uint32_t rshift = 32 - 2 * k;
+  // canonical hash of the k-mer whose 2-bit codes start at bit 0 of kb
+  auto hash_of = [&](uint32_t kb, uint32_t* strand) -> uint32_t {
+    kb &= mask;
+    const uint32_t rv = (~kb) & mask;
+    const uint32_t fw = ReverseGroups32(kb) >> rshift;
+    *strand = rv < fw ? 1u : 0u;
+    const uint32_t h = MixHash32(min(fw, rv), mask);
+    return fw == rv ? kBad : h;  // palindromic k-mers never enter a window
+  };
+
+  // ---- own positions: 8 consecutive k-mers out of one 64-bit funnel ----
+  const int32_t qa = q0 + static_cast<int32_t>(threadIdx.x) * ITEMS;
+  uint32_t own[ITEMS];
+  uint32_t strands = 0;
+  {
+    const uint32_t wi = (static_cast<uint32_t>(qa) >> 5) - w_lo;
+    const uint32_t sh = (static_cast<uint32_t>(qa) & 31) << 1;
+    uint64_t lo = 0;
+    if (qa < q1) {
+      lo = sh_words[wi] >> sh;
+      if (sh) lo |= sh_words[wi + 1] << (64 - sh);
+    }
+    const uint32_t lo_lo = static_cast<uint32_t>(lo), lo_hi = static_cast<uint32_t>(lo >> 32);
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      uint32_t st;
+      const uint32_t h = hash_of(__funnelshift_r(lo_lo, lo_hi, 2 * i), &st);
+      own[i] = qa + i < q1 ? h : kBad;
+      strands |= st << i;
+    }
+  }
+  {  // 16-byte stores: slot of position qa is H + 8 * thread
+    uint32_t* dst = sh_hash + H + threadIdx.x * ITEMS;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) dst[i] = own[i];
+  }
+  // ---- halo positions of the tile: H on each side, one thread each ----
+  if (threadIdx.x < 2 * H) {
+    const bool left = threadIdx.x < H;
+    const int32_t p = left ? q0 - H + static_cast<int32_t>(threadIdx.x)
+                           : q0 + static_cast<int32_t>(kSketchTile) +
+                                 static_cast<int32_t>(threadIdx.x) - H;
+    uint32_t h = kBad;
+    if (p >= 0 && p < L) {
+      const uint32_t wi = (static_cast<uint32_t>(p) >> 5) - w_lo;
+      const uint32_t sh = (static_cast<uint32_t>(p) & 31) << 1;
+      uint64_t lo = sh_words[wi] >> sh;
+      if (sh) lo |= sh_words[wi + 1] << (64 - sh);
+      uint32_t st;
+      h = hash_of(static_cast<uint32_t>(lo), &st);
+    }
+    sh_hash[left ? threadIdx.x : H + kSketchTile + threadIdx.x - H] = h;
+  }
+  __syncthreads();
+
+  // ---- select ----
+  uint32_t flags = 0;
+  if (qa < q1) {
+    uint32_t h[N];
+    const uint32_t* src = sh_hash + threadIdx.x * ITEMS;  // slot of position qa - H
+#pragma unroll
+    for (int j = 0; j < N; ++j) h[j] = src[j];
+    // minimum of the window starting at slot j (positions qa - H + j .. + W - 1),
+    // 0 if the window leaves [0, L)
+    uint32_t wm[ITEMS + H];
+#pragma unroll
+    for (int j = 0; j < ITEMS + H; ++j) {
+      uint32_t v = h[j];
+#pragma unroll
+      for (int t = 1; t < W; ++t) v = min(v, h[j + t]);
+      const int32_t s0 = qa - H + j;
+      wm[j] = (s0 >= 0 && s0 + W <= L) ? v : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      uint32_t best = wm[i];
+#pragma unroll
+      for (int d = 1; d <= H; ++d) best = max(best, wm[i + d]);
+      const uint32_t hq = h[H + i];
+      if (best == hq && hq != kBad) flags |= 1u << i;
+    }
+  }
+
+  uint32_t total;
+  const uint32_t ex =
+      BlockExclusiveSum<uint32_t, kSketchThreads>(__popc(flags), sh_scan, &total);
+
+  // ---- output offset: decoupled look-back by the first warp ----
+  if (threadIdx.x < 32) {
+    const uint32_t lane = threadIdx.x;
+    uint64_t excl = 0;
+    volatile uint64_t* st = status;
+    if (tile > 0) {
+      if (lane == 0) {
+        st[tile] = kStAggregate | total;
+        __threadfence();
+      }
+      __syncwarp();
+      int64_t idx = static_cast<int64_t>(tile) - 1;
+      while (true) {
+        const int64_t mine = idx - lane;
+        uint64_t v = kStPrefix;  // before tile 0: an empty prefix
+        if (mine >= 0) {
+          do {
+            v = st[mine];
+          } while ((v & kStMask) == 0);
+        }
+        const uint32_t pm = __ballot_sync(0xFFFFFFFFu, (v & kStMask) == kStPrefix);
+        const int firstp = __ffs(pm) - 1;
+        uint64_t part = (firstp < 0 || static_cast<int>(lane) <= firstp) ? (v & ~kStMask) : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, d);
+        excl += part;
+        if (firstp >= 0) break;
+        idx -= 32;
+      }
+    }
+    if (lane == 0) {
+      st[tile] = kStPrefix | (excl + total);
+      tile_out[tile] = excl;
+      if (tile + 1 == n_tiles) tile_out[n_tiles] = excl + total;
+      sh_excl = excl;
+    }
+  }
+  __syncthreads();
+  uint64_t dst = sh_excl + ex;
+  const uint64_t id = static_cast<uint64_t>(ids[r]) << 32;
+#pragma unroll
+  for (int i = 0; i < ITEMS; ++i) {
+    if ((flags >> i) & 1u) {
+      if (dst < out_cap) {
+        out_val[dst] = own[i];
+        out_org[dst] = id | (static_cast<uint64_t>(static_cast<uint32_t>(qa + i)) << 1) |
+                       ((strands >> i) & 1u);
+      }
+      ++dst;
+    }
+  }
+}
+
 __global__ void GatherReadOffsets(const uint64_t* __restrict__ tile_off,
                                   const uint64_t* __restrict__ tile_out,
                                   uint32_t first_read, uint32_t n_reads,
@@ -485,7 +701,12 @@ void EnsureSketch(Ctx& c, uint32_t first, uint32_t last) {
       uint64_t* val = c.s_val.reserve(k32 ? cap / 2 + 1 : cap);
       uint64_t* org = c.s_org.reserve(cap);
       RVN_CUDA(cudaMemsetAsync(status, 0, (n_tiles + 2) * sizeof(uint64_t), c.stream));
-      if (k32) {
+      if (k32 && c.prm.w == 5) {  // raven's default window: the fast kernel
+        SketchFastKernel<5><<<static_cast<unsigned>(n_tiles), kSketchThreads, 0, c.stream>>>(
+            c.d_words.get(), c.d_woff.get(), c.d_len.get(), c.d_ids.get(),
+            c.d_tile_off.get(), first, last, c.prm.k, ticket, status, tout, n_tiles, cap,
+            reinterpret_cast<uint32_t*>(val), org);
+      } else if (k32) {
         SketchKernel<uint32_t><<<static_cast<unsigned>(n_tiles), kSketchThreads, smem,
                                  c.stream>>>(
             c.d_words.get(), c.d_woff.get(), c.d_len.get(), c.d_ids.get(),

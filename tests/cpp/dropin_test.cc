@@ -65,7 +65,8 @@ void Dump(std::ofstream& out,
     }
     off.push_back(ovl.size() / 8);
     PileProbe probe;
-    cereal::access::member_serialize(probe, *piles[i]);
+    auto visit = cereal::fields(probe);
+    cereal::access::member_serialize(visit, *piles[i]);
     pile.insert(pile.end(), probe.data.begin(), probe.data.end());
     poff.push_back(pile.size());
   }

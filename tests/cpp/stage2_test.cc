@@ -126,7 +126,8 @@ int main(int argc, char** argv) {
       }
       for (const auto& p : piles) {
         PileDump d{&pd};
-        cereal::access::member_serialize(d, *p);
+        auto visit = cereal::fields(d);
+        cereal::access::member_serialize(visit, *p);
       }
       std::vector<std::uint32_t> order;
       for (const auto& s : seqs) order.push_back(s->id);

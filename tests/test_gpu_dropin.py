@@ -122,3 +122,41 @@ def test_stage2_and_identity_filter_batched_equals_reference(tmp_path, lambda_re
     assert a[0].size > 0                       # something survived the stage
     if identity > 0.85:                        # and the filter bit on 10 % error reads
         assert a[0].size < 8 * 50_000
+
+
+def test_reference_cli_runs_on_b200(tmp_path, oracle, reference, lambda_reads):
+    """The reference's own executable (RavenExe/src/main.cc + all of RavenLib,
+    unmodified; tests/cpp/Makefile `_build/raven`) over the drop-in dependencies:
+    FASTQ.gz in (bioparser), overlap + layout + 2 polishing rounds on the B200,
+    FASTA out - the RavenTest.Assemble configuration (-M, raven_test.cpp:50-67)
+    and its golden value; then `--resume` from the checkpoint (cereal) gives the
+    same answer (RavenTest.Checkpoints, raven_test.cpp:69-95)."""
+    import gzip
+    import oracle_lib
+    from raven_b200 import seqio
+    binary = os.path.join(HERE, "cpp", "_build", "raven")
+    if not os.path.exists(binary):
+        pytest.skip("tests/cpp/_build/raven not built")
+    rs = lambda_reads
+    fq = tmp_path / "lambda.fastq.gz"
+    with gzip.open(fq, "wt", compresslevel=1) as f:
+        for i in range(rs.n):
+            seq = rs.ascii(i).decode()
+            bq = rs.block_quality[int(rs.bq_off[i]):int(rs.bq_off[i + 1])]
+            qual = "".join(chr(33 + int(q)) * 64 for q in bq)[:len(seq)]  # same block means
+            f.write(f"@{rs.names[i]} extra words\n{seq}\n+\n{qual}\n")
+    run = lambda *a: subprocess.run([binary, "-t", "4", "-M", *a, str(fq)], check=True,
+                                    cwd=tmp_path, stdout=subprocess.PIPE,
+                                    stderr=subprocess.DEVNULL, timeout=900).stdout
+    out = run("-p", "2", "-F", "graph.gfa").decode().split("\n")
+    names, seqs = out[0:-1:2], [s.encode() for s in out[1::2]]
+    want_names, want_seqs = oracle_lib.ref_assemble(reference, rs, True, 2, 8)
+    assert [n[1:] for n in names] == want_names
+    assert seqs == want_seqs
+    genome = seqio.ReadSet.load(os.path.join(HERE, "golden", "lambda_genome.npz")).ascii(0)
+    rc = seqs[0].translate(bytes.maketrans(b"ACGT", b"TGCA"))[::-1]
+    assert oracle.edit_distance(rc, genome) == 1137
+    assert os.path.getsize(tmp_path / "graph.gfa") > 0
+    assert os.path.exists(tmp_path / "raven.cereal")
+    again = run("--resume", "-p", "2").decode().split("\n")
+    assert again == out

@@ -55,6 +55,38 @@ def test_poa_variants(gpu_engine, oracle):
     assert ((got["status"] & 1) == (nl >= 3)).all()
 
 
+def _concat_windows(a, b):
+    """Two flat window batches as one."""
+    ns, nb = int(a["win_first"][-1]), int(a["seq_off"][-1])
+    return dict(
+        win_first=np.concatenate([a["win_first"], b["win_first"][1:] + ns]).astype(np.uint32),
+        seq_off=np.concatenate([a["seq_off"], b["seq_off"][1:] + np.uint64(nb)]).astype(np.uint64),
+        bases=np.concatenate([a["bases"], b["bases"]]),
+        quals=None if a["quals"] is None else np.concatenate([a["quals"], b["quals"]]),
+        seq_begin=np.concatenate([a["seq_begin"], b["seq_begin"]]),
+        seq_end=np.concatenate([a["seq_end"], b["seq_end"]]))
+
+
+def test_poa_long_layers_and_mixed_batches(gpu_engine, oracle):
+    """Layers beyond the 575 bases of the register-row kernel take the generic
+    kernel - chosen per WINDOW, so a mixed batch runs both (real ONT windows have
+    such layers: 500 target bases, 3 % insertions and more in the reads)."""
+    long_w = synth.make_windows(n_windows=5, backbone_len=760, layers=14, seed=11)
+    nl = np.diff(long_w["seq_off"].astype(np.int64))
+    assert nl.max() > 600
+    check(gpu_engine, oracle, long_w)
+    short_w = synth.make_windows(n_windows=7, backbone_len=500, layers=20, seed=12)
+    both = _concat_windows(short_w, long_w)
+    got = check(gpu_engine, oracle, both)
+    alone = gpu_engine.poa_batch(short_w)
+    n = int(alone["cons_off"][-1])
+    assert np.array_equal(got["consensus"][:n], alone["consensus"])
+    # one window with a single long, insertion-rich layer among short ones
+    w = synth.make_windows(n_windows=3, backbone_len=520, layers=10, seed=13, ins=0.12, dele=0.01)
+    assert np.diff(w["seq_off"].astype(np.int64)).max() > 576
+    check(gpu_engine, oracle, _concat_windows(w, short_w))
+
+
 def test_poa_rejects_bad_input(gpu_engine):
     w = synth.make_windows(n_windows=2, backbone_len=100, layers=4, seed=8)
     with pytest.raises(ValueError):
