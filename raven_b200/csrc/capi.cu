@@ -494,7 +494,7 @@ RVN_API int rvn_sketch(rvn_ctx* ctx, uint32_t first, uint32_t last, int minhash,
     uint64_t* hv = c.x_val.reserve(total + 1);
     uint64_t* ho = c.x_org.reserve(total + 1);
     uint64_t* hf = c.x_off.reserve(nr + 2ULL);
-    const bool v32 = !minhash && c.s_is32;  // full sketches of k <= 15 hold u32 values
+    const bool v32 = minhash ? c.q_is32 : c.s_is32;  // k <= 15: u32 values
     RVN_CUDA(cudaMemcpyAsync(hv, dv, total * (v32 ? 4 : 8), cudaMemcpyDeviceToHost, c.stream));
     RVN_CUDA(cudaMemcpyAsync(ho, dorg, total * 8, cudaMemcpyDeviceToHost, c.stream));
     for (uint32_t i = 0; i <= nr; ++i) hf[i] = (*hoff)[i];

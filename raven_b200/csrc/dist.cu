@@ -523,7 +523,7 @@ void DistSketchSplit(Ctx& c, uint32_t first, uint32_t last, int which, uint32_t 
   uint64_t n = c.s_n;
   if (which == 1) {
     EnsureMicromizers(c, first, last);
-    sv = ValView{c.q_val.get(), 0};
+    sv = ValView{c.q_val.get(), c.q_is32 ? 1 : 0};
     so = c.q_org.get();
     n = c.q_n;
   }

@@ -55,6 +55,7 @@ struct Ctx {
   // sketch tiles: tile_off[r] = first tile of read r (depends on k)
   std::vector<uint64_t> h_tile_off;
   DevBuf<uint64_t> d_tile_off;
+  DevBuf<uint32_t> d_tile_read;  // read of every tile
   uint32_t tiles_k = 0;
 
   // ---- current sketch (full minimizers of reads [s_first, s_last)) ----
@@ -72,6 +73,7 @@ struct Ctx {
   uint32_t q_first = 0, q_last = 0;
   uint64_t q_n = 0;
   DevBuf<uint64_t> q_val, q_org, q_off;
+  bool q_is32 = false;  // q_val holds u32 values
   std::vector<uint64_t> h_q_off;
 
   // ---- index ----

@@ -194,7 +194,7 @@ void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash) {
   uint64_t n = c.s_n;
   if (minhash) {
     EnsureMicromizers(c, first, last);
-    src_val = ValView{c.q_val.get(), 0};
+    src_val = ValView{c.q_val.get(), c.q_is32 ? 1 : 0};
     src_org = c.q_org.get();
     n = c.q_n;
   }

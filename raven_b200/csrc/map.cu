@@ -1416,7 +1416,7 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
     if (!(c.q_valid && c.q_first <= first && last <= c.q_last)) {
       EnsureMicromizers(c, first, last);
     }
-    qv = ValView{c.q_val.get(), 0};
+    qv = ValView{c.q_val.get(), c.q_is32 ? 1 : 0};
     qo = c.q_org.get();
     d_read_off = c.q_off.get();
     h_read_off = &c.h_q_off;

@@ -108,6 +108,7 @@ struct __align__(16) PassSmem {
   uint32_t bin_dst[kBins];            // global index of staging slot s of bin d = bin_dst[d] + s
   uint32_t scan[34];
   uint32_t tile;
+  uint16_t slot_digit[HAS_VAL ? kTile : 2];  // digit of the element staged at a slot
   union {
     KeyT keys[kTile];
     ValT vals[HAS_VAL ? kTile : 1];
@@ -259,7 +260,7 @@ OnesweepPass(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
   }
   __syncthreads();
 
-  // ---- keys: to their staging slot, then out in bin order ----
+  // ---- staging slot of every item (kept packed in the rank registers) ----
 #pragma unroll
   for (int i = 0; i < kItems; ++i) {
     const uint32_t t = warp_base + i * 32 + lane;
@@ -267,34 +268,51 @@ OnesweepPass(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
       const uint32_t d = Digit<KeyT>(key[i], flip, begin_bit, dmask);
       const uint32_t slot = sm.bin_off[d] + sm.warp_hist[warp][d] + rank[i];
       rank[i] = static_cast<uint16_t>(slot);
-      sm.stage.keys[slot] = key[i];
-    }
-  }
-  __syncthreads();
-  uint32_t dst[kItems];
-#pragma unroll
-  for (int i = 0; i < kItems; ++i) {
-    const uint32_t s = i * kThreads + threadIdx.x;
-    if (s < tile_count) {
-      const KeyT k = sm.stage.keys[s];
-      dst[i] = sm.bin_dst[Digit<KeyT>(k, flip, begin_bit, dmask)] + s;
-      keys_out[dst[i]] = k;
+      if (HAS_VAL) sm.slot_digit[slot] = static_cast<uint16_t>(d);
     }
   }
 
-  // ---- payloads: the same two hops ----
+  // ---- payloads first (the keys wait in registers): global -> staging slot,
+  // then out in bin order. Loads go 8 at a time so that their latencies overlap
+  // without holding a tile's worth of payload registers. ----
   if (HAS_VAL) {
-    __syncthreads();  // every key has left the staging buffer
+    constexpr int kChunk = 8;
 #pragma unroll
-    for (int i = 0; i < kItems; ++i) {
-      const uint32_t t = warp_base + i * 32 + lane;
-      if (t < tile_count) sm.stage.vals[rank[i]] = vals_in[tile_base + t];
+    for (int c0 = 0; c0 < kItems; c0 += kChunk) {
+      ValT v[kChunk];
+#pragma unroll
+      for (int i = 0; i < kChunk; ++i) {
+        const uint32_t t = warp_base + (c0 + i) * 32 + lane;
+        v[i] = t < tile_count ? vals_in[tile_base + t] : ValT(0);
+      }
+#pragma unroll
+      for (int i = 0; i < kChunk; ++i) {
+        const uint32_t t = warp_base + (c0 + i) * 32 + lane;
+        if (t < tile_count) sm.stage.vals[rank[c0 + i]] = v[i];
+      }
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kItems; ++i) {
       const uint32_t s = i * kThreads + threadIdx.x;
-      if (s < tile_count) vals_out[dst[i]] = sm.stage.vals[s];
+      if (s < tile_count) vals_out[sm.bin_dst[sm.slot_digit[s]] + s] = sm.stage.vals[s];
+    }
+    __syncthreads();  // every payload has left the staging buffer
+  }
+
+  // ---- keys: the same two hops ----
+#pragma unroll
+  for (int i = 0; i < kItems; ++i) {
+    const uint32_t t = warp_base + i * 32 + lane;
+    if (t < tile_count) sm.stage.keys[rank[i]] = key[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kItems; ++i) {
+    const uint32_t s = i * kThreads + threadIdx.x;
+    if (s < tile_count) {
+      const KeyT k = sm.stage.keys[s];
+      keys_out[sm.bin_dst[Digit<KeyT>(k, flip, begin_bit, dmask)] + s] = k;
     }
   }
 }

@@ -327,7 +327,8 @@ template <int W>
 __global__ void __launch_bounds__(kSketchThreads)
 SketchFastKernel(const uint64_t* __restrict__ words, const uint64_t* __restrict__ woff,
                  const uint32_t* __restrict__ lens, const uint32_t* __restrict__ ids,
-                 const uint64_t* __restrict__ tile_off, uint32_t first_read,
+                 const uint64_t* __restrict__ tile_off,
+                 const uint32_t* __restrict__ tile_read, uint32_t first_read,
                  uint32_t last_read, uint32_t k, unsigned int* __restrict__ ticket,
                  uint64_t* __restrict__ status, uint64_t* __restrict__ tile_out,
                  uint64_t n_tiles, uint64_t out_cap, uint32_t* __restrict__ out_val,
@@ -345,26 +346,12 @@ SketchFastKernel(const uint64_t* __restrict__ words, const uint64_t* __restrict_
   __shared__ uint32_t sh_read, sh_tile;
   __shared__ uint64_t sh_excl;
 
-  if (threadIdx.x < 32) {
-    uint32_t tk = 0;
-    if (threadIdx.x == 0) tk = atomicAdd(ticket, 1u);
-    tk = __shfl_sync(0xFFFFFFFFu, tk, 0);
-    const uint64_t want = tile_off[first_read] + tk;
-    uint32_t lo = first_read, hi = last_read;  // tile_off[lo] <= want < tile_off[hi]
-    while (hi - lo > 1) {
-      const uint32_t step = (hi - lo + 31) / 32;
-      const uint64_t probe = static_cast<uint64_t>(lo) + (threadIdx.x + 1ULL) * step;
-      const bool le = probe < hi && tile_off[probe] <= want;
-      const uint32_t cnt = __popc(__ballot_sync(0xFFFFFFFFu, le));
-      const uint64_t nlo = static_cast<uint64_t>(lo) + static_cast<uint64_t>(cnt) * step;
-      const uint64_t nhi = nlo + step;
-      lo = static_cast<uint32_t>(nlo);
-      if (nhi < hi) hi = static_cast<uint32_t>(nhi);
-    }
-    if (threadIdx.x == 0) {
-      sh_tile = tk;
-      sh_read = lo;
-    }
+  // ticket, then the read of the tile from the per-tile table (a one-read range,
+  // e.g. an external query, needs no table)
+  if (threadIdx.x == 0) {
+    const uint32_t tk = atomicAdd(ticket, 1u);
+    sh_tile = tk;
+    sh_read = last_read - first_read == 1 ? first_read : tile_read[tile_off[first_read] + tk];
   }
   __syncthreads();
   const uint32_t tile = sh_tile;
@@ -443,6 +430,8 @@ SketchFastKernel(const uint64_t* __restrict__ words, const uint64_t* __restrict_
   __syncthreads();
 
   // ---- select ----
+  // (every window of an interior tile lies inside the read: no bounds tests)
+  const bool interior = q0 >= H && q0 + static_cast<int32_t>(kSketchTile) + H <= L;
   uint32_t flags = 0;
   if (qa < q1) {
     uint32_t h[N];
@@ -458,7 +447,7 @@ SketchFastKernel(const uint64_t* __restrict__ words, const uint64_t* __restrict_
 #pragma unroll
       for (int t = 1; t < W; ++t) v = min(v, h[j + t]);
       const int32_t s0 = qa - H + j;
-      wm[j] = (s0 >= 0 && s0 + W <= L) ? v : 0u;
+      wm[j] = (interior || (s0 >= 0 && s0 + W <= L)) ? v : 0u;
     }
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
@@ -548,7 +537,7 @@ MicromizeKernel(const ValT* __restrict__ s_val,
                 const uint64_t* __restrict__ s_off,  // per read of the sketch
                 uint32_t s_first, const uint64_t* __restrict__ q_off,
                 uint32_t q_first, uint32_t k,
-                uint64_t* __restrict__ q_val, uint64_t* __restrict__ q_org) {
+                ValT* __restrict__ q_val, uint64_t* __restrict__ q_org) {
   __shared__ uint32_t hist[256];
   __shared__ uint32_t sh_scan[34];
   __shared__ uint32_t sh_digit, sh_want;
@@ -623,7 +612,7 @@ MicromizeKernel(const ValT* __restrict__ s_val,
     const bool keep = is_lt || (is_eq && eq_before < need_eq);
     if (keep) {
       const uint64_t d = ob + kept + lt_before + eq_kept_before;
-      q_val[d] = v;
+      q_val[d] = static_cast<ValT>(v);
       q_org[d] = o;
     }
     const uint32_t eq_tot = tot >> 16, lt_tot = tot & 0xFFFF;
@@ -652,6 +641,21 @@ void EnsureTiles(Ctx& c) {
       if (L >= c.prm.w) tiles = (L + kSketchTile - 1) / kSketchTile;
     }
     c.h_tile_off[r + 1] = c.h_tile_off[r] + tiles;
+  }
+  // read of every tile (the fast kernel's lookup)
+  {
+    const uint64_t nt = c.h_tile_off[c.n_reads];
+    if (nt >= 0xFFFFFFFFULL) throw LimitError("too many sketch tiles");
+    std::vector<uint32_t> tr(nt);
+    for (uint32_t r = 0; r < c.n_reads; ++r) {
+      for (uint64_t t = c.h_tile_off[r]; t < c.h_tile_off[r + 1]; ++t) tr[t] = r;
+    }
+    uint32_t* dtr = c.d_tile_read.reserve(nt + 1);
+    if (nt) {
+      RVN_CUDA(cudaMemcpyAsync(dtr, tr.data(), nt * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                               c.stream));
+      RVN_CUDA(cudaStreamSynchronize(c.stream));  // tr goes out of scope
+    }
   }
   // one spare slot: an external query read rides at index n_reads
   uint64_t* d = c.d_tile_off.reserve(c.n_reads + 2ULL);
@@ -704,8 +708,8 @@ void EnsureSketch(Ctx& c, uint32_t first, uint32_t last) {
       if (k32 && c.prm.w == 5) {  // raven's default window: the fast kernel
         SketchFastKernel<5><<<static_cast<unsigned>(n_tiles), kSketchThreads, 0, c.stream>>>(
             c.d_words.get(), c.d_woff.get(), c.d_len.get(), c.d_ids.get(),
-            c.d_tile_off.get(), first, last, c.prm.k, ticket, status, tout, n_tiles, cap,
-            reinterpret_cast<uint32_t*>(val), org);
+            c.d_tile_off.get(), c.d_tile_read.get(), first, last, c.prm.k, ticket, status, tout,
+            n_tiles, cap, reinterpret_cast<uint32_t*>(val), org);
       } else if (k32) {
         SketchKernel<uint32_t><<<static_cast<unsigned>(n_tiles), kSketchThreads, smem,
                                  c.stream>>>(
@@ -768,10 +772,10 @@ void EnsureMicromizers(Ctx& c, uint32_t first, uint32_t last) {
   uint64_t* qo = c.q_org.reserve(total);
   if (nr > 0 && total > 0) {
     TimerBegin(c, "micromize");
-    if (c.s_is32) {
+    if (c.s_is32) {  // micromizer values stay u32 like the sketch's
       MicromizeKernel<uint32_t><<<nr, kMicroThreads, 0, c.stream>>>(
           reinterpret_cast<const uint32_t*>(c.s_val.get()), c.s_org.get(), c.s_off.get(),
-          c.s_first, qoff, first, c.prm.k, qv, qo);
+          c.s_first, qoff, first, c.prm.k, reinterpret_cast<uint32_t*>(qv), qo);
     } else {
       MicromizeKernel<uint64_t><<<nr, kMicroThreads, 0, c.stream>>>(
           c.s_val.get(), c.s_org.get(), c.s_off.get(), c.s_first, qoff, first, c.prm.k, qv,
@@ -785,6 +789,7 @@ void EnsureMicromizers(Ctx& c, uint32_t first, uint32_t last) {
   c.q_first = first;
   c.q_last = last;
   c.q_n = total;
+  c.q_is32 = c.s_is32;
   c.q_valid = true;
 }
 
