@@ -52,6 +52,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--poa-windows", type=int, default=8192,
                     help="windows of the POA sub-benchmark (0 = skip)")
+    ap.add_argument("--c3-reads", type=int, default=20_000,
+                    help="reads of the C3-shaped polishing run (0 = skip)")
+    ap.add_argument("--c5-reads", type=int, default=30_000,
+                    help="HiFi reads of the C5-shaped run: stage 1 + identity filter (0 = skip)")
     return ap.parse_args()
 
 
@@ -432,6 +436,10 @@ def main_ours(a):
             out["dist_trace_ms"] = {k: round(v, 2) for k, v in last["trace_ms"].items()}
         if world == 1 and a.poa_windows > 0:
             out["poa"] = bench_poa(eng, a, peak, not a.no_cpu_baseline)
+        if world == 1 and a.c3_reads > 0:
+            out["poa"] = dict(out.get("poa", {}), c3=bench_c3(a, not a.no_cpu_baseline))
+        if world == 1 and a.c5_reads > 0:
+            out["c5"] = bench_c5(a, local, not a.no_cpu_baseline)
         if world == 1 and not a.no_cpu_baseline:
             step, n_map_cpu, kind, threads, sample = run_cpu(a, "reference")
             dt, cpu_res = step()
@@ -531,6 +539,152 @@ def bench_poa(eng, a, peak, with_cpu):
                                "sample": f"{512 * reps} of the same windows, scalar int32 DP "
                                          "(upstream spoa uses SIMD)",
                                "gcups": float(rc["cells"].sum()) * reps / dtc / 1e9}
+    return out
+
+
+def bench_c3(a, with_cpu):
+    """C3-shaped polishing (BASELINE configs[2]: the C2 read model, one round, m=3 n=-5
+    g=-4): windows cut by the REAL polisher - racon::Polisher facade: GPU mapping of
+    the reads to draft contigs, host alignment paths + breaking points, GPU POA of
+    every 500-base window - instead of synthetic windows."""
+    from bench import synth
+    from raven_b200 import polish
+    n = min(a.c3_reads, a.reads)
+    g = max(int(a.genome * n / max(a.reads, 1)), 8 * a.mean_len)
+    reads = synth.make_reads(SEED + 1, g, n, a.mean_len)
+    draft = synth.make_contigs(SEED + 1, g, contig_len=1_000_000)
+    threads = os.cpu_count() or 1
+    polish.polish(draft, reads, threads=threads)            # warm-up (allocations)
+    _, st = polish.polish(draft, reads, threads=threads)
+    out = {
+        "workload": f"C3-shaped: {n} ONT reads (~{a.mean_len // 1000} kb, 40x) polished onto "
+                    f"{draft.n} draft contigs ({g / 1e6:.1f} Mbp, ~1% error), one round, w=500 "
+                    "m=3 n=-5 g=-4 trim, through the racon::Polisher facade",
+        "windows": st["windows"], "polished_windows": st["polished_windows"],
+        "value": st["polished_windows"] / st["poa_seconds"], "unit": "windows/s",
+        "note": "value = polished windows / consensus phase (H2D of the window batch + POA "
+                "kernels + D2H); e2e = the whole Polish call",
+        "e2e": {"value": st["polished_windows"] / st["seconds"], "unit": "windows/s",
+                "seconds": st["seconds"], "poa_seconds": st["poa_seconds"]},
+    }
+    if with_cpu:
+        import oracle_lib
+        O = oracle_lib.Oracle()
+        ns = max(1, n // 8)  # bounded CPU sample: 1/8 of the reads over 1/8 of the genome
+        gs = max(g // 8, 8 * a.mean_len)
+        sreads = synth.make_reads(SEED + 2, gs, ns, a.mean_len)
+        sdraft = synth.make_contigs(SEED + 2, gs, contig_len=1_000_000)
+        _, _, ost = O.polish(sdraft, sreads, threads=threads)
+        _, gst = polish.polish(sdraft, sreads, threads=threads)
+        out["cpu_baseline"] = {
+            "value": float(ost[1]) / float(ost[2]), "unit": "windows/s (whole Polish call)",
+            "cores": threads, "kind": "port",
+            "sample": f"{ns} reads / {gs / 1e6:.2f} Mbp of the same model; scalar restatement of "
+                      "racon/spoa (upstream spoa is SIMD), whole Polish call",
+            "gpu_same_sample": {"value": gst["polished_windows"] / gst["seconds"],
+                                "unit": "windows/s (whole Polish call)"}}
+    return out
+
+
+def bench_c5(a, local, with_cpu):
+    """C5-shaped (BASELINE configs[4], one GPU's worth): PacBio HiFi reads ~15 kb,
+    k=19 w=10 f=0.001 kMaxNumOverlaps=32, identity 0.95: stage 1
+    (FindOverlapsAndCreatePiles) and the identity filter's edit distances
+    (construct.cc:162-217) on the kept overlaps, batched on the device."""
+    import numpy as np
+    import torch
+    from bench import synth
+    from raven_b200 import engine
+    n, mean = a.c5_reads, 15_000
+    g = int(n * mean / 30)  # 30x
+    rs = synth.make_reads(SEED + 5, g, n, mean, sub=0.002, ins=0.0015, dele=0.0015)
+    eng = engine.Engine(device=local)
+    eng.configure(19, 10)
+    eng.upload(rs)
+    for _ in range(2):
+        eng.find_overlaps_and_create_piles(0.001, 32, False, fetch=False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        eng.find_overlaps_and_create_piles(0.001, 32, False, fetch=False)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / a.steps
+    st = eng.stats()
+    res = eng.find_overlaps_and_create_piles(0.001, 32, False, fetch=True)
+    o = res["overlaps"]
+    o = o[o[:, 0] < o[:, 3]]  # each pair once (the lists hold both directions)
+    ll, rl = o[:, 2] - o[:, 1], o[:, 5] - o[:, 4]
+    longest = np.maximum(ll, rl).astype(np.float64)
+    identity = 0.95
+    limit = (np.floor((1 - identity) * longest) + 2).astype(np.int32)
+    args = (o[:, 0], o[:, 1], ll, o[:, 3], o[:, 4], rl, o[:, 7], limit)
+    eng.edit_distance_batch(*args)
+    t0 = time.perf_counter()
+    d = eng.edit_distance_batch(*args)
+    dte = time.perf_counter() - t0
+    score = 1.0 - d.astype(np.float64) / longest
+    keep = (d >= 0) & ~(score < identity)
+    out = {
+        "workload": f"C5-shaped, one GPU: {n} synthetic HiFi reads ~15 kb over a "
+                    f"{g / 1e6:.0f} Mbp genome (30x, 0.5% error), k=19 w=10 f=0.001 "
+                    "kMaxNumOverlaps=32 identity=0.95",
+        "stage1": {"value": st["overlaps"] / dt, "unit": "overlaps/s", "ms_per_step": 1e3 * dt,
+                   "overlaps_per_step": int(st["overlaps"]),
+                   "phases_ms": {k: round(v, 3) for k, v in sorted(eng.timings().items())}},
+        "identity_filter": {"value": int(o.shape[0]) / dte, "unit": "alignments/s",
+                            "pairs": int(o.shape[0]), "seconds": dte,
+                            "mean_pair_bases": float(longest.mean()) if o.shape[0] else 0.0,
+                            "kept_fraction": float(keep.mean()) if o.shape[0] else 0.0,
+                            "gcups_equivalent": float((ll.astype(np.float64) * rl).sum()) / dte / 1e9},
+    }
+    if with_cpu and o.shape[0]:
+        # host leg: the product's own edlib (raven_b200/host/edlib.cc, what the reference's
+        # per-overlap edlibAlign call runs on), one thread, a bounded sample
+        import ctypes as C
+        import subprocess as sp
+        sp.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "host"], check=True,
+               stdout=sp.DEVNULL)
+        lib = C.CDLL(os.path.join(ROOT, "tests", "cpp", "_build", "libhost_edlib.so"))
+
+        class Cfg(C.Structure):
+            _fields_ = [("k", C.c_int), ("mode", C.c_int), ("task", C.c_int),
+                        ("eq", C.c_void_p), ("n_eq", C.c_int)]
+
+        class Res(C.Structure):
+            _fields_ = [("status", C.c_int), ("editDistance", C.c_int),
+                        ("endLocations", C.POINTER(C.c_int)), ("startLocations", C.POINTER(C.c_int)),
+                        ("numLocations", C.c_int), ("alignment", C.POINTER(C.c_ubyte)),
+                        ("alignmentLength", C.c_int), ("alphabetLength", C.c_int)]
+
+        lib.edlibAlign.restype = Res
+        lib.edlibAlign.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, Cfg]
+        lib.edlibFreeAlignResult.argtypes = [Res]
+        letters = np.frombuffer(b"ACGT", np.uint8)
+        m = min(200, o.shape[0])
+        pairs = []
+        for x in o[:m]:
+            a_ = rs.codes(int(x[0]))[int(x[1]):int(x[2])]
+            b_ = rs.codes(int(x[3]))[int(x[4]):int(x[5])]
+            if not x[7]:
+                b_ = (3 - b_[::-1]).astype(np.uint8)
+            pairs.append((letters[a_].tobytes(), letters[b_].tobytes()))
+        t0 = time.perf_counter()
+        same = True
+        for i, (sa, sb) in enumerate(pairs):
+            r = lib.edlibAlign(sa, len(sa), sb, len(sb), Cfg(-1, 0, 0, None, 0))
+            if d[i] >= 0 and r.editDistance != d[i]:
+                same = False
+            if d[i] < 0 and r.editDistance <= limit[i]:
+                same = False
+            lib.edlibFreeAlignResult(r)
+        dtc = time.perf_counter() - t0
+        out["identity_filter"]["cpu_baseline"] = {
+            "value": m / dtc, "unit": "alignments/s", "cores": 1, "kind": "port",
+            "sample": f"the first {m} pairs, host bit-vector edlib (band doubling), exact "
+                      "distance like edlibDefaultAlignConfig()"}
+        out["identity_filter"]["parity"] = {"checked": f"{m} distances vs the host edlib",
+                                            "identical": bool(same)}
+    eng.close()
     return out
 
 

@@ -120,6 +120,61 @@ __attribute__((visibility("default"))) void* synth_reads(
   return res;
 }
 
+// Draft contigs of the SAME genome (polishing targets of the C3-shaped bench):
+// the genome cut into pieces of contig_len bases, each with draft-like errors.
+__attribute__((visibility("default"))) void* synth_contigs(
+    std::uint64_t seed, std::uint64_t genome_len, std::uint64_t contig_len, double sub,
+    double ins, double del, std::uint32_t threads) {
+  if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+  const std::uint64_t gwords = (genome_len + 31) / 32;
+  std::vector<std::uint64_t> genome(gwords);
+  ParallelFor((gwords + 4095) / 4096, threads, [&](std::uint64_t c) {
+    Rng r(seed * 0x2545F4914F6CDD1DULL + c + 1);
+    for (std::uint64_t i = c * 4096; i < std::min(gwords, (c + 1) * 4096); ++i) {
+      genome[i] = r.next();
+    }
+  });
+  auto base = [&](std::uint64_t p) -> std::uint32_t {
+    return (genome[p >> 5] >> ((p & 31) << 1)) & 3;
+  };
+  const std::uint32_t n = static_cast<std::uint32_t>((genome_len + contig_len - 1) / contig_len);
+  std::vector<std::vector<std::uint64_t>> packed(n);
+  auto* res = new Result();
+  res->lens.assign(n, 0);
+  ParallelFor(n, threads, [&](std::uint64_t i) {
+    Rng r((seed ^ 0x0123456789ABCDEFULL) + 0x9E3779B97F4A7C15ULL * (i + 1));
+    const std::uint64_t start = i * contig_len, span = std::min(contig_len, genome_len - start);
+    auto& out = packed[i];
+    out.assign((span + span / 8 + 64) / 32 + 2, 0);
+    std::uint64_t m = 0;
+    auto push = [&](std::uint64_t c) {
+      if ((m >> 5) >= out.size()) out.resize(out.size() * 2, 0);
+      out[m >> 5] |= c << ((m & 31) << 1);
+      ++m;
+    };
+    for (std::uint64_t j = 0; j < span; ++j) {
+      std::uint32_t c = base(start + j);
+      const double u = r.uniform();
+      if (u < del) continue;
+      if (u < del + sub) c = (c + 1 + r.next() % 3) & 3;
+      push(c);
+      if (r.uniform() < ins) push(r.next() & 3);
+    }
+    out.resize((m + 31) / 32);
+    res->lens[i] = static_cast<std::uint32_t>(m);
+  });
+  res->word_off.assign(n + 1ULL, 0);
+  for (std::uint32_t i = 0; i < n; ++i) res->word_off[i + 1] = res->word_off[i] + packed[i].size();
+  res->words.resize(res->word_off[n]);
+  for (std::uint32_t i = 0; i < n; ++i) {
+    std::copy(packed[i].begin(), packed[i].end(), res->words.begin() + res->word_off[i]);
+  }
+  return res;
+}
+__attribute__((visibility("default"))) std::uint32_t synth_n_reads(void* h) {
+  return static_cast<std::uint32_t>(static_cast<Result*>(h)->lens.size());
+}
+
 __attribute__((visibility("default"))) std::uint64_t synth_n_words(void* h) {
   return static_cast<Result*>(h)->words.size();
 }

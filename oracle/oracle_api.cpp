@@ -338,3 +338,39 @@ ORC_EXPORT std::int64_t orc_nw_path(const char* q, int nq, const char* t, int nt
   std::memcpy(out, p.data(), p.size());
   return static_cast<std::int64_t>(p.size());
 }
+
+// racon::Polisher::Create(...)->Polish(targets, sequences, false) of the ORACLE
+// (oracle/racon_polisher.cpp): the checker of the product's polisher facade and
+// the CPU leg of the polishing bench
+ORC_EXPORT orc_bag* orc_polish(orc_reads* targets, orc_reads* sequences, double q, double e,
+                               std::uint32_t w, int trim, int m, int n, int g,
+                               std::uint32_t threads) {
+  auto pool = std::make_shared<thread_pool::ThreadPool>(std::max(1U, threads));
+  auto t0 = std::chrono::steady_clock::now();
+  auto polisher = racon::Polisher::Create(pool, q, e, w, trim != 0, m, n, g);
+  auto out = polisher->Polish(targets->seqs, sequences->seqs, false);
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  auto* bag = new orc_bag();
+  std::vector<char> seq, names;
+  std::vector<std::uint64_t> off{0};
+  for (const auto& s : out) {
+    const std::string d = s->InflateData();
+    seq.insert(seq.end(), d.begin(), d.end());
+    off.emplace_back(seq.size());
+    names.insert(names.end(), s->name.begin(), s->name.end());
+    names.push_back('\n');
+  }
+  bag->Put("sequences", seq);
+  bag->Put("seq_off", off);
+  bag->Put("names", names);
+  std::vector<double> st{static_cast<double>(polisher->num_windows()),
+                         static_cast<double>(polisher->num_polished_windows()), secs};
+  bag->Put("stats", st);
+  return bag;
+}
+
+ORC_EXPORT void orc_reads_set_names(orc_reads* r, const char* prefix) {
+  for (std::size_t i = 0; i < r->seqs.size(); ++i) {
+    r->seqs[i]->name = std::string(prefix) + std::to_string(i);
+  }
+}

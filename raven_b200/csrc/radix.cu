@@ -153,6 +153,17 @@ OnesweepPass(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
     key[i] = t < tile_count ? keys_in[tile_base + t] : static_cast<KeyT>(0);
   }
 
+  // first half of the payloads: in flight while the keys are ranked
+  constexpr int kHalf = kItems / 2;
+  ValT early[HAS_VAL ? kHalf : 1];
+  if (HAS_VAL) {
+#pragma unroll
+    for (int i = 0; i < kHalf; ++i) {
+      const uint32_t t = warp_base + i * 32 + lane;
+      early[i] = t < tile_count ? vals_in[tile_base + t] : ValT(0);
+    }
+  }
+
   // ---- rank inside the warp, in input order ----
   uint16_t rank[kItems];
   uint16_t* my_hist = sm.warp_hist[warp];
@@ -160,9 +171,17 @@ OnesweepPass(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
   for (int i = 0; i < kItems; ++i) {
     const uint32_t t = warp_base + i * 32 + lane;
     const bool valid = t < tile_count;
-    // invalid lanes get a digit of their own (never equal to a real one)
-    const uint32_t d = valid ? Digit<KeyT>(key[i], flip, begin_bit, dmask) : (0x8000u | lane);
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+    // lanes with the same digit: one ballot per digit bit (the hardware MATCH.ANY
+    // is several times slower than ten votes); invalid lanes stand alone
+    const uint32_t d = valid ? Digit<KeyT>(key[i], flip, begin_bit, dmask) : 0u;
+    uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
+#pragma unroll
+    for (int bit = 0; bit < kRadixMaxBits; ++bit) {
+      const bool one = (d >> bit) & 1u;
+      const uint32_t vote = __ballot_sync(0xFFFFFFFFu, one);
+      peers &= one ? vote : ~vote;
+    }
+    if (!valid) peers = 1u << lane;
     const uint32_t leader = __ffs(peers) - 1;
     uint32_t before = 0;
     if (lane == leader && valid) {
@@ -273,23 +292,24 @@ OnesweepPass(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
   }
 
   // ---- payloads first (the keys wait in registers): global -> staging slot,
-  // then out in bin order. Loads go 8 at a time so that their latencies overlap
-  // without holding a tile's worth of payload registers. ----
+  // then out in bin order. The first half was loaded before the ranking, the
+  // second half goes out as one batch of independent loads. ----
   if (HAS_VAL) {
-    constexpr int kChunk = 8;
+    ValT late[kHalf];
 #pragma unroll
-    for (int c0 = 0; c0 < kItems; c0 += kChunk) {
-      ValT v[kChunk];
+    for (int i = 0; i < kHalf; ++i) {
+      const uint32_t t = warp_base + (kHalf + i) * 32 + lane;
+      late[i] = t < tile_count ? vals_in[tile_base + t] : ValT(0);
+    }
 #pragma unroll
-      for (int i = 0; i < kChunk; ++i) {
-        const uint32_t t = warp_base + (c0 + i) * 32 + lane;
-        v[i] = t < tile_count ? vals_in[tile_base + t] : ValT(0);
-      }
+    for (int i = 0; i < kHalf; ++i) {
+      const uint32_t t = warp_base + i * 32 + lane;
+      if (t < tile_count) sm.stage.vals[rank[i]] = early[i];
+    }
 #pragma unroll
-      for (int i = 0; i < kChunk; ++i) {
-        const uint32_t t = warp_base + (c0 + i) * 32 + lane;
-        if (t < tile_count) sm.stage.vals[rank[c0 + i]] = v[i];
-      }
+    for (int i = 0; i < kHalf; ++i) {
+      const uint32_t t = warp_base + (kHalf + i) * 32 + lane;
+      if (t < tile_count) sm.stage.vals[rank[kHalf + i]] = late[i];
     }
     __syncthreads();
 #pragma unroll

@@ -323,8 +323,10 @@ SketchKernel(const uint64_t* __restrict__ words,
 // quarter of the instructions of the generic kernel; same tiles, same look-back,
 // same output order.
 // ---------------------------------------------------------------------------
+constexpr int kFastGroup = 4;  // consecutive tiles per CTA: one look-back for all
+
 template <int W>
-__global__ void __launch_bounds__(kSketchThreads)
+__global__ void __launch_bounds__(kSketchThreads, 4)
 SketchFastKernel(const uint64_t* __restrict__ words, const uint64_t* __restrict__ woff,
                  const uint32_t* __restrict__ lens, const uint32_t* __restrict__ ids,
                  const uint64_t* __restrict__ tile_off,
@@ -338,39 +340,26 @@ SketchFastKernel(const uint64_t* __restrict__ words, const uint64_t* __restrict_
   constexpr int ITEMS = 8;
   constexpr int N = ITEMS + 2 * H;  // hashes a thread looks at
   constexpr int kSlots = kSketchTile + 2 * H;
+  constexpr int G = kFastGroup;
   static_assert(kSketchTile == ITEMS * kSketchThreads, "8 positions per thread");
   static_assert(W >= 2 && W <= 8, "window of 2..8 k-mers");
   __shared__ uint64_t sh_words[(kSlots + 31 + 31) / 32 + 3];
-  __shared__ __align__(16) uint32_t sh_hash[kSlots + 8];  // slot j = position q0 - H + j
+  // hashes of every tile of the group (they are the output values; a register copy
+  // would cost occupancy): slot j of tile g = position q0 - H + j
+  __shared__ __align__(16) uint32_t sh_hash_all[kFastGroup][kSlots + 8];
   __shared__ uint32_t sh_scan[34];
-  __shared__ uint32_t sh_read, sh_tile;
+  __shared__ uint32_t sh_group;
   __shared__ uint64_t sh_excl;
 
-  // ticket, then the read of the tile from the per-tile table (a one-read range,
-  // e.g. an external query, needs no table)
-  if (threadIdx.x == 0) {
-    const uint32_t tk = atomicAdd(ticket, 1u);
-    sh_tile = tk;
-    sh_read = last_read - first_read == 1 ? first_read : tile_read[tile_off[first_read] + tk];
-  }
+  // ticket: the group of G consecutive tiles this CTA sketches (tiles of one launch
+  // are ordered by (read, position), so a group may span reads)
+  if (threadIdx.x == 0) sh_group = atomicAdd(ticket, 1u);
   __syncthreads();
-  const uint32_t tile = sh_tile;
-  const uint32_t r = sh_read;
-  const int32_t L = static_cast<int32_t>(lens[r] - k + 1);  // k-mer positions, >= W
-  const int32_t q0 =
-      static_cast<int32_t>((tile_off[first_read] + tile - tile_off[r]) * kSketchTile);
-  const int32_t q1 = min(q0 + static_cast<int32_t>(kSketchTile), L);
-
-  // ---- stage the packed words of positions [q0 - H, q1 + H) (+ k - 1 bases) ----
-  const uint64_t* rw = words + woff[r];
-  const uint32_t nwords = static_cast<uint32_t>(woff[r + 1] - woff[r]);
-  const int32_t p_lo = max(q0 - H, 0);
-  const uint32_t w_lo = static_cast<uint32_t>(p_lo) >> 5;
-  const uint32_t w_hi = ((static_cast<uint32_t>(min(q1 + H, L)) - 1 + k - 1) >> 5) + 2;
-  for (uint32_t i = w_lo + threadIdx.x; i < w_hi; i += kSketchThreads) {
-    sh_words[i - w_lo] = i < nwords ? __ldg(rw + i) : 0ULL;
-  }
-  __syncthreads();
+  const uint32_t group = sh_group;
+  const uint64_t t_first = static_cast<uint64_t>(group) * G;
+  const int g_count = static_cast<int>(min(static_cast<uint64_t>(G), n_tiles - t_first));
+  const uint64_t tile_base = tile_off[first_read];
+  const bool one_read = last_read - first_read == 1;  // e.g. an external query: no table
 
   const uint32_t mask = (1u << (2 * k)) - 1u;
   const uint32_t rshift = 32 - 2 * k;
@@ -384,100 +373,130 @@ SketchFastKernel(const uint64_t* __restrict__ words, const uint64_t* __restrict_
     return fw == rv ? kBad : h;  // palindromic k-mers never enter a window
   };
 
-  // ---- own positions: 8 consecutive k-mers out of one 64-bit funnel ----
-  const int32_t qa = q0 + static_cast<int32_t>(threadIdx.x) * ITEMS;
-  uint32_t own[ITEMS];
-  uint32_t strands = 0;
-  {
-    const uint32_t wi = (static_cast<uint32_t>(qa) >> 5) - w_lo;
-    const uint32_t sh = (static_cast<uint32_t>(qa) & 31) << 1;
-    uint64_t lo = 0;
-    if (qa < q1) {
-      lo = sh_words[wi] >> sh;
-      if (sh) lo |= sh_words[wi + 1] << (64 - sh);
-    }
-    const uint32_t lo_lo = static_cast<uint32_t>(lo), lo_hi = static_cast<uint32_t>(lo >> 32);
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      uint32_t st;
-      const uint32_t h = hash_of(__funnelshift_r(lo_lo, lo_hi, 2 * i), &st);
-      own[i] = qa + i < q1 ? h : kBad;
-      strands |= st << i;
-    }
-  }
-  {  // 16-byte stores: slot of position qa is H + 8 * thread
-    uint32_t* dst = sh_hash + H + threadIdx.x * ITEMS;
-#pragma unroll
-    for (int i = 0; i < ITEMS; ++i) dst[i] = own[i];
-  }
-  // ---- halo positions of the tile: H on each side, one thread each ----
-  if (threadIdx.x < 2 * H) {
-    const bool left = threadIdx.x < H;
-    const int32_t p = left ? q0 - H + static_cast<int32_t>(threadIdx.x)
-                           : q0 + static_cast<int32_t>(kSketchTile) +
-                                 static_cast<int32_t>(threadIdx.x) - H;
-    uint32_t h = kBad;
-    if (p >= 0 && p < L) {
-      const uint32_t wi = (static_cast<uint32_t>(p) >> 5) - w_lo;
-      const uint32_t sh = (static_cast<uint32_t>(p) & 31) << 1;
-      uint64_t lo = sh_words[wi] >> sh;
-      if (sh) lo |= sh_words[wi + 1] << (64 - sh);
-      uint32_t st;
-      h = hash_of(static_cast<uint32_t>(lo), &st);
-    }
-    sh_hash[left ? threadIdx.x : H + kSketchTile + threadIdx.x - H] = h;
-  }
-  __syncthreads();
+  uint32_t flags[G], strands[G], ex[G], tot[G], rd[G];
+  int32_t qa_of[G];
 
-  // ---- select ----
-  // (every window of an interior tile lies inside the read: no bounds tests)
-  const bool interior = q0 >= H && q0 + static_cast<int32_t>(kSketchTile) + H <= L;
-  uint32_t flags = 0;
-  if (qa < q1) {
-    uint32_t h[N];
-    const uint32_t* src = sh_hash + threadIdx.x * ITEMS;  // slot of position qa - H
 #pragma unroll
-    for (int j = 0; j < N; ++j) h[j] = src[j];
-    // minimum of the window starting at slot j (positions qa - H + j .. + W - 1),
-    // 0 if the window leaves [0, L)
-    uint32_t wm[ITEMS + H];
+  for (int g = 0; g < G; ++g) {
+    flags[g] = strands[g] = ex[g] = tot[g] = rd[g] = 0;
+    qa_of[g] = 0;
+    if (g < g_count) {  // (uniform over the CTA)
+      const uint64_t t = t_first + g;
+      const uint32_t r = one_read ? first_read : tile_read[tile_base + t];
+      rd[g] = r;
+      const int32_t L = static_cast<int32_t>(lens[r] - k + 1);  // k-mer positions, >= W
+      const int32_t q0 = static_cast<int32_t>((tile_base + t - tile_off[r]) * kSketchTile);
+      const int32_t q1 = min(q0 + static_cast<int32_t>(kSketchTile), L);
+      uint32_t* sh_hash = sh_hash_all[g];
+
+      // ---- stage the packed words of positions [q0 - H, q1 + H) (+ k - 1 bases) ----
+      const uint64_t* rw = words + woff[r];
+      const uint32_t nwords = static_cast<uint32_t>(woff[r + 1] - woff[r]);
+      const int32_t p_lo = max(q0 - H, 0);
+      const uint32_t w_lo = static_cast<uint32_t>(p_lo) >> 5;
+      const uint32_t w_hi = ((static_cast<uint32_t>(min(q1 + H, L)) - 1 + k - 1) >> 5) + 2;
+      __syncthreads();  // the previous tile is done with sh_words
+      for (uint32_t i = w_lo + threadIdx.x; i < w_hi; i += kSketchThreads) {
+        sh_words[i - w_lo] = i < nwords ? __ldg(rw + i) : 0ULL;
+      }
+      __syncthreads();
+
+      // ---- own positions: 8 consecutive k-mers out of one 64-bit funnel ----
+      const int32_t qa = q0 + static_cast<int32_t>(threadIdx.x) * ITEMS;
+      qa_of[g] = qa;
+      {
+        const uint32_t wi = (static_cast<uint32_t>(qa) >> 5) - w_lo;
+        const uint32_t sh = (static_cast<uint32_t>(qa) & 31) << 1;
+        uint64_t lo = 0;
+        if (qa < q1) {
+          lo = sh_words[wi] >> sh;
+          if (sh) lo |= sh_words[wi + 1] << (64 - sh);
+        }
+        const uint32_t lo_lo = static_cast<uint32_t>(lo), lo_hi = static_cast<uint32_t>(lo >> 32);
+        uint32_t st_bits = 0;
+        uint32_t* dst = sh_hash + H + threadIdx.x * ITEMS;  // slot of position qa
 #pragma unroll
-    for (int j = 0; j < ITEMS + H; ++j) {
-      uint32_t v = h[j];
+        for (int i = 0; i < ITEMS; ++i) {
+          uint32_t st;
+          const uint32_t h = hash_of(__funnelshift_r(lo_lo, lo_hi, 2 * i), &st);
+          dst[i] = qa + i < q1 ? h : kBad;
+          st_bits |= st << i;
+        }
+        strands[g] = st_bits;
+      }
+      // ---- halo positions of the tile: H on each side, one thread each ----
+      if (threadIdx.x < 2 * H) {
+        const bool left = threadIdx.x < H;
+        const int32_t p = left ? q0 - H + static_cast<int32_t>(threadIdx.x)
+                               : q0 + static_cast<int32_t>(kSketchTile) +
+                                     static_cast<int32_t>(threadIdx.x) - H;
+        uint32_t h = kBad;
+        if (p >= 0 && p < L) {
+          const uint32_t wi = (static_cast<uint32_t>(p) >> 5) - w_lo;
+          const uint32_t sh = (static_cast<uint32_t>(p) & 31) << 1;
+          uint64_t lo = sh_words[wi] >> sh;
+          if (sh) lo |= sh_words[wi + 1] << (64 - sh);
+          uint32_t st;
+          h = hash_of(static_cast<uint32_t>(lo), &st);
+        }
+        sh_hash[left ? threadIdx.x : H + kSketchTile + threadIdx.x - H] = h;
+      }
+      __syncthreads();
+
+      // ---- select ----
+      // (every window of an interior tile lies inside the read: no bounds tests)
+      const bool interior = q0 >= H && q0 + static_cast<int32_t>(kSketchTile) + H <= L;
+      uint32_t fl = 0;
+      if (qa < q1) {
+        uint32_t h[N];
+        const uint32_t* src = sh_hash + threadIdx.x * ITEMS;  // slot of position qa - H
 #pragma unroll
-      for (int t = 1; t < W; ++t) v = min(v, h[j + t]);
-      const int32_t s0 = qa - H + j;
-      wm[j] = (interior || (s0 >= 0 && s0 + W <= L)) ? v : 0u;
-    }
+        for (int j = 0; j < N; ++j) h[j] = src[j];
+        // minimum of the window starting at slot j (positions qa - H + j .. + W - 1),
+        // 0 if the window leaves [0, L)
+        uint32_t wm[ITEMS + H];
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      uint32_t best = wm[i];
+        for (int j = 0; j < ITEMS + H; ++j) {
+          uint32_t v = h[j];
 #pragma unroll
-      for (int d = 1; d <= H; ++d) best = max(best, wm[i + d]);
-      const uint32_t hq = h[H + i];
-      if (best == hq && hq != kBad) flags |= 1u << i;
+          for (int t2 = 1; t2 < W; ++t2) v = min(v, h[j + t2]);
+          const int32_t s0 = qa - H + j;
+          wm[j] = (interior || (s0 >= 0 && s0 + W <= L)) ? v : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+          uint32_t best = wm[i];
+#pragma unroll
+          for (int d = 1; d <= H; ++d) best = max(best, wm[i + d]);
+          const uint32_t hq = h[H + i];
+          if (best == hq && hq != kBad) fl |= 1u << i;
+        }
+      }
+      flags[g] = fl;
+      uint32_t total;
+      ex[g] = BlockExclusiveSum<uint32_t, kSketchThreads>(__popc(fl), sh_scan, &total);
+      tot[g] = total;
     }
   }
+  uint32_t group_total = 0;
+#pragma unroll
+  for (int g = 0; g < G; ++g) group_total += tot[g];
 
-  uint32_t total;
-  const uint32_t ex =
-      BlockExclusiveSum<uint32_t, kSketchThreads>(__popc(flags), sh_scan, &total);
-
-  // ---- output offset: decoupled look-back by the first warp ----
+  // ---- output offset of the group: decoupled look-back by the first warp ----
   if (threadIdx.x < 32) {
     const uint32_t lane = threadIdx.x;
     uint64_t excl = 0;
     volatile uint64_t* st = status;
-    if (tile > 0) {
+    if (group > 0) {
       if (lane == 0) {
-        st[tile] = kStAggregate | total;
+        st[group] = kStAggregate | group_total;
         __threadfence();
       }
       __syncwarp();
-      int64_t idx = static_cast<int64_t>(tile) - 1;
+      int64_t idx = static_cast<int64_t>(group) - 1;
       while (true) {
         const int64_t mine = idx - lane;
-        uint64_t v = kStPrefix;  // before tile 0: an empty prefix
+        uint64_t v = kStPrefix;  // before group 0: an empty prefix
         if (mine >= 0) {
           do {
             v = st[mine];
@@ -494,24 +513,36 @@ SketchFastKernel(const uint64_t* __restrict__ words, const uint64_t* __restrict_
       }
     }
     if (lane == 0) {
-      st[tile] = kStPrefix | (excl + total);
-      tile_out[tile] = excl;
-      if (tile + 1 == n_tiles) tile_out[n_tiles] = excl + total;
+      st[group] = kStPrefix | (excl + group_total);
+      uint64_t run = excl;
+      for (int g = 0; g < g_count; ++g) {
+        tile_out[t_first + g] = run;
+        run += tot[g];
+      }
+      if (t_first + g_count == n_tiles) tile_out[n_tiles] = run;
       sh_excl = excl;
     }
   }
   __syncthreads();
-  uint64_t dst = sh_excl + ex;
-  const uint64_t id = static_cast<uint64_t>(ids[r]) << 32;
+  uint64_t base = sh_excl;
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    if ((flags >> i) & 1u) {
-      if (dst < out_cap) {
-        out_val[dst] = own[i];
-        out_org[dst] = id | (static_cast<uint64_t>(static_cast<uint32_t>(qa + i)) << 1) |
-                       ((strands >> i) & 1u);
+  for (int g = 0; g < G; ++g) {
+    if (g < g_count) {
+      uint64_t dst = base + ex[g];
+      const uint64_t id = static_cast<uint64_t>(ids[rd[g]]) << 32;
+      const uint32_t* own = sh_hash_all[g] + H + threadIdx.x * ITEMS;
+#pragma unroll
+      for (int i = 0; i < ITEMS; ++i) {
+        if ((flags[g] >> i) & 1u) {
+          if (dst < out_cap) {
+            out_val[dst] = own[i];
+            out_org[dst] = id | (static_cast<uint64_t>(static_cast<uint32_t>(qa_of[g] + i)) << 1) |
+                           ((strands[g] >> i) & 1u);
+          }
+          ++dst;
+        }
       }
-      ++dst;
+      base += tot[g];
     }
   }
 }
@@ -706,7 +737,9 @@ void EnsureSketch(Ctx& c, uint32_t first, uint32_t last) {
       uint64_t* org = c.s_org.reserve(cap);
       RVN_CUDA(cudaMemsetAsync(status, 0, (n_tiles + 2) * sizeof(uint64_t), c.stream));
       if (k32 && c.prm.w == 5) {  // raven's default window: the fast kernel
-        SketchFastKernel<5><<<static_cast<unsigned>(n_tiles), kSketchThreads, 0, c.stream>>>(
+        // (status words of this kernel: one per group of kFastGroup tiles)
+        SketchFastKernel<5><<<static_cast<unsigned>((n_tiles + kFastGroup - 1) / kFastGroup),
+                              kSketchThreads, 0, c.stream>>>(
             c.d_words.get(), c.d_woff.get(), c.d_len.get(), c.d_ids.get(),
             c.d_tile_off.get(), c.d_tile_read.get(), first, last, c.prm.k, ticket, status, tout,
             n_tiles, cap, reinterpret_cast<uint32_t*>(val), org);

@@ -210,6 +210,26 @@ class Oracle(_Flat):
                                     cov_off=np.uint64, status=np.uint8, cells=np.uint64,
                                     seconds=np.float64))
 
+    def polish(self, targets, sequences, q=0.0, e=0.3, w=500, trim=True, m=3, n=-5, g=-4,
+               threads=4):
+        """racon::Polisher (oracle): polished targets as ASCII + names + stats."""
+        L = self.lib
+        L.orc_polish.restype = C.c_void_p
+        L.orc_polish.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_uint32,
+                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32]
+        t, s = self.reads(targets), self.reads(sequences)
+        # names "Utg<i>" / "r<i>" like the product's host shim
+        L.orc_reads_set_names.argtypes = [C.c_void_p, C.c_char_p]
+        L.orc_reads_set_names(t.h, b"Utg")
+        L.orc_reads_set_names(s.h, b"r")
+        bag = L.orc_polish(t.h, s.h, q, e, w, int(trim), m, n, g, threads)
+        r = self.unbag(bag, dict(sequences=np.uint8, seq_off=np.uint64, names=np.uint8,
+                                 stats=np.float64))
+        names = r["names"].tobytes().decode().split("\n")[:-1]
+        seqs = [r["sequences"][int(r["seq_off"][i]):int(r["seq_off"][i + 1])].tobytes()
+                for i in range(len(names))]
+        return names, seqs, r["stats"]
+
     def edit_distance(self, a: bytes, b: bytes) -> int:
         return self.lib.orc_edit_distance(a, len(a), b, len(b))
 

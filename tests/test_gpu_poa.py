@@ -101,3 +101,29 @@ def test_poa_rejects_bad_input(gpu_engine):
                  seq_end=np.zeros(0, np.uint32))
     got = gpu_engine.poa_batch(empty)
     assert got["cons_off"].tolist() == [0]
+
+
+def test_polisher_facade_equals_oracle_polisher(oracle):
+    """racon::Polisher::Polish (polish.cc:43-51) through the product facade (GPU map +
+    host edlib path + GPU POA) == the oracle polisher (CPU): same polished targets,
+    same name tags, on ONT-like reads over draft contigs, with and without qualities."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from bench import synth as bsynth
+    from raven_b200 import polish
+    reads = bsynth.make_reads(77, 60_000, 240, 5000, min_len=1500)
+    draft = bsynth.make_contigs(77, 60_000, contig_len=25_000)
+    assert draft.n == 3
+    for with_q in (False, True):
+        if with_q:
+            rng = np.random.default_rng(1)
+            nb = (reads.lens.astype(np.int64) + 63) // 64
+            reads.block_quality = rng.integers(6, 20, int(nb.sum())).astype(np.uint8)
+            reads.bq_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.uint64)
+        q = 10.0 if with_q else 0.0
+        got, st = polish.polish(draft, reads, q=q, threads=4)
+        names, seqs, ost = oracle.polish(draft, reads, q=q, threads=8)
+        assert got.names == names
+        assert [got.ascii(i) for i in range(got.n)] == seqs
+        assert st["windows"] == int(ost[0]) and st["polished_windows"] == int(ost[1])
+        assert st["polished_windows"] > 100
