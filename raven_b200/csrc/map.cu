@@ -353,7 +353,8 @@ __device__ uint32_t ChainRead(const ChainWork<IdxT>& wk, uint32_t n,
                               const ChainParams& cp, uint32_t* sm32,
                               rvn_overlap* __restrict__ ovl_raw,
                               unsigned long long* __restrict__ ovl_counter,
-                              uint64_t ovl_cap, uint64_t* out_base) {
+                              uint64_t ovl_cap, uint64_t* out_base,
+                              uint64_t* __restrict__ ovl_key = nullptr, uint64_t key_hi = 0) {
   uint64_t* G = wk.G;
   uint64_t* P = wk.P;
   __shared__ unsigned long long sh_base;
@@ -576,6 +577,9 @@ __device__ uint32_t ChainRead(const ChainWork<IdxT>& wk, uint32_t n,
     const uint32_t ex = BlockExclusiveSum<uint32_t, THREADS>(mine, sm32, &tot);
     if (mine) {
       rvn_overlap* dst = ovl_raw + base + carry + ex;
+      // (pair-at-a-time callers: emission sequence number of every overlap)
+      uint64_t* kdst = ovl_key ? ovl_key + base + carry + ex : nullptr;
+      uint32_t seq = carry + ex;
       const uint32_t jb = wk.IB[b];
       const uint32_t longest = wk.IE[b];
       const uint64_t* Pb = P + jb;
@@ -621,6 +625,7 @@ __device__ uint32_t ChainRead(const ChainWork<IdxT>& wk, uint32_t n,
               o.score = min(lm, rm);
               o.strand = strand;
               *dst++ = o;
+              if (kdst) *kdst++ = key_hi | seq++;
             }
           }
           l = kk;
@@ -632,8 +637,10 @@ __device__ uint32_t ChainRead(const ChainWork<IdxT>& wk, uint32_t n,
   return total;
 }
 
-constexpr uint32_t kChainSmemCap = 8191;   // hits per read on the split path
-constexpr uint32_t kChainMaxGroup = 2048;  // larger (rhs, strand) pairs -> generic path
+constexpr uint32_t kChainSmemCap = 65535;  // hits per read on the split path (16-bit offsets)
+constexpr uint32_t kSplitMaxTable = 8192;  // pair hash table entries per read, at most
+constexpr uint32_t kPairMaxHits = 8191;    // hits of one pair PairChainKernel holds on chip
+constexpr uint32_t kThreadPairMax = 48;   // larger (rhs, strand) pairs get a CTA each
 
 // ---------------------------------------------------------------------------
 // Fast path, two kernels.
@@ -671,10 +678,10 @@ __host__ __device__ inline SplitLayout MakeSplitLayout(uint32_t n) {
   // does fill up: a random key match drags in every read covering that locus,
   // so single-hit pairs are about as many as half the hits.)
   uint32_t hs = 64;
-  while (hs < n + 1) hs <<= 1;
-  L.hs = hs;
+  while (hs < n + 1 && hs < kSplitMaxTable) hs <<= 1;
+  L.hs = hs;  // (reads beyond 8191 hits: a full table sends the read to the generic path)
   uint32_t gpad = 2;
-  while (gpad < n / 4 + 1) gpad <<= 1;
+  while (gpad < n / 4 + 1 && gpad < hs) gpad <<= 1;
   L.gpad = gpad;
   size_t o = 0;
   L.hk = o; o += 4ULL * hs;
@@ -730,14 +737,23 @@ SplitKernel(const uint64_t* __restrict__ h_grp, const uint64_t* __restrict__ h_p
   for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
     const uint32_t gid = static_cast<uint32_t>(hg[i] >> 32);
     uint32_t s = HashGid(gid) & hmask;
+    uint32_t probes = 0;
     while (true) {
       const uint32_t prev = atomicCAS(&HK[s], 0xFFFFFFFFu, gid);
       if (prev == 0xFFFFFFFFu || prev == gid) break;
       s = (s + 1) & hmask;
+      if (++probes > hmask) {  // table full (only possible beyond 8191 hits)
+        sh_bail = 1;
+        break;
+      }
     }
-    atomicAdd(&HC[s], 1u);
+    if (probes <= hmask) atomicAdd(&HC[s], 1u);
   }
   __syncthreads();
+  if (sh_bail) {  // more distinct pairs than the table holds: the generic kernel
+    if (threadIdx.x == 0) fallback_list[atomicAdd(fallback_cnt, 1u)] = r;
+    return;
+  }
 
   // ---- pairs with >= 4 hits: list + offsets inside the read's kept hits ----
   uint32_t carry = 0;  // low 16: pairs so far, high 16: kept hits so far
@@ -745,7 +761,7 @@ SplitKernel(const uint64_t* __restrict__ h_grp, const uint64_t* __restrict__ h_p
     const uint32_t s = b + threadIdx.x;
     const uint32_t cnt = s < L.hs ? HC[s] : 0;
     const uint32_t keep = cnt >= 4;
-    if (cnt > kChainMaxGroup) sh_bail = 1;
+    if (cnt > kPairMaxHits) sh_bail = 1;  // (a pair PairChainKernel cannot hold on chip)
     uint32_t tot;
     const uint32_t ex = BlockExclusiveSum<uint32_t, THREADS>(
         keep ? ((cnt << 16) | 1u) : 0u, sm32, &tot);
@@ -1031,6 +1047,57 @@ __global__ void GroupChainKernel(const GroupDesc* __restrict__ desc,
   }
 }
 
+// One CTA per (query, rhs, strand) pair with more than kThreadPairMax hits - the
+// true overlaps, above all on HiFi reads where a pair holds hundreds of hits: the
+// pair's hits live in shared memory, both orders come from parallel bitonic
+// sorts and the bands from block scans (ChainRead); only the LIS of a band is one
+// thread's work. CTA blockIdx.x handles pair order[first + blockIdx.x]; every
+// pair of a launch has at most npad - 1 hits.
+constexpr int kPairThreads = 64;
+
+__host__ __device__ inline size_t PairChainSmem(uint32_t npad) {
+  const uint32_t n = npad - 1, nb = n / 4 + 1;
+  size_t o = 16ULL * npad;                        // G, P
+  o += 2ULL * (n + nb + 2) + 2ULL * (n + 1) + 2ULL * 2 * nb;  // LB, PD, IB, IE (u16)
+  o = (o + 3) & ~size_t(3);
+  o += 4ULL * nb;                                 // CNT
+  return (o + 15) & ~size_t(15);
+}
+
+__global__ void __launch_bounds__(kPairThreads)
+PairChainKernel(const GroupDesc* __restrict__ desc, const uint32_t* __restrict__ order,
+                uint64_t first, uint32_t npad, const uint32_t* __restrict__ g_diag,
+                const uint64_t* __restrict__ g_pos, ChainParams cp,
+                rvn_overlap* __restrict__ out, uint64_t* __restrict__ out_key,
+                unsigned long long* __restrict__ out_cnt, uint64_t out_cap) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ uint32_t sm32[34];
+  const uint32_t g = order[first + blockIdx.x];
+  const GroupDesc d = desc[g];
+  const uint32_t n = d.cnt;
+  const uint32_t ncap = npad - 1, nbmax = ncap / 4 + 1;
+  ChainWork<uint16_t> wk;
+  wk.G = reinterpret_cast<uint64_t*>(smem);
+  wk.P = wk.G + npad;
+  wk.LB = reinterpret_cast<uint16_t*>(wk.P + npad);
+  wk.PD = wk.LB + (ncap + nbmax + 2);
+  wk.IB = wk.PD + (ncap + 1);
+  wk.IE = wk.IB + nbmax;
+  wk.CNT = reinterpret_cast<uint32_t*>(
+      (reinterpret_cast<uintptr_t>(wk.IE + nbmax) + 3) & ~uintptr_t(3));
+  // padding beyond the pair's hits sorts last (all ones), like the reference's dummy
+  uint32_t np2 = 8;
+  while (np2 < n + 1) np2 <<= 1;
+  for (uint32_t i = threadIdx.x; i < np2; i += kPairThreads) {
+    wk.G[i] = i < n ? (static_cast<uint64_t>(d.gid) << 32) | g_diag[d.hit_off + i] : ~0ULL;
+    wk.P[i] = i < n ? g_pos[d.hit_off + i] : ~0ULL;
+  }
+  __syncthreads();
+  uint64_t base = 0;
+  ChainRead<uint16_t, kPairThreads>(wk, n, np2, d.lhs_id, cp, sm32, out, out_cnt, out_cap, &base,
+                                    out_key, static_cast<uint64_t>(g) << 16);
+}
+
 // first index of a descending-sorted count array with count <= bound[i]
 __global__ void SizeClassStarts(const uint32_t* __restrict__ sorted_cnt, uint64_t n,
                                 const uint32_t* __restrict__ bound, uint32_t n_bounds,
@@ -1179,7 +1246,7 @@ uint64_t ChainGroupedHits(Ctx& c, const uint64_t* hg, const uint64_t* hp,
   RVN_CUDA(cudaMemsetAsync(loc, 0, (nr + 1ULL) * sizeof(uint64_t), c.stream));
 
   // ---- fast path: split by (rhs, strand) pair, then one thread per pair ----
-  static const uint32_t kBounds[] = {256, 512, 1024, 2048, 4096, 8192};
+  static const uint32_t kBounds[] = {256, 512, 1024, 2048, 4096, 8192, 65536};
   constexpr int kClasses = sizeof(kBounds) / sizeof(kBounds[0]);
   std::vector<uint32_t> cls[kClasses];
   std::vector<uint32_t> big;
@@ -1251,7 +1318,7 @@ uint64_t ChainGroupedHits(Ctx& c, const uint64_t* hg, const uint64_t* hp,
         RVN_LAUNCH_CHECK();
         ++c.launches;
       }
-      // pair count, reads handed back (a pair with > kChainMaxGroup hits)
+      // pair count, reads handed back (pair table full / a pair beyond kPairMaxHits)
       uint64_t* hpin = c.pin64.reserve(8);
       RVN_CUDA(cudaMemcpyAsync(hpin, counter, 4 * sizeof(uint64_t),
                                cudaMemcpyDeviceToHost, c.stream));
@@ -1275,8 +1342,8 @@ uint64_t ChainGroupedHits(Ctx& c, const uint64_t* hg, const uint64_t* hp,
 
       if (n_groups) {
         // largest pairs first: lanes of a warp get pairs of similar size
-        // (stable descending radix sort on the 12 count bits, radix.cu)
-        const int w_desc = RadixSortPairs(c, dcnt, dcnt2, dcnt, didx, didx2, didx, n_groups, 0, 12,
+        // (stable descending radix sort on the 13 count bits, radix.cu)
+        const int w_desc = RadixSortPairs(c, dcnt, dcnt2, dcnt, didx, didx2, didx, n_groups, 0, 13,
                                           /*descending=*/true);
         const uint32_t* sorted_cnt = w_desc == 0 ? dcnt2 : dcnt;
         const uint32_t* sorted_idx = w_desc == 0 ? didx2 : didx;
@@ -1285,10 +1352,14 @@ uint64_t ChainGroupedHits(Ctx& c, const uint64_t* hg, const uint64_t* hp,
         uint64_t* key2 = c.m_okey2.reserve(ovl_cap);
         uint32_t* oidx = c.m_oidx.reserve(ovl_cap);
         uint32_t* oidx2 = c.m_oidx2.reserve(ovl_cap);
-        // one launch per size class of the (descending) pair order: shared
-        // memory per CTA = threads x class bound x 12 B
-        static const uint32_t kGB[] = {2048, 1024, 512, 256, 128, 96, 64, 48, 32, 24, 16, 8};
+        // One launch per size class of the (descending) pair order. Pairs with more
+        // than kThreadPairMax hits get a CTA each (PairChainKernel, shared memory
+        // by class); the many small ones a thread each (GroupChainKernel: shared
+        // memory per CTA = threads x class bound x 12 B).
+        static const uint32_t kGB[] = {8191, 4095, 2047, 1023, 511, 255, 127, 63,
+                                       kThreadPairMax, 32, 24, 16, 8};
         constexpr uint32_t kNB = sizeof(kGB) / sizeof(kGB[0]);
+        constexpr uint32_t kFirstThreadClass = 8;  // kGB[8] == kThreadPairMax
         uint32_t* d_bounds = c.m_bounds.reserve(kNB);
         uint64_t* d_starts = c.m_starts.reserve(kNB + 1);
         RVN_CUDA(cudaMemcpyAsync(d_bounds, kGB, sizeof(kGB), cudaMemcpyHostToDevice,
@@ -1299,19 +1370,30 @@ uint64_t ChainGroupedHits(Ctx& c, const uint64_t* hg, const uint64_t* hp,
                                  cudaMemcpyDeviceToHost, c.stream));
         RVN_CUDA(cudaStreamSynchronize(c.stream));
         h_starts[kNB] = n_groups;
+        h_starts[0] = 0;  // (a read has at most kChainSmemCap = 8191 hits on this path)
         RVN_CUDA(cudaFuncSetAttribute(GroupChainKernel,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       200 * 1024));
+        RVN_CUDA(cudaFuncSetAttribute(PairChainKernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(PairChainSmem(8192))));
         for (uint32_t b = 0; b < kNB; ++b) {
-          // pairs with bound[b+1] < count <= bound[b]  (class 0 starts at index 0)
-          const uint64_t lo = b == 0 ? 0 : h_starts[b], hi = h_starts[b + 1];
+          // pairs with bound[b+1] < count <= bound[b]
+          const uint64_t lo = h_starts[b], hi = h_starts[b + 1];
           if (hi <= lo) continue;
-          uint32_t threads = 128;
-          while (threads > 8 && 12ULL * kGB[b] * threads > 196 * 1024) threads >>= 1;
-          const size_t smem = 12ULL * kGB[b] * threads;
-          GroupChainKernel<<<CeilDiv(hi - lo, threads), threads, smem, c.stream>>>(
-              desc, sorted_idx, lo, hi, kGB[b], g_diag, g_pos, cp, tmp_ovl, key, ctr + 3,
-              ovl_cap);
+          if (b < kFirstThreadClass) {
+            const uint32_t npad = kGB[b] + 1;
+            PairChainKernel<<<static_cast<unsigned>(hi - lo), kPairThreads, PairChainSmem(npad),
+                              c.stream>>>(desc, sorted_idx, lo, npad, g_diag, g_pos, cp, tmp_ovl,
+                                          key, ctr + 3, ovl_cap);
+          } else {
+            uint32_t threads = 128;
+            while (threads > 8 && 12ULL * kGB[b] * threads > 196 * 1024) threads >>= 1;
+            const size_t smem = 12ULL * kGB[b] * threads;
+            GroupChainKernel<<<CeilDiv(hi - lo, threads), threads, smem, c.stream>>>(
+                desc, sorted_idx, lo, hi, kGB[b], g_diag, g_pos, cp, tmp_ovl, key, ctr + 3,
+                ovl_cap);
+          }
           RVN_LAUNCH_CHECK();
           ++c.launches;
         }

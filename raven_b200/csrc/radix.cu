@@ -237,27 +237,45 @@ OnesweepPass(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
       asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(st4 + my4),
                    "r"(agg.x), "r"(agg.y), "r"(agg.z), "r"(agg.w)
                    : "memory");
+      // kLook predecessors per round, their loads in flight together: one
+      // dependent L2 round trip per tile would make the walk slower than the rate
+      // at which tiles start, and the chain would grow to every tile in flight
+      constexpr int kLook = 4;
       uint32_t open = 0xF;  // chains still walking
       int64_t p = static_cast<int64_t>(tile) - 1;
       while (open) {
-        uint4 v;
-        const uint4* src = st4 + static_cast<uint64_t>(p) * (kBins / 4) + threadIdx.x;
-        do {  // every status word of the tile must have been written
-          asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                       : "l"(src)
-                       : "memory");
-        } while (((v.x & kFlagMask) == 0) || ((v.y & kFlagMask) == 0) ||
-                 ((v.z & kFlagMask) == 0) || ((v.w & kFlagMask) == 0));
-        const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+        uint4 v[kLook];
 #pragma unroll
-        for (int j = 0; j < kBinsPerThread; ++j) {
-          if (open & (1u << j)) {
-            excl[j] += vv[j] & kValueMask;
-            if ((vv[j] & kFlagMask) == kFlagPrefix) open &= ~(1u << j);
+        for (int u = 0; u < kLook; ++u) {
+          const int64_t q = p - u;
+          if (q >= 0) {
+            const uint4* src = st4 + static_cast<uint64_t>(q) * (kBins / 4) + threadIdx.x;
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w)
+                         : "l"(src)
+                         : "memory");
+          } else {  // before tile 0: empty prefixes
+            v[u] = make_uint4(kFlagPrefix, kFlagPrefix, kFlagPrefix, kFlagPrefix);
           }
         }
-        --p;  // (tile 0 publishes prefixes only: every chain ends there at the latest)
+        int used = 0;
+#pragma unroll
+        for (int u = 0; u < kLook; ++u) {
+          const uint32_t vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+          const bool ready = (vv[0] & kFlagMask) && (vv[1] & kFlagMask) && (vv[2] & kFlagMask) &&
+                             (vv[3] & kFlagMask);
+          if (used == u && ready && open) {  // (in order; stop at the first unwritten tile)
+#pragma unroll
+            for (int j = 0; j < kBinsPerThread; ++j) {
+              if (open & (1u << j)) {
+                excl[j] += vv[j] & kValueMask;
+                if ((vv[j] & kFlagMask) == kFlagPrefix) open &= ~(1u << j);
+              }
+            }
+            used = u + 1;
+          }
+        }
+        p -= used;  // (used == 0: the nearest tile has not published yet - poll again)
       }
     }
     uint4 pre;

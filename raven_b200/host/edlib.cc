@@ -175,6 +175,58 @@ int BandedDistance(const unsigned char* q, int m, const unsigned char* t, int n,
   return d <= k ? d : -1;
 }
 
+// D[r][cols] for r = 0..m inside the band |row - column| <= k (block granularity),
+// a large value outside: the forward / backward columns of the Hirschberg split.
+// Every entry <= k is exact, and a row on an optimal path of a problem whose
+// distance is k lies inside the band.
+void BandedColumns(const unsigned char* q, int m, const unsigned char* t, int cols, int k,
+                   std::vector<std::int32_t>* scores) {
+  constexpr std::int32_t kFar = 1 << 29;
+  scores->assign(static_cast<std::size_t>(m) + 1, kFar);
+  const Peq peq(q, m);
+  const int blocks = peq.blocks;
+  const int last_bits = m - (blocks - 1) * kWord;
+  const std::uint64_t last_high = 1ULL << (last_bits - 1);
+  std::vector<std::uint64_t> pv(blocks), mv(blocks);
+  std::vector<std::int32_t> bottom(blocks);
+  auto rows_of = [&](int b) { return b == blocks - 1 ? last_bits : kWord; };
+  int lo = 0;
+  int hi = (std::min(m, std::max(1, k)) - 1) / kWord;
+  for (int b = 0; b <= hi; ++b) {
+    pv[b] = ~0ULL;
+    mv[b] = 0;
+    bottom[b] = std::min(m, (b + 1) * kWord);
+  }
+  for (int j = 1; j <= cols; ++j) {
+    const int want_hi = (std::min(m, j + k) - 1) / kWord;
+    while (hi < want_hi) {
+      ++hi;
+      pv[hi] = ~0ULL;
+      mv[hi] = 0;
+      bottom[hi] = bottom[hi - 1] + rows_of(hi);
+    }
+    const int want_lo = (std::max(1, j - k) - 1) / kWord;
+    if (want_lo > lo) lo = want_lo;
+    const std::uint64_t* eq = peq.of(t[j - 1]);
+    int h = 1;
+    for (int b = lo; b <= hi; ++b) {
+      h = Step(eq[b], h, b == blocks - 1 ? last_high : (1ULL << 63), pv[b], mv[b]);
+      bottom[b] += h;
+    }
+  }
+  // rows of the blocks still in the band, from each block's bottom upwards
+  if (lo == 0 && cols <= k) (*scores)[0] = cols;
+  for (int b = lo; b <= hi; ++b) {
+    const int rows = rows_of(b);
+    std::int32_t v = bottom[b];
+    for (int bit = rows - 1; bit >= 0; --bit) {
+      (*scores)[static_cast<std::size_t>(b) * kWord + bit + 1] = v;
+      v -= static_cast<std::int32_t>((pv[b] >> bit) & 1) -
+           static_cast<std::int32_t>((mv[b] >> bit) & 1);
+    }
+  }
+}
+
 int GlobalDistance(const unsigned char* q, int m, const unsigned char* t, int n,
                    int k_limit) {
   if (m == 0) return (k_limit < 0 || n <= k_limit) ? n : -1;
@@ -250,13 +302,14 @@ void ObtainAlignment(const unsigned char* q, int m, const unsigned char* t, int 
     return;
   }
   const int left = n / 2, right = n - left;
+  // (banded by the known distance: rows off the band cannot lie on an optimal path)
   std::vector<std::int32_t> fw, bw;
-  FullColumns(q, m, t, left, nullptr, &fw);
+  BandedColumns(q, m, t, left, best, &fw);
   {
     std::vector<unsigned char> rq(q, q + m), rt(t + left, t + n);
     std::reverse(rq.begin(), rq.end());
     std::reverse(rt.begin(), rt.end());
-    FullColumns(rq.data(), m, rt.data(), right, nullptr, &bw);
+    BandedColumns(rq.data(), m, rt.data(), right, best, &bw);
   }
   // bw[m - r] = distance of q[r, m) and t[left, n)
   int split = -1;
