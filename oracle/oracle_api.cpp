@@ -374,3 +374,7 @@ ORC_EXPORT void orc_reads_set_names(orc_reads* r, const char* prefix) {
     r->seqs[i]->name = std::string(prefix) + std::to_string(i);
   }
 }
+
+// AVX2 int16 matrix fill in the oracle's spoa (the CPU legs of the benches time
+// the SIMD engine like upstream spoa's; the tests check both ways agree)
+ORC_EXPORT void orc_spoa_use_simd(int on) { spoa::AlignmentEngine::UseSimd(on != 0); }

@@ -107,6 +107,10 @@ class Graph {
 class AlignmentEngine {
  public:
   AlignmentEngine(std::int8_t m, std::int8_t n, std::int8_t g) : m_(m), n_(n), g_(g) {}
+  // fill the matrix with AVX2 int16 rows (16 cells per instruction, the horizontal
+  // gap recurrence as a prefix maximum) like upstream spoa's SIMD engine, whenever
+  // the worst-case score fits int16; same cell values, same traceback
+  static void UseSimd(bool on);
   Alignment Align(const char* sequence, std::uint32_t sequence_len,
                   const Graph& graph, std::int32_t* score = nullptr);
   // DP cells evaluated so far (for GCUPS figures)
@@ -115,7 +119,9 @@ class AlignmentEngine {
  private:
   std::int8_t m_, n_, g_;
   std::uint64_t cells_ = 0;
+  bool FillSimd16(const char* sequence, std::uint32_t sequence_len, const Graph& graph);
   std::vector<std::int32_t> H_;
+  std::vector<std::int16_t> H16_, profile16_;
   std::vector<std::int32_t> profile_;
   std::vector<std::uint32_t> node_id_to_rank_;
 };

@@ -371,6 +371,123 @@ std::string Graph::GenerateConsensus(std::vector<std::uint32_t>* coverages) {
 // ---------------------------------------------------------------------------
 // global alignment, linear gaps
 // ---------------------------------------------------------------------------
+namespace {
+bool g_use_simd = false;
+}
+void AlignmentEngine::UseSimd(bool on) { g_use_simd = on; }
+
+#if defined(__AVX2__)
+}  // namespace spoa
+#include <immintrin.h>
+namespace spoa {
+
+namespace {
+
+// v shifted up by one 16-bit lane, lane 0 = `fill` (across the two 128-bit halves)
+inline __m256i ShiftUp1(__m256i v, __m256i fill) {
+  const __m256i t = _mm256_permute2x128_si256(fill, v, 0x21);  // [fill.hi | v.lo]
+  return _mm256_alignr_epi8(v, t, 14);
+}
+inline __m256i ShiftUpN(__m256i v, __m256i fill, int n) {  // n in {1, 2, 4, 8}
+  const __m256i t = _mm256_permute2x128_si256(fill, v, 0x21);
+  switch (n) {
+    case 1: return _mm256_alignr_epi8(v, t, 14);
+    case 2: return _mm256_alignr_epi8(v, t, 12);
+    case 4: return _mm256_alignr_epi8(v, t, 8);
+    default: return t;  // 8 lanes = one 128-bit half
+  }
+}
+
+}  // namespace
+
+// Same cell values as the scalar loops of Align, 16 int16 cells at a time:
+//   x[j]   = max over predecessors p of max(H[p][j-1] + profile[j], H[p][j] + g)
+//   H[i][j] = max(x[j], H[i][j-1] + g) = j*g + prefix_max_k<=j (x[k] - k*g)
+// H16_ rows are `stride` wide (a multiple of 16, 16 spare lanes on the left so
+// that column -1 reads are harmless).
+bool AlignmentEngine::FillSimd16(const char* sequence, std::uint32_t sequence_len,
+                                 const Graph& graph) {
+  const auto& rank_to_node = graph.rank_to_node();
+  const std::uint64_t width = sequence_len + 1ULL;
+  const std::uint64_t height = graph.nodes().size() + 1ULL;
+  const int amax = std::max(std::max(std::abs(m_), std::abs(n_)), std::abs(g_));
+  if (static_cast<std::uint64_t>(amax) * (2 * width + height + 32) > 32000) return false;
+  const std::uint64_t stride = ((width + 15) / 16) * 16 + 16;  // 16 guard lanes in front
+  constexpr std::int16_t kNeg = -32000;
+  H16_.assign(stride * height, kNeg);
+  profile16_.assign(graph.num_codes() * stride, 0);
+  for (std::uint32_t c = 0; c < graph.num_codes(); ++c) {
+    for (std::uint64_t j = 0; j < sequence_len; ++j) {
+      profile16_[c * stride + 16 + (j + 1)] =
+          (static_cast<std::int32_t>(c) == graph.coder(sequence[j])) ? m_ : n_;
+    }
+  }
+  auto row_of = [&](std::uint64_t i) { return H16_.data() + i * stride + 16; };
+  for (std::uint64_t j = 0; j < width; ++j) row_of(0)[j] = static_cast<std::int16_t>(j * g_);
+  for (std::uint64_t i = 1; i < height; ++i) {
+    const auto& edges = rank_to_node[i - 1]->inedges;
+    std::int32_t penalty = edges.empty() ? 0 : -1000000;
+    for (const auto& it : edges) {
+      penalty = std::max<std::int32_t>(penalty, row_of(node_id_to_rank_[it->tail->id] + 1)[0]);
+    }
+    row_of(i)[0] = static_cast<std::int16_t>(penalty + g_);
+  }
+  // j * g per lane, and the per-vector step 16 * g
+  alignas(32) std::int16_t ramp[16];
+  for (int l = 0; l < 16; ++l) ramp[l] = static_cast<std::int16_t>(l * g_);
+  const __m256i vramp = _mm256_load_si256(reinterpret_cast<const __m256i*>(ramp));
+  const __m256i vg = _mm256_set1_epi16(g_);
+  const __m256i vneg = _mm256_set1_epi16(kNeg);
+  const std::uint64_t nvec = (width + 15) / 16;
+  for (const auto& it : rank_to_node) {
+    const std::uint64_t i = node_id_to_rank_[it->id] + 1;
+    std::int16_t* row = row_of(i);
+    const std::int16_t* prof = profile16_.data() + it->code * stride + 16;
+    const std::int16_t col0 = row[0];
+    const std::size_t np = std::max<std::size_t>(1, it->inedges.size());
+    std::int16_t carry = kNeg;  // prefix max of x[k] - k*g over the vectors before
+    for (std::uint64_t v = 0; v < nvec; ++v) {
+      const std::uint64_t j0 = v * 16;
+      __m256i x = vneg;
+      for (std::size_t p = 0; p < np; ++p) {
+        const std::uint64_t pred_i =
+            it->inedges.empty() ? 0 : node_id_to_rank_[it->inedges[p]->tail->id] + 1;
+        const std::int16_t* pred = row_of(pred_i);
+        const __m256i up = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(pred + j0));
+        const __m256i dg = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(pred + j0 - 1));
+        const __m256i pf = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(prof + j0));
+        x = _mm256_max_epi16(x, _mm256_max_epi16(_mm256_add_epi16(dg, pf),
+                                                 _mm256_add_epi16(up, vg)));
+      }
+      // y[l] = x[l] - (j0 + l) * g ; column 0 is fixed by the column initialisation
+      const __m256i base = _mm256_set1_epi16(static_cast<std::int16_t>(j0 * g_));
+      const __m256i off = _mm256_add_epi16(base, vramp);
+      __m256i y = _mm256_sub_epi16(x, off);
+      if (v == 0) {
+        alignas(32) std::int16_t tmp[16];
+        _mm256_store_si256(reinterpret_cast<__m256i*>(tmp), y);
+        tmp[0] = col0;  // (0 * g = 0)
+        y = _mm256_load_si256(reinterpret_cast<const __m256i*>(tmp));
+      }
+      // inclusive prefix maximum over the 16 lanes, then over the vectors before
+      y = _mm256_max_epi16(y, ShiftUpN(y, vneg, 1));
+      y = _mm256_max_epi16(y, ShiftUpN(y, vneg, 2));
+      y = _mm256_max_epi16(y, ShiftUpN(y, vneg, 4));
+      y = _mm256_max_epi16(y, ShiftUpN(y, vneg, 8));
+      y = _mm256_max_epi16(y, _mm256_set1_epi16(carry));
+      _mm256_storeu_si256(reinterpret_cast<__m256i*>(row + j0), _mm256_add_epi16(y, off));
+      alignas(32) std::int16_t last[16];
+      _mm256_store_si256(reinterpret_cast<__m256i*>(last), y);
+      carry = last[15];
+    }
+    row[0] = col0;
+  }
+  return true;
+}
+#else
+bool AlignmentEngine::FillSimd16(const char*, std::uint32_t, const Graph&) { return false; }
+#endif
+
 Alignment AlignmentEngine::Align(const char* sequence, std::uint32_t sequence_len,
                                  const Graph& graph, std::int32_t* score) {
   if (graph.nodes().empty() || sequence_len == 0) {
@@ -395,46 +512,62 @@ Alignment AlignmentEngine::Align(const char* sequence, std::uint32_t sequence_le
     node_id_to_rank_[rank_to_node[i]->id] = i;
   }
 
-  H_.assign(width * height, 0);
-  for (std::uint64_t j = 1; j < width; ++j) {
-    H_[j] = static_cast<std::int32_t>(j) * g_;
-  }
-  for (std::uint64_t i = 1; i < height; ++i) {
-    const auto& edges = rank_to_node[i - 1]->inedges;
-    std::int32_t penalty = edges.empty() ? 0 : kNegInf;
-    for (const auto& it : edges) {
-      const std::uint64_t pred_i = node_id_to_rank_[it->tail->id] + 1;
-      penalty = std::max(penalty, H_[pred_i * width]);
-    }
-    H_[i * width] = penalty + g_;
-  }
-
+  const bool simd = g_use_simd && FillSimd16(sequence, sequence_len, graph);
+  const std::uint64_t stride16 = ((width + 15) / 16) * 16 + 16;
+  auto HH = [&](std::uint64_t i, std::uint64_t j) -> std::int32_t {
+    return simd ? static_cast<std::int32_t>(H16_[i * stride16 + 16 + j]) : H_[i * width + j];
+  };
   std::int32_t max_score = kNegInf;
   std::int64_t max_i = -1, max_j = -1;
-  for (const auto& it : rank_to_node) {
-    const std::int32_t* prof = &profile_[it->code * width];
-    const std::uint64_t i = node_id_to_rank_[it->id] + 1;
-    std::uint64_t pred_i =
-        it->inedges.empty() ? 0 : node_id_to_rank_[it->inedges[0]->tail->id] + 1;
-    std::int32_t* row = &H_[i * width];
-    const std::int32_t* pred = &H_[pred_i * width];
+  if (!simd) {
+    H_.assign(width * height, 0);
     for (std::uint64_t j = 1; j < width; ++j) {
-      row[j] = std::max(pred[j - 1] + prof[j], pred[j] + g_);
+      H_[j] = static_cast<std::int32_t>(j) * g_;
     }
-    for (std::uint32_t p = 1; p < it->inedges.size(); ++p) {
-      pred_i = node_id_to_rank_[it->inedges[p]->tail->id] + 1;
-      pred = &H_[pred_i * width];
+    for (std::uint64_t i = 1; i < height; ++i) {
+      const auto& edges = rank_to_node[i - 1]->inedges;
+      std::int32_t penalty = edges.empty() ? 0 : kNegInf;
+      for (const auto& it : edges) {
+        const std::uint64_t pred_i = node_id_to_rank_[it->tail->id] + 1;
+        penalty = std::max(penalty, H_[pred_i * width]);
+      }
+      H_[i * width] = penalty + g_;
+    }
+
+    for (const auto& it : rank_to_node) {
+      const std::int32_t* prof = &profile_[it->code * width];
+      const std::uint64_t i = node_id_to_rank_[it->id] + 1;
+      std::uint64_t pred_i =
+          it->inedges.empty() ? 0 : node_id_to_rank_[it->inedges[0]->tail->id] + 1;
+      std::int32_t* row = &H_[i * width];
+      const std::int32_t* pred = &H_[pred_i * width];
       for (std::uint64_t j = 1; j < width; ++j) {
-        row[j] = std::max(pred[j - 1] + prof[j], std::max(row[j], pred[j] + g_));
+        row[j] = std::max(pred[j - 1] + prof[j], pred[j] + g_);
+      }
+      for (std::uint32_t p = 1; p < it->inedges.size(); ++p) {
+        pred_i = node_id_to_rank_[it->inedges[p]->tail->id] + 1;
+        pred = &H_[pred_i * width];
+        for (std::uint64_t j = 1; j < width; ++j) {
+          row[j] = std::max(pred[j - 1] + prof[j], std::max(row[j], pred[j] + g_));
+        }
+      }
+      for (std::uint64_t j = 1; j < width; ++j) {
+        row[j] = std::max(row[j - 1] + g_, row[j]);
+      }
+      if (it->outedges.empty() && max_score < row[width - 1]) {  // sinks, first maximum
+        max_score = row[width - 1];
+        max_i = i;
+        max_j = width - 1;
       }
     }
-    for (std::uint64_t j = 1; j < width; ++j) {
-      row[j] = std::max(row[j - 1] + g_, row[j]);
-    }
-    if (it->outedges.empty() && max_score < row[width - 1]) {  // sinks, first maximum
-      max_score = row[width - 1];
-      max_i = i;
-      max_j = width - 1;
+  } else {
+    for (const auto& it : rank_to_node) {  // sinks, first maximum (rank order)
+      const std::uint64_t i = node_id_to_rank_[it->id] + 1;
+      if (it->outedges.empty() && max_score < HH(i, width - 1)) {
+        max_score = HH(i, width - 1);
+        max_i = i;
+        max_j = width - 1;
+      }
     }
   }
   if (max_i == -1 && max_j == -1) {
@@ -449,7 +582,7 @@ Alignment AlignmentEngine::Align(const char* sequence, std::uint32_t sequence_le
   std::uint64_t i = max_i, j = max_j;
   std::uint64_t prev_i = 0, prev_j = 0;
   while (!(i == 0 && j == 0)) {
-    const std::int32_t h = H_[i * width + j];
+    const std::int32_t h = HH(i, j);
     bool found = false;
     if (i != 0 && j != 0) {
       const auto& it = rank_to_node[i - 1];
@@ -458,7 +591,7 @@ Alignment AlignmentEngine::Align(const char* sequence, std::uint32_t sequence_le
       for (std::size_t p = 0; p < np; ++p) {
         const std::uint64_t pred_i =
             it->inedges.empty() ? 0 : node_id_to_rank_[it->inedges[p]->tail->id] + 1;
-        if (h == H_[pred_i * width + (j - 1)] + match) {
+        if (h == HH(pred_i, j - 1) + match) {
           prev_i = pred_i;
           prev_j = j - 1;
           found = true;
@@ -472,7 +605,7 @@ Alignment AlignmentEngine::Align(const char* sequence, std::uint32_t sequence_le
       for (std::size_t p = 0; p < np; ++p) {
         const std::uint64_t pred_i =
             it->inedges.empty() ? 0 : node_id_to_rank_[it->inedges[p]->tail->id] + 1;
-        if (h == H_[pred_i * width + j] + g_) {
+        if (h == HH(pred_i, j) + g_) {
           prev_i = pred_i;
           prev_j = j;
           found = true;
@@ -480,7 +613,7 @@ Alignment AlignmentEngine::Align(const char* sequence, std::uint32_t sequence_le
         }
       }
     }
-    if (!found && j != 0 && h == H_[i * width + j - 1] + g_) {
+    if (!found && j != 0 && h == HH(i, j - 1) + g_) {
       prev_i = i;
       prev_j = j - 1;
       found = true;

@@ -44,93 +44,117 @@ IndexTableKernel(const ValT* __restrict__ val, uint64_t n, int shift,
                  unsigned long long* __restrict__ hist, uint64_t* __restrict__ gaps) {
   __shared__ uint32_t sh[kSmemBins];
   __shared__ uint32_t keys;
+  __shared__ uint32_t warp_first[kThreads / 32];
   for (uint32_t i = threadIdx.x; i < kSmemBins; i += kThreads) sh[i] = 0;
   if (threadIdx.x == 0) keys = 0;
   __syncthreads();
-  const uint32_t lane = threadIdx.x & 31;
   // persistent CTAs: the shared histogram is set up and flushed once per CTA
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kThreads;
   for (uint64_t base = static_cast<uint64_t>(blockIdx.x) * kThreads; base <= n; base += stride) {
-    const uint64_t i = base + threadIdx.x;
-    // record i (the virtual record n closes the table and the last run)
-    uint64_t cur = 0, prev = 0;
-    if (i < n) cur = val[i];
-    {  // the left neighbour: the lane below, or one more load at the warp edge
-      const uint64_t up = __shfl_up_sync(0xFFFFFFFFu, cur, 1);
-      prev = lane ? up : (i > 0 && i <= n ? static_cast<uint64_t>(val[i - 1]) : 0);
-    }
-    bool start = false;
-    uint32_t fill_cnt = 0;
-    uint64_t fill_lo = 0;
-    if (i <= n) {
-      // record i is the first one of buckets (prev_bucket, this_bucket]
-      const uint64_t lo = i == 0 ? 0 : (prev >> shift) + 1;
-      const uint64_t hi = i == n ? n_buckets : (cur >> shift);
-      if (hi >= lo) {
-        if (hi + 1 - lo <= kShortGap) {
-          fill_lo = lo;
-          fill_cnt = static_cast<uint32_t>(hi + 1 - lo);
-        } else {
-          const unsigned long long g = atomicAdd(&hist[kHistBins + 1], 1ULL);
-          if (g < kMaxLongGaps) {
-            gaps[3 * g] = lo;
-            gaps[3 * g + 1] = hi;
-            gaps[3 * g + 2] = i;
-          } else {  // (never seen: the list holds a million gaps)
-            for (uint64_t b = lo; b <= hi; ++b) bucket[b] = static_cast<uint32_t>(i);
-          }
+  const uint64_t i = base + threadIdx.x;
+  bool start = false;
+  uint32_t len = 0;
+  uint64_t fill_lo = 0, mine = 0;
+  uint32_t fill_cnt = 0;  // buckets (prev_bucket, this_bucket] this record owns
+  if (i <= n) {
+    const uint64_t prev = i == 0 ? 0 : val[i - 1];
+    const uint64_t cur = i == n ? 0 : val[i];
+    // record i is the first one of buckets (prev_bucket, this_bucket]
+    const uint64_t lo = i == 0 ? 0 : (prev >> shift) + 1;
+    const uint64_t hi = i == n ? n_buckets : (cur >> shift);
+    if (hi >= lo) {
+      if (hi + 1 - lo <= kShortGap) {
+        fill_lo = lo;
+        fill_cnt = static_cast<uint32_t>(hi + 1 - lo);
+      } else {
+        const unsigned long long g = atomicAdd(&hist[kHistBins + 1], 1ULL);
+        if (g < kMaxLongGaps) {
+          gaps[3 * g] = lo;
+          gaps[3 * g + 1] = hi;
+          gaps[3 * g + 2] = i;
+        } else {  // (never seen: the list holds a million gaps)
+          for (uint64_t b = lo; b <= hi; ++b) bucket[b] = static_cast<uint32_t>(i);
         }
       }
-      start = i < n && (i == 0 || cur != prev);  // a run starts here
     }
-    // ---- buckets: nearly every record owns 0..2 of them (written by its own
-    // thread); the wider stretches at the sparse top of the value range are
-    // filled by the whole warp, one owner at a time ----
-    if (fill_cnt <= 4) {
-      for (uint32_t t = 0; t < fill_cnt; ++t) bucket[fill_lo + t] = static_cast<uint32_t>(i);
-    }
-    uint32_t wide = __ballot_sync(0xFFFFFFFFu, fill_cnt > 4);
-    while (wide) {
-      const int src = __ffs(wide) - 1;
-      wide &= wide - 1;
-      const uint64_t wlo = __shfl_sync(0xFFFFFFFFu, fill_lo, src);
-      const uint32_t wcnt = __shfl_sync(0xFFFFFFFFu, fill_cnt, src);
-      const uint32_t wi = static_cast<uint32_t>(base + (threadIdx.x & ~31u) + src);
-      for (uint32_t t = lane; t < wcnt; t += 32) bucket[wlo + t] = wi;
-    }
-    // ---- run length = distance to the next run start: in the warp's ballot, or
-    // (a run that crosses the warp edge: a few per cent) by reading on ----
-    const uint32_t marks = __ballot_sync(0xFFFFFFFFu, start || i >= n);
-    uint32_t len = 0;
+    start = i < n && (i == 0 || cur != prev);  // a run starts here
+    mine = cur;
+  }
+  // Run length = distance to the next run start: found in the warp's ballot, else
+  // in the following warps of this tile (shared memory), else - the run crosses
+  // the tile end - by scanning on from there. (A per-thread forward scan costs
+  // every warp its longest run in dependent loads.) The virtual record n ends
+  // the last run.
+  {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t marks = __ballot_sync(0xFFFFFFFFu, start || i == n);
+    if (lane == 0) warp_first[wid] = marks ? static_cast<uint32_t>(__ffs(marks) - 1) : 32u;
+    __syncthreads();
     if (start) {
       const uint32_t above = lane == 31 ? 0u : (marks & ~((2u << lane) - 1u));
       if (above) {
         len = static_cast<uint32_t>(__ffs(above) - 1) - lane;
       } else {
         len = 32 - lane;
-        uint64_t pos = i + len;
-        while (len < kHistBins - 1 && pos < n && val[pos] == cur) {
-          ++pos;
-          ++len;
+        uint32_t w2 = wid + 1;
+        while (w2 < kThreads / 32 && warp_first[w2] == 32u) {
+          len += 32;
+          ++w2;
+        }
+        if (w2 < kThreads / 32) {
+          len += warp_first[w2];
+        } else {
+          uint64_t pos = base + kThreads;
+          while (len < kHistBins - 1 && pos < n && val[pos] == mine) {
+            ++pos;
+            ++len;
+          }
         }
       }
       if (len > kHistBins - 1) len = kHistBins - 1;
     }
-    // ---- histogram: the common lengths are counted per warp, the rest singly ----
-    const uint32_t starts = __ballot_sync(0xFFFFFFFFu, start);
+    __syncthreads();
+  }
+  // the warp fills its records' buckets together (a per-thread loop would run
+  // as long as the widest gap among the 32 records): slot t of the warp's
+  // total belongs to the lane found by a shuffle search over the prefixes
+  {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t incl = fill_cnt;
 #pragma unroll
-    for (uint32_t l = 1; l <= 3; ++l) {
-      const uint32_t m = __ballot_sync(0xFFFFFFFFu, start && len == l);
-      if (lane == 0 && m) atomicAdd(&sh[l], static_cast<uint32_t>(__popc(m)));
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= static_cast<uint32_t>(d)) incl += o;
     }
-    if (start && len > 3) {
+    const uint32_t rel = incl - fill_cnt;
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+      const uint32_t t = t0 + lane;
+      uint32_t q = 0;
+#pragma unroll
+      for (uint32_t step = 16; step > 0; step >>= 1) {
+        const uint32_t r = __shfl_sync(0xFFFFFFFFu, rel, q + step);
+        if (r <= t) q += step;
+      }
+      const uint32_t qrel = __shfl_sync(0xFFFFFFFFu, rel, q);
+      const uint64_t qlo = __shfl_sync(0xFFFFFFFFu, fill_lo, q);
+      if (t < total) bucket[qlo + (t - qrel)] = static_cast<uint32_t>(base + (threadIdx.x & ~31u) + q);
+    }
+  }
+  // warp-aggregated: nearly all runs have the same few lengths
+  const uint32_t starts = __ballot_sync(0xFFFFFFFFu, start);
+  if (start) {
+    const uint32_t same = __match_any_sync(starts, len);
+    if ((threadIdx.x & 31) == static_cast<uint32_t>(__ffs(same) - 1)) {
       if (len < kSmemBins) {
-        atomicAdd(&sh[len], 1u);
+        atomicAdd(&sh[len], static_cast<uint32_t>(__popc(same)));
       } else {
-        atomicAdd(&hist[len], 1ULL);
+        atomicAdd(&hist[len], static_cast<unsigned long long>(__popc(same)));
       }
     }
-    if (lane == 0 && starts) atomicAdd(&keys, static_cast<uint32_t>(__popc(starts)));
+  }
+  if ((threadIdx.x & 31) == 0 && starts) atomicAdd(&keys, static_cast<uint32_t>(__popc(starts)));
+
   }
   __syncthreads();
   for (uint32_t b = threadIdx.x; b < kSmemBins; b += kThreads) {

@@ -569,10 +569,6 @@ MicromizeKernel(const ValT* __restrict__ s_val,
                 uint32_t s_first, const uint64_t* __restrict__ q_off,
                 uint32_t q_first, uint32_t k,
                 ValT* __restrict__ q_val, uint64_t* __restrict__ q_org) {
-  // the read's values are staged once (32 KB: reads of up to ~24 kb at w = 5;
-  // longer ones are re-read from global memory, L2 resident)
-  constexpr uint32_t kCap = 32768 / sizeof(ValT);
-  __shared__ ValT sh_val[kCap];
   __shared__ uint32_t hist[256];
   __shared__ uint32_t sh_scan[34];
   __shared__ uint32_t sh_digit, sh_want;
@@ -592,11 +588,6 @@ MicromizeKernel(const ValT* __restrict__ s_val,
     }
     return;
   }
-  const bool staged = cnt <= kCap;
-  if (staged) {
-    for (uint32_t i = threadIdx.x; i < cnt; i += kMicroThreads) sh_val[i] = val[i];
-  }
-  const ValT* V = staged ? sh_val : val;
 
   // radix select of the value with ascending rank m-1
   uint64_t prefix = 0, prefix_mask = 0;
@@ -604,44 +595,22 @@ MicromizeKernel(const ValT* __restrict__ s_val,
   for (int shift = static_cast<int>((2 * k + 7) / 8 - 1) * 8; shift >= 0;
        shift -= 8) {
     hist[threadIdx.x] = 0;
-    __syncthreads();  // (also: the staged values are visible)
+    __syncthreads();
     for (uint32_t i = threadIdx.x; i < cnt; i += kMicroThreads) {
-      const uint64_t v = V[i];
+      const uint64_t v = val[i];
       if ((v & prefix_mask) == prefix) {
         atomicAdd(&hist[(v >> shift) & 255], 1u);
       }
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
-      // the digit whose cumulative count first exceeds `want`: 8 bins per lane,
-      // one warp scan
-      const uint32_t lane = threadIdx.x;
-      uint32_t c[8], sum = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        c[j] = hist[lane * 8 + j];
-        sum += c[j];
+    if (threadIdx.x == 0) {
+      uint32_t cum = 0, d = 0;
+      for (; d < 256; ++d) {
+        if (cum + hist[d] > want) break;
+        cum += hist[d];
       }
-      uint32_t incl = sum;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= static_cast<uint32_t>(d)) incl += o;
-      }
-      const uint32_t before = incl - sum;  // records in the bins below this lane's
-      const bool mine = before <= want && want < incl;
-      if (mine) {  // exactly one lane (the total exceeds want)
-        uint32_t cum = before, d = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (d == static_cast<uint32_t>(j) && cum + c[j] <= want) {
-            cum += c[j];
-            d = j + 1;
-          }
-        }
-        sh_digit = lane * 8 + d;
-        sh_want = want - cum;
-      }
+      sh_digit = d;
+      sh_want = want - cum;
     }
     __syncthreads();
     prefix |= static_cast<uint64_t>(sh_digit) << shift;
@@ -652,15 +621,15 @@ MicromizeKernel(const ValT* __restrict__ s_val,
   const uint64_t T = prefix;
   const uint32_t need_eq = want + 1;  // first need_eq records equal to T
 
-  // ordered compaction, one chunk of kMicroThreads records at a time (origins
-  // are only read for the records that stay: one in five)
+  // ordered compaction, one chunk of kMicroThreads records at a time
   uint32_t kept = 0, eq_seen = 0;
   for (uint32_t base = 0; base < cnt; base += kMicroThreads) {
     const uint32_t i = base + threadIdx.x;
-    uint64_t v = 0;
+    uint64_t v = 0, o = 0;
     uint32_t is_eq = 0, is_lt = 0;
     if (i < cnt) {
-      v = V[i];
+      v = val[i];
+      o = org[i];
       is_eq = v == T;
       is_lt = v < T;
     }
@@ -675,7 +644,7 @@ MicromizeKernel(const ValT* __restrict__ s_val,
     if (keep) {
       const uint64_t d = ob + kept + lt_before + eq_kept_before;
       q_val[d] = static_cast<ValT>(v);
-      q_org[d] = org[i];
+      q_org[d] = o;
     }
     const uint32_t eq_tot = tot >> 16, lt_tot = tot & 0xFFFF;
     kept += lt_tot + (min(eq_seen + eq_tot, need_eq) - min(eq_seen, need_eq));

@@ -342,3 +342,25 @@ def test_product_edlib_equals_oracle(oracle):
         if d > 0:
             assert align(sa, sb, 0, d - 1)[0] == -1
         assert align(sa, sb, 0, d)[0] == d
+
+
+def test_oracle_spoa_simd_fill_equals_scalar(oracle):
+    """The oracle's AVX2 int16 matrix fill (what upstream spoa's SIMD engine does;
+    the CPU legs of bench.py time it) gives the same consensus, coverages, status
+    and cell counts as the scalar int32 loops."""
+    sets = [synth.make_windows(n_windows=10, backbone_len=500, layers=25, seed=21),
+            synth.make_windows(n_windows=6, backbone_len=300, layers=12, seed=5,
+                               with_quality=False, partial=1.0),
+            synth.make_windows(n_windows=4, backbone_len=760, layers=10, seed=11),
+            synth.make_windows(n_windows=8, backbone_len=200, layers=6, seed=7, min_layers=0)]
+    for w in sets:
+        for kw in (dict(), dict(m=5, n=-4, g=-8), dict(trim=False)):
+            oracle.lib.orc_spoa_use_simd(0)
+            a = oracle.poa_batch(w, threads=4, **kw)
+            oracle.lib.orc_spoa_use_simd(1)
+            try:
+                b = oracle.poa_batch(w, threads=4, **kw)
+            finally:
+                oracle.lib.orc_spoa_use_simd(0)
+            for k in ("consensus", "cons_off", "coverage", "status", "cells"):
+                assert np.array_equal(a[k], b[k]), k
