@@ -87,12 +87,21 @@ void Stage1(Ctx& c, double freq, uint64_t kmax, bool minhash, uint64_t ib,
   c.st_mapped = 0;
 
   uint64_t bases = 0;
+  uint64_t tmax = 0;  // largest micromizer value of the reads sketched so far
   for (uint32_t i = 0, j = 0; i < n; ++i) {
     bases += c.h_len[i];
     if (i != n - 1 && bases < ib) continue;
     bases = 0;
 
-    BuildIndex(c, j, i + 1, minhash);
+    // Queries are micromizers only (construct.cc:62): no record above the largest
+    // micromizer value of any read so far can be hit - those are counted for the
+    // occurrence threshold but stay out of the index (index.cu, tiers)
+    uint64_t limit = ~0ULL;
+    if (!minhash) {
+      tmax = std::max(tmax, MaxMicromizerValue(c, j, i + 1));
+      limit = tmax;
+    }
+    BuildIndex(c, j, i + 1, minhash, limit);
     FilterIndex(c, freq);
 
     // every read up to the end of this index batch is a query, flushed per
@@ -628,6 +637,8 @@ RVN_API int rvn_set_option(rvn_ctx* ctx, const char* name, int64_t value) {
   return Guard(ctx, [&](Ctx& c) {
     if (name && std::strcmp(name, "keep_hits") == 0) {
       c.keep_hits = value != 0;
+    } else if (name && std::strcmp(name, "tier_min_records") == 0) {
+      c.tier_min_records = value < 0 ? 0 : static_cast<uint64_t>(value);
     } else if (name && std::strcmp(name, "reset_stats") == 0) {
       std::memset(&c.stats, 0, sizeof(c.stats));
       c.launches = 0;

@@ -571,7 +571,7 @@ void DistHitsSplit(Ctx& c, const uint64_t* d_qval, const uint64_t* d_qorg, uint6
   CheckParts(parts, 0);
   if (n_query > c.n_reads) throw InvalidArgument("query range out of bounds");
   IndexView2 ix{ValView{c.i_val.get(), c.i_is32 ? 1 : 0}, c.i_org.get(), c.i_bucket.get(), c.i_n,
-                static_cast<int>(2 * c.prm.k) - c.i_bucket_bits, c.occurrence};
+                c.i_shift, c.occurrence};
   const uint32_t per_part = CeilDiv(n_query, parts);
   const uint64_t slots = static_cast<uint64_t>(per_part) * parts;
   uint32_t* cnt = c.m_cnt.reserve(n_q + 1);

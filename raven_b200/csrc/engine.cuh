@@ -82,6 +82,14 @@ struct Ctx {
   uint64_t i_n = 0, i_keys = 0;
   DevBuf<uint64_t> i_val, i_org, i_val_alt, i_org_alt;
   bool i_is32 = false;  // i_val holds u32 values
+  int i_shift = 0;             // bucket = value >> i_shift
+  uint64_t i_limit = ~0ULL;    // tiered build: only values <= i_limit are in the index
+  // tiers (index.cu): staging of the probe-able tier and the bare keys beyond it
+  DevBuf<uint32_t> t_cnt;
+  DevBuf<uint64_t> t_off, t_aval, t_aorg, t_b0, t_b1, t_b2;
+  const uint32_t* t_sorted_b = nullptr;
+  uint64_t t_nb = 0;
+  uint64_t tier_min_records = 1ULL << 18;  // smaller index batches are not worth a partition
   DevBuf<uint32_t> i_bucket;
   int i_bucket_bits = 0;
   DevBuf<uint64_t> i_gaps;  // long empty stretches of the bucket table (index.cu)
@@ -211,11 +219,15 @@ void EnsureSketch(Ctx& c, uint32_t first, uint32_t last);
 void EnsureMicromizers(Ctx& c, uint32_t first, uint32_t last);
 
 // ---- index.cu ----
-void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash);
+// value_limit: records whose value exceeds it are counted (occurrence threshold)
+// but not indexed - the caller guarantees that no query value is larger
+void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash,
+                uint64_t value_limit = ~0ULL);
+uint64_t MaxMicromizerValue(Ctx& c, uint32_t first, uint32_t last);
 // index from device records already in (read, position) order (values as u32
 // or u64, see ValView)
 void BuildIndexFrom(Ctx& c, ValView src_val, const uint64_t* src_org, uint64_t n,
-                    uint64_t index_bases);
+                    uint64_t index_bases, uint64_t value_limit = ~0ULL);
 
 // ---- radix.cu ---- stable LSD radix sort on key bits [begin_bit, end_bit).
 // The source arrays are only read (src may alias buffer b: it is dead once the

@@ -37,7 +37,7 @@ constexpr uint32_t kSmemBins = 1024;
 constexpr uint32_t kShortGap = 1024;
 constexpr uint32_t kMaxLongGaps = 1u << 20;
 
-template <typename ValT>
+template <typename ValT, bool kFill>
 __global__ void __launch_bounds__(kThreads)
 IndexTableKernel(const ValT* __restrict__ val, uint64_t n, int shift,
                  uint32_t n_buckets, uint32_t* __restrict__ bucket,
@@ -62,7 +62,7 @@ IndexTableKernel(const ValT* __restrict__ val, uint64_t n, int shift,
     // record i is the first one of buckets (prev_bucket, this_bucket]
     const uint64_t lo = i == 0 ? 0 : (prev >> shift) + 1;
     const uint64_t hi = i == n ? n_buckets : (cur >> shift);
-    if (hi >= lo) {
+    if (kFill && hi >= lo) {
       if (hi + 1 - lo <= kShortGap) {
         fill_lo = lo;
         fill_cnt = static_cast<uint32_t>(hi + 1 - lo);
@@ -138,7 +138,7 @@ IndexTableKernel(const ValT* __restrict__ val, uint64_t n, int shift,
       }
       const uint32_t qrel = __shfl_sync(0xFFFFFFFFu, rel, q);
       const uint64_t qlo = __shfl_sync(0xFFFFFFFFu, fill_lo, q);
-      if (t < total) bucket[qlo + (t - qrel)] = static_cast<uint32_t>(base + (threadIdx.x & ~31u) + q);
+      if (kFill && t < total) bucket[qlo + (t - qrel)] = static_cast<uint32_t>(base + (threadIdx.x & ~31u) + q);
     }
   }
   // warp-aggregated: nearly all runs have the same few lengths
@@ -183,9 +183,105 @@ __global__ void CollectLongRuns(const ValT* __restrict__ val, uint64_t n,
   out[atomicAdd(counter, 1ULL)] = static_cast<uint32_t>(len);
 }
 
+// ---- tiers ------------------------------------------------------------------
+// Stage 1 probes the index with micromizers only: with T = the largest micromizer
+// value of every query read, a record whose value exceeds T can never be hit.
+// Such records (about three in four at k = 15, w = 5) still count for the
+// occurrence threshold, which ranks the multiplicities of ALL keys - so they are
+// sorted as bare 4-byte keys, while only the probe-able tier carries its origins
+// through the sort and into the table. Stable partition: count, scan, scatter.
+constexpr uint32_t kTierTile = 4096;  // records per CTA (16 warp steps of 32 per warp x 8)
+
+__global__ void __launch_bounds__(kThreads)
+TierCountKernel(const uint32_t* __restrict__ val, uint64_t n, uint32_t limit,
+                uint32_t* __restrict__ tile_cnt) {
+  __shared__ uint32_t sm[34];
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kTierTile;
+  uint32_t mine = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < kTierTile / kThreads; ++i) {
+    const uint64_t idx = base + i * kThreads + threadIdx.x;
+    mine += (idx < n && val[idx] <= limit) ? 1u : 0u;
+  }
+  uint32_t total;
+  BlockExclusiveSum<uint32_t, kThreads>(mine, sm, &total);
+  if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kThreads)
+TierScatterKernel(const uint32_t* __restrict__ val, const uint64_t* __restrict__ org, uint64_t n,
+                  uint32_t limit, const uint64_t* __restrict__ tile_off_a,
+                  uint32_t* __restrict__ a_val, uint64_t* __restrict__ a_org,
+                  uint32_t* __restrict__ b_val) {
+  __shared__ uint32_t warp_a[kThreads / 32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr uint32_t kWarpSpan = kTierTile / (kThreads / 32);  // 512 consecutive records
+  const uint64_t tile_base = static_cast<uint64_t>(blockIdx.x) * kTierTile;
+  const uint64_t warp_base = tile_base + warp * kWarpSpan;
+  uint32_t v[kWarpSpan / 32];
+  uint32_t cnt = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < kWarpSpan / 32; ++i) {
+    const uint64_t idx = warp_base + i * 32 + lane;
+    v[i] = idx < n ? val[idx] : 0xFFFFFFFFu;
+    cnt += __popc(__ballot_sync(0xFFFFFFFFu, idx < n && v[i] <= limit));
+  }
+  if (lane == 0) warp_a[warp] = cnt;
+  __syncthreads();
+  uint64_t a_at = tile_off_a[blockIdx.x];
+  for (uint32_t w = 0; w < warp; ++w) a_at += warp_a[w];
+  uint64_t b_at = warp_base - a_at;  // records before this warp that are not in tier A
+#pragma unroll
+  for (uint32_t i = 0; i < kWarpSpan / 32; ++i) {
+    const uint64_t idx = warp_base + i * 32 + lane;
+    const bool in = idx < n;
+    const bool is_a = in && v[i] <= limit;
+    const uint32_t ma = __ballot_sync(0xFFFFFFFFu, is_a);
+    const uint32_t mb = __ballot_sync(0xFFFFFFFFu, in && !is_a);
+    const uint32_t below = (1u << lane) - 1u;
+    if (is_a) {
+      const uint64_t d = a_at + __popc(ma & below);
+      a_val[d] = v[i];
+      a_org[d] = org[idx];
+    } else if (in) {
+      b_val[b_at + __popc(mb & below)] = v[i];
+    }
+    a_at += __popc(ma);
+    b_at += __popc(mb);
+  }
+}
+
+__global__ void MaxU32Kernel(const uint32_t* __restrict__ v, uint64_t n,
+                             unsigned int* __restrict__ out) {
+  uint32_t m = 0;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += stride) {
+    m = max(m, v[i]);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, d));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
 }  // namespace
 
-void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash) {
+// largest micromizer value of reads [first, last) (their micromizers in c.q_*)
+uint64_t MaxMicromizerValue(Ctx& c, uint32_t first, uint32_t last) {
+  EnsureMicromizers(c, first, last);
+  if (c.q_n == 0) return 0;
+  if (!c.q_is32) return ~0ULL;  // (tiers are only built over u32 values)
+  uint64_t* w = c.m_counter.reserve(8);
+  RVN_CUDA(cudaMemsetAsync(w, 0, sizeof(uint64_t), c.stream));
+  MaxU32Kernel<<<std::min<unsigned>(CeilDiv(c.q_n, 256), 148 * 8), 256, 0, c.stream>>>(
+      reinterpret_cast<const uint32_t*>(c.q_val.get()), c.q_n,
+      reinterpret_cast<unsigned int*>(w));
+  RVN_LAUNCH_CHECK();
+  ++c.launches;
+  return ReadU64(c, w) & 0xFFFFFFFFULL;
+}
+
+void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash, uint64_t value_limit) {
   c.i_valid = false;
   c.occurrence = 0xFFFFFFFFu;
   EnsureSketch(c, first, last);
@@ -202,12 +298,12 @@ void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash) {
   for (uint32_t r = first; r < last; ++r) bases += c.h_len[r];
   c.i_first = first;
   c.i_last = last;
-  BuildIndexFrom(c, src_val, src_org, n, bases);
+  BuildIndexFrom(c, src_val, src_org, n, bases, minhash ? ~0ULL : value_limit);
   c.i_sorted_ids = c.ids_ascending;
 }
 
 void BuildIndexFrom(Ctx& c, ValView src_val, const uint64_t* src_org, uint64_t n,
-                    uint64_t index_bases) {
+                    uint64_t index_bases, uint64_t value_limit) {
   c.i_valid = false;
   c.i_sorted_ids = false;
   c.occurrence = 0xFFFFFFFFu;
@@ -219,58 +315,127 @@ void BuildIndexFrom(Ctx& c, ValView src_val, const uint64_t* src_org, uint64_t n
   const bool is32 = src_val.is32 != 0;
   c.i_is32 = is32;
 
+  const int key_bits = static_cast<int>(2 * c.prm.k);
+  const uint64_t value_mask = key_bits >= 64 ? ~0ULL : ((1ULL << key_bits) - 1);
+  // tiers: only for u32 values, a real limit and inputs worth a partition pass
+  const bool tiered = is32 && value_limit < value_mask && n >= c.tier_min_records;
+  const uint32_t limit32 = static_cast<uint32_t>(value_limit);
+  c.i_limit = tiered ? value_limit : ~0ULL;
+  uint64_t n_a = n, n_b = 0;
+  const uint32_t* sorted_b = nullptr;
+
   TimerBegin(c, "index_sort");
-  // stable LSD radix sort on the 2k value bits (radix.cu). The sketch arrays are
+  // stable LSD radix sort on the value bits (radix.cu). The sketch arrays are
   // only read (they still serve the queries of this batch); values of up to 30
   // bits (k <= 15) are u32 keys straight from the sketch kernel: 12 instead of
   // 16 bytes per record and pass, three 10-bit passes at k = 15.
-  const int key_bits = static_cast<int>(2 * c.prm.k);
-  const uint64_t val_elems = is32 ? n / 2 + 2 : n + 1;
-  c.i_val.reserve(val_elems);
-  c.i_val_alt.reserve(val_elems);
-  c.i_org.reserve(n + 1);
-  c.i_org_alt.reserve(n + 1);
-  if (n > 0) {
-    int where;
-    if (is32) {
-      where = RadixSortPairs(c, static_cast<const uint32_t*>(src_val.p),
-                             reinterpret_cast<uint32_t*>(c.i_val.get()),
-                             reinterpret_cast<uint32_t*>(c.i_val_alt.get()), src_org,
-                             c.i_org.get(), c.i_org_alt.get(), n, 0, key_bits);
-    } else {
-      where = RadixSortPairs(c, static_cast<const uint64_t*>(src_val.p), c.i_val.get(),
-                             c.i_val_alt.get(), src_org, c.i_org.get(), c.i_org_alt.get(), n, 0,
-                             key_bits);
+  if (tiered) {
+    const uint32_t* src32 = static_cast<const uint32_t*>(src_val.p);
+    const uint64_t tiles = (n + kTierTile - 1) / kTierTile;
+    uint32_t* tcnt = c.t_cnt.reserve(tiles + 1);
+    uint64_t* toff = c.t_off.reserve(tiles + 2);
+    TierCountKernel<<<static_cast<unsigned>(tiles), kThreads, 0, c.stream>>>(src32, n, limit32,
+                                                                          tcnt);
+    ExclusiveScanU32(c, tcnt, toff, tiles);
+    n_a = ReadU64(c, toff + tiles);
+    n_b = n - n_a;
+    uint32_t* a_val = reinterpret_cast<uint32_t*>(c.t_aval.reserve(n_a / 2 + 2));
+    uint64_t* a_org = c.t_aorg.reserve(n_a + 1);
+    uint32_t* b_src = reinterpret_cast<uint32_t*>(c.t_b0.reserve(n_b / 2 + 2));
+    TierScatterKernel<<<static_cast<unsigned>(tiles), kThreads, 0, c.stream>>>(
+        src32, src_org, n, limit32, toff, a_val, a_org, b_src);
+    RVN_LAUNCH_CHECK();
+    c.launches += 2;
+    // the probe-able tier: values <= limit need fewer key bits
+    int bits_a = 1;
+    while (bits_a < key_bits && (value_limit >> bits_a) != 0) ++bits_a;
+    c.i_val.reserve(n_a / 2 + 2);
+    c.i_val_alt.reserve(n_a / 2 + 2);
+    c.i_org.reserve(n_a + 1);
+    c.i_org_alt.reserve(n_a + 1);
+    if (n_a > 0) {
+      const int where = RadixSortPairs(c, a_val, reinterpret_cast<uint32_t*>(c.i_val.get()),
+                                       reinterpret_cast<uint32_t*>(c.i_val_alt.get()), a_org,
+                                       c.i_org.get(), c.i_org_alt.get(), n_a, 0, bits_a);
+      if (where == 1) {
+        c.i_val.swap(c.i_val_alt);
+        c.i_org.swap(c.i_org_alt);
+      }
     }
-    if (where == 1) {
-      c.i_val.swap(c.i_val_alt);
-      c.i_org.swap(c.i_org_alt);
+    // the rest: bare keys, only their multiplicities matter
+    uint32_t* b1 = reinterpret_cast<uint32_t*>(c.t_b1.reserve(n_b / 2 + 2));
+    uint32_t* b2 = reinterpret_cast<uint32_t*>(c.t_b2.reserve(n_b / 2 + 2));
+    if (n_b > 0) {
+      const int where = RadixSortKeys(c, b_src, b1, b2, n_b, 0, key_bits);
+      sorted_b = where < 0 ? b_src : (where == 0 ? b1 : b2);
     }
+    c.t_sorted_b = sorted_b;
+    c.t_nb = n_b;
+  } else {
+    const uint64_t val_elems = is32 ? n / 2 + 2 : n + 1;
+    c.i_val.reserve(val_elems);
+    c.i_val_alt.reserve(val_elems);
+    c.i_org.reserve(n + 1);
+    c.i_org_alt.reserve(n + 1);
+    if (n > 0) {
+      int where;
+      if (is32) {
+        where = RadixSortPairs(c, static_cast<const uint32_t*>(src_val.p),
+                               reinterpret_cast<uint32_t*>(c.i_val.get()),
+                               reinterpret_cast<uint32_t*>(c.i_val_alt.get()), src_org,
+                               c.i_org.get(), c.i_org_alt.get(), n, 0, key_bits);
+      } else {
+        where = RadixSortPairs(c, static_cast<const uint64_t*>(src_val.p), c.i_val.get(),
+                               c.i_val_alt.get(), src_org, c.i_org.get(), c.i_org_alt.get(), n, 0,
+                               key_bits);
+      }
+      if (where == 1) {
+        c.i_val.swap(c.i_val_alt);
+        c.i_org.swap(c.i_org_alt);
+      }
+    }
+    c.t_sorted_b = nullptr;
+    c.t_nb = 0;
   }
+  c.i_n = n_a;
   TimerEnd(c);
   const uint64_t* kv = c.i_val.get();
 
   TimerBegin(c, "index_table");
-  // bucket table over the top bits of the value + run-length histogram + #keys
+  // bucket table over the top bits of the (probe-able) value range + run-length
+  // histogram + #keys
+  int top_bits = key_bits;  // values are below 2^top_bits
+  if (tiered) {
+    top_bits = 1;
+    while (top_bits < key_bits && (value_limit >> top_bits) != 0) ++top_bits;
+  }
   int bits = 8;
-  while (bits < 28 && (1ULL << (bits + 1)) <= n) ++bits;
-  bits = std::min<int>(bits, 2 * c.prm.k);
+  while (bits < 28 && (1ULL << (bits + 1)) <= n_a) ++bits;
+  bits = std::min<int>(bits, top_bits);
   c.i_bucket_bits = bits;
-  const int shift = static_cast<int>(2 * c.prm.k) - bits;
-  const uint32_t n_buckets = 1u << bits;
+  const int shift = top_bits - bits;
+  c.i_shift = shift;
+  const uint32_t n_buckets =
+      tiered ? static_cast<uint32_t>((value_limit >> shift) + 1) : (1u << bits);
   uint32_t* bucket = c.i_bucket.reserve(n_buckets + 2ULL);
   static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
   uint64_t* hist = c.i_hist.reserve(kHistBins + 8);
   RVN_CUDA(cudaMemsetAsync(hist, 0, (kHistBins + 8) * sizeof(uint64_t), c.stream));
   uint64_t* gaps = c.i_gaps.reserve(3ULL * kMaxLongGaps);
-  const unsigned grid = std::min<unsigned>(CeilDiv(n + 1, kThreads), 148 * 8);
+  const unsigned grid = std::min<unsigned>(CeilDiv(n_a + 1, kThreads), 148 * 8);
   if (is32) {
-    IndexTableKernel<uint32_t><<<grid, kThreads, 0, c.stream>>>(
-        reinterpret_cast<const uint32_t*>(kv), n, shift, n_buckets, bucket,
+    IndexTableKernel<uint32_t, true><<<grid, kThreads, 0, c.stream>>>(
+        reinterpret_cast<const uint32_t*>(kv), n_a, shift, n_buckets, bucket,
         reinterpret_cast<unsigned long long*>(hist), gaps);
+    if (tiered && n_b > 0) {  // multiplicities of the keys beyond the limit
+      IndexTableKernel<uint32_t, false>
+          <<<std::min<unsigned>(CeilDiv(n_b + 1, kThreads), 148 * 8), kThreads, 0, c.stream>>>(
+              sorted_b, n_b, 0, 0, nullptr, reinterpret_cast<unsigned long long*>(hist), nullptr);
+      ++c.launches;
+    }
   } else {
-    IndexTableKernel<uint64_t><<<grid, kThreads, 0, c.stream>>>(
-        kv, n, shift, n_buckets, bucket, reinterpret_cast<unsigned long long*>(hist), gaps);
+    IndexTableKernel<uint64_t, true><<<grid, kThreads, 0, c.stream>>>(
+        kv, n_a, shift, n_buckets, bucket, reinterpret_cast<unsigned long long*>(hist), gaps);
   }
   RVN_LAUNCH_CHECK();
   ++c.launches;
@@ -345,6 +510,10 @@ uint32_t FilterIndex(Ctx& c, double frequency) {
       CollectLongRuns<uint32_t><<<CeilDiv(c.i_n, kThreads), kThreads, 0, c.stream>>>(
           reinterpret_cast<const uint32_t*>(c.i_val.get()), c.i_n,
           reinterpret_cast<unsigned long long*>(counter), out);
+      if (c.t_sorted_b && c.t_nb) {  // tiered build: the keys beyond the limit too
+        CollectLongRuns<uint32_t><<<CeilDiv(c.t_nb, kThreads), kThreads, 0, c.stream>>>(
+            c.t_sorted_b, c.t_nb, reinterpret_cast<unsigned long long*>(counter), out);
+      }
     } else {
       CollectLongRuns<uint64_t><<<CeilDiv(c.i_n, kThreads), kThreads, 0, c.stream>>>(
           c.i_val.get(), c.i_n, reinterpret_cast<unsigned long long*>(counter), out);

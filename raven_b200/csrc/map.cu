@@ -38,11 +38,17 @@ struct IndexView {
   uint64_t n;
   int shift;
   uint32_t occurrence;
+  uint64_t limit;  // values beyond it are not indexed (tiered build)
 };
 
 // first record with value v and the run length capped at occurrence+1
 __device__ __forceinline__ void Lookup(const IndexView& ix, uint64_t v,
                                        uint32_t* first, uint32_t* count) {
+  if (v > ix.limit) {
+    *first = 0;
+    *count = 0;
+    return;
+  }
   const uint64_t b = v >> ix.shift;
   uint32_t lo = ix.bucket[b], hi = ix.bucket[b + 1];
   while (hi - lo > 8) {  // long buckets: bisect down to a short scan
@@ -1517,7 +1523,7 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
   const uint64_t n_q = (*h_read_off)[off_base_read + nr] - q_begin;
 
   IndexView ix{ValView{c.i_val.get(), c.i_is32 ? 1 : 0}, c.i_org.get(), c.i_bucket.get(), c.i_n,
-               static_cast<int>(2 * c.prm.k) - c.i_bucket_bits, c.occurrence};
+               c.i_shift, c.occurrence, c.i_limit};
 
   // ---- probe + expand ----
   TimerBegin(c, "probe");

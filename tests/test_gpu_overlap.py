@@ -264,6 +264,40 @@ def test_stage1_synthetic_schedules(gpu_engine, oracle, cfg):
         assert got["num_mapped"] == int(want["num_mapped"][0])
 
 
+def test_stage1_tiered_index(gpu_engine, oracle, lambda_reads):
+    """Stage 1 with the tiered index forced on small inputs (bench-size batches take
+    it by default): records above the largest micromizer value are only counted for
+    the occurrence threshold. Same result as the golden files / the oracle, incl.
+    several index batches and a frequency that cuts deep."""
+    gpu_engine.set_option("tier_min_records", 0)
+    try:
+        gpu_engine.configure(k=15, w=5)
+        gpu_engine.upload(lambda_reads)
+        got = gpu_engine.find_overlaps_and_create_piles(0.001, 32, False)
+        for k in ("overlaps", "ovl_off", "pile", "pile_off"):
+            assert np.array_equal(got[k], GOLD[f"stage1_plain_{k}"]), k
+        assert got["num_mapped"] == META["stage1_plain_num_mapped"]
+        rs = synth.make_reads(30_000, 150, 3000, seed=3)
+        gpu_engine.upload(rs)
+        for freq, ib, qb in ((0.001, 120_000, 50_000), (0.05, 0, 0), (0.3, 200_000, 0)):
+            got = gpu_engine.find_overlaps_and_create_piles(freq, 8, False, ib, qb)
+            want = oracle.stage1(oracle.engine(15, 5, threads=4), oracle.reads(rs), freq, 8,
+                                 False, ib or 1 << 32, qb or 1 << 30)
+            for k in ("overlaps", "ovl_off", "pile", "pile_off"):
+                assert np.array_equal(got[k], want[k]), (freq, ib, k)
+        # a map call with full sketches after a tiered stage 1 must not see the tiers
+        gpu_engine.minimize(0, rs.n, False)
+        gpu_engine.filter(0.001)
+        a = gpu_engine.map(0, rs.n, True, True, False)
+        eng = oracle.engine(15, 5, threads=4)
+        reads = oracle.reads(rs)
+        oracle.minimize(eng, reads, 0, rs.n, False)
+        oracle.filter(eng, 0.001)
+        assert np.array_equal(a["overlaps"], oracle.map(eng, reads, 0, rs.n, True, True, False)["overlaps"])
+    finally:
+        gpu_engine.set_option("tier_min_records", 1 << 18)
+
+
 def test_stage1_hifi_params(gpu_engine, oracle):
     rs = synth.make_reads(60_000, 120, 6000, seed=6, sub=0.002, ins=0.0015, dele=0.0015)
     gpu_engine.configure(k=19, w=10)
