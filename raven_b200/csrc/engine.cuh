@@ -86,7 +86,7 @@ struct Ctx {
   uint64_t i_limit = ~0ULL;    // tiered build: only values <= i_limit are in the index
   // tiers (index.cu): staging of the probe-able tier and the bare keys beyond it
   DevBuf<uint32_t> t_cnt;
-  DevBuf<uint64_t> t_off, t_aval, t_aorg, t_b0, t_b1, t_b2;
+  DevBuf<uint64_t> t_off, t_aval, t_aorg, t_b0, t_b1, t_b2, t_narrow;
   const uint32_t* t_sorted_b = nullptr;
   uint64_t t_nb = 0;
   uint64_t tier_min_records = 1ULL << 18;  // smaller index batches are not worth a partition
