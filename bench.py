@@ -369,8 +369,8 @@ def main_ours(a):
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         tr = json.load(open(prof)) if os.path.exists(prof) else {}
         traffic = tr.get(dom)
-        # index_sort is cub::DeviceRadixSort (library); the largest phase made of
-        # this repo's own kernels gets its own roofline entry
+        # the largest phase that is ONE kernel launch per step (the sort phase is a
+        # partition + 6 radix passes + histograms) gets its own entry
         od = max((k for k in own if k != "index_sort"), key=own.get)
         od_ach = alg.get(od, 0.0) / (own[od] * 1e-3) / 1e9 if own[od] > 0 else 0.0
         own_roofline = {"kernel": od, "bound": "hbm", "achieved": od_ach, "peak": peak,
@@ -415,8 +415,8 @@ def main_ours(a):
             "phases_ms": {k: round(v, 3) for k, v in sorted(phases.items())},
             "query_mbases_per_s": st["query_bases"] / 1e6 / (ms_total / a.steps * 1e-3),
             "index_mbases_per_s": st["index_bases"] / 1e6 / (ms_total / a.steps * 1e-3),
-            "roofline": {"kernel": dom + (" (cub::DeviceRadixSort, library)"
-                                          if dom == "index_sort" else ""), "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": PHASE_KERNELS.get(dom, dom), "bound": "hbm",
+                         "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"
                          if peaks else "fallback 6650 GB/s (of fallback)",
@@ -572,7 +572,8 @@ def bench_c3(a, with_cpu):
         "note": "value = polished windows / consensus phase (H2D of the window batch + POA "
                 "kernels + D2H); e2e = the whole Polish call",
         "e2e": {"value": st["polished_windows"] / st["seconds"], "unit": "windows/s",
-                "seconds": st["seconds"], "poa_seconds": st["poa_seconds"]},
+                "seconds": st["seconds"], "poa_seconds": st["poa_seconds"],
+                "phases_s": {k: round(v, 3) for k, v in st["phases_s"].items()}},
     }
     if with_cpu:
         import oracle_lib
@@ -699,17 +700,29 @@ def bench_c5(a, local, with_cpu):
     return out
 
 
-def algorithmic_bytes(st):
-    """SURVEY.md §8(d) / DESIGN.md: bytes each phase must move at minimum."""
+PHASE_KERNELS = {
+    "index_sort": "index_sort (radix.cu: RadixHistogramKernel + OnesweepPass per digit; "
+                  "index.cu: TierCount/TierScatter)",
+    "sketch": "sketch (SketchFastKernel<5>)",
+    "chain": "chain (SplitKernel + GroupChainKernel + PairChainKernel)",
+    "probe": "probe (query radix sort + ProbeSortedKernel)",
+}
+
+
+def algorithmic_bytes(st, k=K):
+    """SURVEY.md §8(d) / DESIGN.md §4: bytes each phase must move at minimum. A
+    minimizer record is value + origin: 12 bytes while the value fits 32 bits
+    (2k <= 30; §8(d) counted 16), 16 otherwise."""
     nb, nm, nk = st["index_bases"], st["index_records"], st["index_keys"]
     qb, qm, nh, no = st["query_bases"], st["query_records"], st["hits"], st["overlaps"]
+    rec = 12.0 if 2 * k <= 30 else 16.0
     return {
-        "sketch": 0.25 * nb + 16.0 * nm,
-        "micromize": 16.0 * nm + 16.0 * qm,
-        "index_sort": 2 * 16.0 * nm,
-        "index_table": 8.0 * nm + 4.0 * nk,
+        "sketch": 0.25 * nb + rec * nm,
+        "micromize": rec * nm + rec * qm,
+        "index_sort": 2 * rec * nm,
+        "index_table": (rec - 8.0) * nm + 4.0 * nk,
         "filter": 4.0 * nk,
-        "probe": 16.0 * qm + 16.0 * qm,
+        "probe": rec * qm + rec * qm,
         "expand": 8.0 * nh + 16.0 * nh,
         "chain": 16.0 * nh + 32.0 * no,
         "pile": 2 * 2.0 * st["pile_bins"],

@@ -47,6 +47,9 @@ class Polisher {
   std::uint64_t num_windows() const { return num_windows_; }
   std::uint64_t num_polished_windows() const { return num_polished_windows_; }
   double poa_seconds() const { return poa_seconds_; }
+  // map (GPU), alignment paths + window cuts (GPU), window packing, consensus (GPU),
+  // stitch, layer rules (host pool)
+  const double* phase_seconds() const { return phase_seconds_; }
 
  private:
   Polisher(std::shared_ptr<thread_pool::ThreadPool> thread_pool, double q, double e,
@@ -60,6 +63,7 @@ class Polisher {
   rvn_ctx* ctx_;
   std::uint64_t num_windows_ = 0, num_polished_windows_ = 0;
   double poa_seconds_ = 0;
+  double phase_seconds_[6] = {0, 0, 0, 0, 0, 0};
 };
 
 }  // namespace racon

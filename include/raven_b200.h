@@ -19,6 +19,10 @@
  *                          edlibAlign(lhs, rhs, edlibDefaultAlignConfig()) of the
  *                          identity filter      RavenLib/src/construct.cc:176-199,
  *                                                                        :393-416
+ *   rvn_align_breaking_points
+ *                          edlibAlign(read, unitig, NW, EDLIB_TASK_PATH) + the window
+ *                          breaking points of racon::Polisher::Polish
+ *                                                      RavenLib/src/polish.cc:43-51
  *   rvn_find_overlaps_and_create_piles
  *                          raven::FindOverlapsAndCreatePiles
  *                                                      RavenLib/src/construct.cc:14-121
@@ -167,6 +171,28 @@ int rvn_edit_distance_batch(rvn_ctx* ctx, uint64_t n_pairs, const uint32_t* lhs_
                             const uint32_t* rhs_read, const uint32_t* rhs_begin,
                             const uint32_t* rhs_len, const uint8_t* strand,
                             const int32_t* limit, int32_t* distance);
+
+/* The read-to-target alignments of racon::Polisher::Polish (RavenLib/src/polish.cc:43-51:
+ * edlibAlign(query, target, EDLIB_MODE_NW, EDLIB_TASK_PATH) per read) and the walk along
+ * each path that cuts it at the target's windows, for n_pairs alignments at once.
+ * Pair i: query = bases [q_begin, +q_len) of uploaded read q_read[i], reverse
+ * complemented as a whole when strand[i] == 0; target = bases [t_begin, +t_len) of read
+ * t_read[i]. The path is the ONE upstream edlib returns (its traceback order and its
+ * Hirschberg split of large problems are kept), so the cuts are the reference's.
+ * Output: distance[i] = the edit distance, and for every window x of `window` target
+ * bases that the target substring touches (x = t_begin/window .. (t_begin+t_len-1)/window)
+ * the slot s = bp_off[i] + (x - t_begin/window) of breaking_points (4 values per slot):
+ *   [4s+0] target position of the first match/mismatch column inside the window,
+ *   [4s+1] its query position (0-based inside the oriented query substring),
+ *   [4s+2], [4s+3] one past the last such pair;
+ * all four 0xFFFFFFFF when no match/mismatch falls into the window. bp_off (n_pairs + 1
+ * entries, computed by the caller) must count exactly those windows. */
+int rvn_align_breaking_points(rvn_ctx* ctx, uint64_t n_pairs, const uint32_t* q_read,
+                              const uint32_t* q_begin, const uint32_t* q_len,
+                              const uint8_t* strand, const uint32_t* t_read,
+                              const uint32_t* t_begin, const uint32_t* t_len, uint32_t window,
+                              const uint64_t* bp_off, int32_t* distance,
+                              uint32_t* breaking_points);
 
 /* raven::FindOverlapsAndCreatePiles over the uploaded read set: index batches
  * of >= index_batch_bases (reference: 1<<32), query flushes of >=

@@ -571,6 +571,24 @@ RVN_API int rvn_edit_distance_batch(rvn_ctx* ctx, uint64_t n_pairs, const uint32
   });
 }
 
+RVN_API int rvn_align_breaking_points(rvn_ctx* ctx, uint64_t n_pairs, const uint32_t* q_read,
+                                      const uint32_t* q_begin, const uint32_t* q_len,
+                                      const uint8_t* strand, const uint32_t* t_read,
+                                      const uint32_t* t_begin, const uint32_t* t_len,
+                                      uint32_t window, const uint64_t* bp_off, int32_t* distance,
+                                      uint32_t* breaking_points) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (!bp_off) throw InvalidArgument("null argument");
+    if (n_pairs && (!q_read || !q_begin || !q_len || !strand || !t_read || !t_begin || !t_len ||
+                    !distance || (bp_off[n_pairs] && !breaking_points))) {
+      throw InvalidArgument("null argument");
+    }
+    AlignBreakingPoints(c, n_pairs, q_read, q_begin, q_len, strand, t_read, t_begin, t_len, window,
+                        bp_off, distance, breaking_points);
+    TimerCollect(c);
+  });
+}
+
 // the engine's radix sort on host arrays (parity tests of radix.cu)
 RVN_API int rvn_debug_sort_pairs(rvn_ctx* ctx, int key_bytes, int val_bytes, void* keys,
                                  void* vals, uint64_t n, int begin_bit, int end_bit,

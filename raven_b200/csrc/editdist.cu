@@ -21,6 +21,7 @@
 #include <numeric>
 
 #include "engine.cuh"
+#include "myers.cuh"
 
 namespace rvn {
 
@@ -35,38 +36,6 @@ struct PairDesc {
   uint32_t slot;     // index of the pair in the caller's arrays
 };
 
-__device__ __forceinline__ uint32_t BaseAt(const uint64_t* __restrict__ w, uint64_t pos) {
-  return static_cast<uint32_t>(w[pos >> 5] >> ((pos & 31) << 1)) & 3u;
-}
-
-// 64 bases starting at base `pos` of a packed read as two words (32 bases each)
-__device__ __forceinline__ void Bases64(const uint64_t* __restrict__ w, uint64_t pos,
-                                        uint64_t n_words, uint64_t* w0, uint64_t* w1) {
-  const uint64_t i = pos >> 5;
-  const uint32_t sh = static_cast<uint32_t>(pos & 31) << 1;
-  const uint64_t a = i < n_words ? w[i] : 0, b = i + 1 < n_words ? w[i + 1] : 0,
-                 c = i + 2 < n_words ? w[i + 2] : 0;
-  if (sh == 0) {
-    *w0 = a;
-    *w1 = b;
-  } else {
-    *w0 = (a >> sh) | (b << (64 - sh));
-    *w1 = (b >> sh) | (c << (64 - sh));
-  }
-}
-
-// bit r of the result = (2-bit group r of w == sym), r = 0..31
-__device__ __forceinline__ uint64_t EqMask32(uint64_t w, uint32_t sym) {
-  const uint64_t x = w ^ (0x5555555555555555ULL * sym);
-  uint64_t z = ~(x | (x >> 1)) & 0x5555555555555555ULL;
-  z = (z | (z >> 1)) & 0x3333333333333333ULL;
-  z = (z | (z >> 2)) & 0x0F0F0F0F0F0F0F0FULL;
-  z = (z | (z >> 4)) & 0x00FF00FF00FF00FFULL;
-  z = (z | (z >> 8)) & 0x0000FFFF0000FFFFULL;
-  z = (z | (z >> 16)) & 0x00000000FFFFFFFFULL;
-  return z;
-}
-
 // match mask of query block b (rows 64b .. 64b+63 of the lhs substring)
 __device__ __forceinline__ uint64_t BlockEq(const uint64_t* __restrict__ qw, uint64_t q_words,
                                             uint32_t q_begin, uint32_t m, uint32_t b,
@@ -77,32 +46,6 @@ __device__ __forceinline__ uint64_t BlockEq(const uint64_t* __restrict__ qw, uin
   const uint32_t rows = min(64u, m - 64u * b);
   if (rows < 64) eq &= (1ULL << rows) - 1ULL;
   return eq;
-}
-
-// one column step of one block; hin/hout in {-1, 0, +1}
-__device__ __forceinline__ int Step(uint64_t eq, int hin, uint64_t high, uint64_t& pv,
-                                    uint64_t& mv) {
-  const uint64_t xv = eq | mv;
-  if (hin < 0) eq |= 1ULL;
-  const uint64_t xh = (((eq & pv) + pv) ^ pv) | eq;
-  uint64_t ph = mv | ~(xh | pv);
-  uint64_t mh = pv & xh;
-  int hout = 0;
-  if (ph & high) {
-    hout = 1;
-  } else if (mh & high) {
-    hout = -1;
-  }
-  ph <<= 1;
-  mh <<= 1;
-  if (hin < 0) {
-    mh |= 1ULL;
-  } else if (hin > 0) {
-    ph |= 1ULL;
-  }
-  pv = mh | ~(xv | ph);
-  mv = ph & xv;
-  return hout;
 }
 
 // target symbol of column j (1-based) of the rhs substring, reverse

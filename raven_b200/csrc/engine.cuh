@@ -300,6 +300,10 @@ void ArenaFlush(Ctx& c);
 void ArenaRelease(Ctx& c);
 
 // ---- editdist.cu ---- batched global edit distance of read substrings
+void AlignBreakingPoints(Ctx& c, uint64_t n, const uint32_t* q_read, const uint32_t* q_begin,
+                         const uint32_t* q_len, const uint8_t* strand, const uint32_t* t_read,
+                         const uint32_t* t_begin, const uint32_t* t_len, uint32_t window,
+                         const uint64_t* bp_off, int32_t* distance, uint32_t* bp);
 void EditDistanceBatch(Ctx& c, uint64_t n, const uint32_t* lhs_read, const uint32_t* lhs_begin,
                        const uint32_t* lhs_len, const uint32_t* rhs_read,
                        const uint32_t* rhs_begin, const uint32_t* rhs_len,

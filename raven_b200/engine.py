@@ -230,6 +230,27 @@ class Engine:
             out.ctypes.data_as(C.POINTER(C.c_int32))))
         return out
 
+    def align_breaking_points(self, q_read, q_begin, q_len, strand, t_read, t_begin, t_len,
+                              window=500):
+        """racon's read-to-target alignments + window cuts (polish.cc:43-51): distances,
+        slot offsets (n + 1) and the breaking points, one row (first target, first
+        query, last target + 1, last query + 1) per window a target substring touches."""
+        a = [np.ascontiguousarray(x, dtype=np.uint32)
+             for x in (q_read, q_begin, q_len, t_read, t_begin, t_len)]
+        st = np.ascontiguousarray(strand, dtype=np.uint8)
+        tb, tl = a[4].astype(np.int64), a[5].astype(np.int64)
+        wins = np.where(tl > 0, (tb + tl - 1) // window - tb // window + 1, 0)
+        off = np.concatenate([[0], np.cumsum(wins)]).astype(np.uint64)
+        dist = np.zeros(a[0].size, dtype=np.int32)
+        bp = np.zeros((int(off[-1]), 4), dtype=np.uint32)
+        self._check(self.lib.rvn_align_breaking_points(
+            self.h, a[0].size, a[0].ctypes.data_as(U32P), a[1].ctypes.data_as(U32P),
+            a[2].ctypes.data_as(U32P), st.ctypes.data_as(C.POINTER(C.c_uint8)),
+            a[3].ctypes.data_as(U32P), a[4].ctypes.data_as(U32P), a[5].ctypes.data_as(U32P),
+            window, off.ctypes.data_as(U64P), dist.ctypes.data_as(C.POINTER(C.c_int32)),
+            bp.ctypes.data_as(U32P)))
+        return dist, off, bp
+
     def debug_sort_pairs(self, keys, vals=None, begin_bit=0, end_bit=None, descending=False):
         """The engine's stable radix sort (csrc/radix.cu) on host arrays; returns copies."""
         k = np.ascontiguousarray(keys).copy()

@@ -40,7 +40,9 @@ struct PolishResult {
   std::vector<std::uint64_t> words, woff;
   std::vector<std::uint32_t> lens;
   std::string names, error;
-  double stats[4] = {0, 0, 0, 0};  // windows, polished windows, POA seconds, total seconds
+  // windows, polished windows, POA seconds, total seconds, then the phases of
+  // Polish: map, alignment paths, window packing, consensus, stitch, layer rules
+  double stats[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 }  // namespace
@@ -79,6 +81,7 @@ RVNH_API void* rvnh_polish(const std::uint64_t* t_words, const std::uint64_t* t_
     res->stats[2] = polisher->poa_seconds();
     res->stats[3] =
         std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (int i = 0; i < 6; ++i) res->stats[4 + i] = polisher->phase_seconds()[i];
   } catch (const std::exception& ex) {
     res->error = ex.what();
     if (res->error.empty()) res->error = "error";

@@ -1,9 +1,9 @@
 // raven_b200 — racon::Polisher facade (include/racon/polisher.hpp).
 // Reference contract: RavenLib/src/polish.cc:43-51; behaviour of the stages:
-// SURVEY.md App. A.4. GPU: mapping (rvn_minimize/rvn_filter/rvn_map) and the
-// per-window consensus (rvn_poa_batch). Host pool: best overlap per read,
-// global alignment path (edlibAlign, EDLIB_TASK_PATH), breaking points, window
-// assembly, stitching.
+// SURVEY.md App. A.4. GPU: mapping (rvn_minimize/rvn_filter/rvn_map), the global
+// alignment paths of the reads (edlibAlign NW PATH) cut at the windows
+// (rvn_align_breaking_points) and the per-window consensus (rvn_poa_batch). Host
+// pool: best overlap per read, racon's per-layer rules, window assembly, stitching.
 #include "racon/polisher.hpp"
 
 #include <algorithm>
@@ -13,7 +13,6 @@
 #include <stdexcept>
 #include <string>
 
-#include "edlib.h"
 #include "raven_b200.h"
 
 namespace racon {
@@ -81,6 +80,13 @@ std::vector<std::unique_ptr<biosoup::NucleicAcid>> Polisher::Polish(
     return {};
   }
   const std::uint32_t T = targets.size(), S = sequences.size();
+  auto t_phase = std::chrono::steady_clock::now();
+  const auto Seconds = [](std::chrono::steady_clock::time_point& since) {
+    const auto now = std::chrono::steady_clock::now();
+    const double s = std::chrono::duration<double>(now - since).count();
+    since = now;
+    return s;
+  };
 
   // ---- 1. GPU: index the targets, map every read (ram k=15 w=5 f=0.001) ----
   // device set = targets (ids 0..T-1) followed by reads (ids T..T+S-1)
@@ -135,105 +141,88 @@ std::vector<std::unique_ptr<biosoup::NucleicAcid>> Polisher::Polish(
     j = i + 1;
   }
 
-  // ---- 2. host pool: alignment path -> breaking points -> layer pieces ----
+  phase_seconds_[0] = Seconds(t_phase);
+
+  // ---- 2. GPU: alignment paths cut at the windows (rvn_align_breaking_points),
+  //         host pool: the per-window rules of racon -> layer pieces ----
   std::vector<std::uint64_t> first_window(T + 1ULL, 0);
   for (std::uint32_t i = 0; i < T; ++i) {
     first_window[i + 1] = first_window[i] + (targets[i]->inflated_len + w_ - 1) / w_;
   }
-  std::vector<std::future<std::vector<Piece>>> futures;
   std::vector<std::uint32_t> coverage(T, 0);
+  std::vector<std::uint32_t> a_read, a_qread, a_qbegin, a_qlen, a_tread, a_tbegin, a_tlen;
+  std::vector<std::uint8_t> a_strand;
+  std::vector<std::uint64_t> bp_off{0};
   for (std::uint32_t k = 0; k < S; ++k) {
     if (!best[k].valid) continue;
     const rvn_overlap o = best[k].o;
     const double ql = o.lhs_end - o.lhs_begin, tl = o.rhs_end - o.rhs_begin;
     if (1 - std::min(ql, tl) / std::max(ql, tl) > e_) continue;
     ++coverage[o.rhs_id];
+    a_read.push_back(k);
+    a_qread.push_back(T + k);
+    a_qbegin.push_back(o.lhs_begin);
+    a_qlen.push_back(o.lhs_end - o.lhs_begin);
+    a_strand.push_back(o.strand ? 1 : 0);
+    a_tread.push_back(o.rhs_id);
+    a_tbegin.push_back(o.rhs_begin);
+    a_tlen.push_back(o.rhs_end - o.rhs_begin);
+    const std::uint64_t windows =
+        o.rhs_end > o.rhs_begin ? (o.rhs_end - 1) / w_ - o.rhs_begin / w_ + 1 : 0;
+    bp_off.push_back(bp_off.back() + windows);
+  }
+  const std::size_t A = a_read.size();
+  std::vector<std::int32_t> a_dist(A);
+  std::vector<std::uint32_t> bp(4 * bp_off.back() + 4);
+  Check(ctx_, rvn_align_breaking_points(ctx_, A, a_qread.data(), a_qbegin.data(), a_qlen.data(),
+                                        a_strand.data(), a_tread.data(), a_tbegin.data(),
+                                        a_tlen.data(), w_, bp_off.data(), a_dist.data(),
+                                        bp.data()));
+  phase_seconds_[1] = Seconds(t_phase);
+
+  std::vector<std::future<std::vector<Piece>>> futures;
+  const std::size_t a_chunk = std::max<std::size_t>(64, A / 1024 + 1);
+  for (std::size_t a0 = 0; a0 < A; a0 += a_chunk) {
     futures.emplace_back(thread_pool_->Submit(
-        [&](std::uint32_t k, rvn_overlap o) {
+        [&](std::size_t a0, std::size_t a1) {
           std::vector<Piece> pieces;
-          const auto& seq = *sequences[k];
-          biosoup::NucleicAcid view(seq);
-          std::uint32_t qb = o.lhs_begin, qe = o.lhs_end;
-          if (!o.strand) {  // the reverse complement of the read is aligned
-            view.ReverseAndComplement();
-            qb = seq.inflated_len - o.lhs_end;
-            qe = seq.inflated_len - o.lhs_begin;
-          }
-          const std::string q = view.InflateData(qb, qe - qb);
-          const std::string t =
-              targets[o.rhs_id]->InflateData(o.rhs_begin, o.rhs_end - o.rhs_begin);
-          EdlibAlignResult r = edlibAlign(
-              q.c_str(), q.size(), t.c_str(), t.size(),
-              edlibNewAlignConfig(-1, EDLIB_MODE_NW, EDLIB_TASK_PATH, nullptr, 0));
-          if (r.status != EDLIB_STATUS_OK) {
-            edlibFreeAlignResult(r);
-            return pieces;
-          }
-          // breaking points: first / one-past-last aligned (target, read) pair
-          // of every window the overlap touches
-          std::int64_t next_end;  // last target position of the current window
-          {
-            const std::uint32_t tb = o.rhs_begin;
-            next_end = std::min<std::int64_t>(
-                static_cast<std::int64_t>(tb / w_ + 1) * w_ - 1,
-                static_cast<std::int64_t>(o.rhs_end) - 1);
-          }
-          bool found = false;
-          std::uint32_t ft = 0, fq = 0, lt = 0, lq = 0;
-          std::int64_t qp = static_cast<std::int64_t>(qb) - 1;
-          std::int64_t tp = static_cast<std::int64_t>(o.rhs_begin) - 1;
-          auto close = [&]() {
-            if (tp != next_end) return;
-            if (found && lq - fq >= 0.02 * w_) {
-              bool keep = true;
+          for (std::size_t a = a0; a < a1; ++a) {
+            const std::uint32_t k = a_read[a];
+            const auto& seq = *sequences[k];
+            biosoup::NucleicAcid view(seq);
+            // query positions are those of the aligned orientation of the read
+            std::uint32_t qb = a_qbegin[a];
+            if (!a_strand[a]) {
+              view.ReverseAndComplement();
+              qb = seq.inflated_len - (a_qbegin[a] + a_qlen[a]);
+            }
+            for (std::uint64_t s = bp_off[a]; s < bp_off[a + 1]; ++s) {
+              if (bp[4 * s] == 0xFFFFFFFFu) continue;  // no aligned pair in this window
+              const std::uint32_t ft = bp[4 * s], fq = qb + bp[4 * s + 1], lt = bp[4 * s + 2],
+                                  lq = qb + bp[4 * s + 3];
+              if (!(lq - fq >= 0.02 * w_)) continue;
               if (!view.block_quality.empty()) {
                 double avg = 0;
                 for (std::uint32_t x = fq; x < lq; ++x) avg += view.Score(x);
                 avg /= lq - fq;
-                keep = !(avg < q_);
+                if (avg < q_) continue;
               }
-              const std::uint32_t ws0 = (ft / w_) * w_;
-              if (ft - ws0 >= lt - ws0 - 1) keep = false;  // racon skips begin == end
-              if (keep) {
-                const std::uint32_t ws = (ft / w_) * w_;
-                pieces.push_back(Piece{first_window[o.rhs_id] + ft / w_, k, fq, lq,
-                                       ft - ws, lt - ws - 1, o.strand != 0});
-              }
-            }
-            found = false;
-            next_end = std::min<std::int64_t>(next_end + w_,
-                                              static_cast<std::int64_t>(o.rhs_end) - 1);
-          };
-          for (int a = 0; a < r.alignmentLength; ++a) {
-            const unsigned char op = r.alignment[a];
-            if (op == EDLIB_EDOP_MATCH || op == EDLIB_EDOP_MISMATCH) {
-              ++qp;
-              ++tp;
-              if (!found) {
-                found = true;
-                ft = tp;
-                fq = qp;
-              }
-              lt = tp + 1;
-              lq = qp + 1;
-              close();
-            } else if (op == EDLIB_EDOP_INSERT) {
-              ++qp;
-            } else {
-              ++tp;
-              close();
+              const std::uint32_t ws = (ft / w_) * w_;
+              if (ft - ws >= lt - ws - 1) continue;  // racon skips begin == end
+              pieces.push_back(Piece{first_window[a_tread[a]] + ft / w_, k, fq, lq, ft - ws,
+                                     lt - ws - 1, a_strand[a] != 0});
             }
           }
-          edlibFreeAlignResult(r);
           return pieces;
         },
-        k, o));
+        a0, std::min(A, a0 + a_chunk)));
   }
   std::vector<Piece> pieces;
   for (auto& f : futures) {
     auto p = f.get();
     pieces.insert(pieces.end(), p.begin(), p.end());
   }
+  phase_seconds_[5] = Seconds(t_phase);
 
   // ---- 3. windows in the flat layout of rvn_poa_batch ----
   const std::uint64_t n_windows = first_window[T];
@@ -280,21 +269,40 @@ std::vector<std::unique_ptr<biosoup::NucleicAcid>> Polisher::Polish(
       }
     }
   }
-  for (std::size_t x = 0; x < pieces.size(); ++x) {
-    const auto& p = pieces[x];
-    biosoup::NucleicAcid view(*sequences[p.read]);
-    if (!p.strand) view.ReverseAndComplement();
-    const std::string d = view.InflateData(p.qb, p.qe - p.qb);
-    std::memcpy(&bases[seq_off[piece_seq[x]]], d.data(), d.size());
-    if (any_quality) {
-      if (!view.block_quality.empty()) {
-        const std::string qv = view.InflateQuality(p.qb, p.qe - p.qb);
-        std::memcpy(&quals[seq_off[piece_seq[x]]], qv.data(), qv.size());
-      } else {
-        std::memset(&quals[seq_off[piece_seq[x]]], '!' + 1, p.qe - p.qb);  // weight 1
-      }
+  // pieces of one read are contiguous (the futures were collected in read order):
+  // one (reverse complemented) view per read, reads spread over the pool
+  {
+    std::vector<std::future<void>> fills;
+    const std::size_t chunk = std::max<std::size_t>(256, pieces.size() / 1024 + 1);
+    for (std::size_t x0 = 0; x0 < pieces.size();) {
+      std::size_t x1 = std::min(pieces.size(), x0 + chunk);
+      while (x1 < pieces.size() && pieces[x1].read == pieces[x1 - 1].read) ++x1;
+      fills.emplace_back(thread_pool_->Submit(
+          [&](std::size_t x0, std::size_t x1) {
+            for (std::size_t x = x0; x < x1;) {
+              const std::uint32_t read = pieces[x].read;
+              biosoup::NucleicAcid view(*sequences[read]);
+              if (!pieces[x].strand) view.ReverseAndComplement();
+              for (; x < x1 && pieces[x].read == read; ++x) {
+                const auto& p = pieces[x];
+                const std::string d = view.InflateData(p.qb, p.qe - p.qb);
+                std::memcpy(&bases[seq_off[piece_seq[x]]], d.data(), d.size());
+                if (!any_quality) continue;
+                if (!view.block_quality.empty()) {
+                  const std::string qv = view.InflateQuality(p.qb, p.qe - p.qb);
+                  std::memcpy(&quals[seq_off[piece_seq[x]]], qv.data(), qv.size());
+                } else {
+                  std::memset(&quals[seq_off[piece_seq[x]]], '!' + 1, p.qe - p.qb);  // weight 1
+                }
+              }
+            }
+          },
+          x0, x1));
+      x0 = x1;
     }
+    for (auto& f : fills) f.get();
   }
+  phase_seconds_[2] = Seconds(t_phase);
 
   // ---- 4. GPU: consensus of every window ----
   const auto t0 = std::chrono::steady_clock::now();
@@ -307,6 +315,7 @@ std::vector<std::unique_ptr<biosoup::NucleicAcid>> Polisher::Polish(
   const std::uint8_t* status = nullptr;
   Check(ctx_, rvn_poa_results(ctx_, &cons, &cons_off, &status, nullptr, nullptr));
   poa_seconds_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  phase_seconds_[3] = Seconds(t_phase);
 
   // ---- 5. stitch ----
   std::vector<std::unique_ptr<biosoup::NucleicAcid>> dst;
@@ -325,6 +334,7 @@ std::vector<std::unique_ptr<biosoup::NucleicAcid>> Polisher::Polish(
       dst.emplace_back(new biosoup::NucleicAcid(targets[i]->name + tags, polished));
     }
   }
+  phase_seconds_[4] = Seconds(t_phase);
   return dst;
 }
 

@@ -83,7 +83,9 @@ def polish(targets, sequences, q=0.0, e=0.3, w=500, trim=True, m=3, n=-5, g=-4, 
         rs.names = lib.rvnh_polish_names(h).decode().split("\n")[:-1]
         st = lib.rvnh_polish_stats(h)
         stats = dict(windows=int(st[0]), polished_windows=int(st[1]), poa_seconds=st[2],
-                     seconds=st[3])
+                     seconds=st[3],
+                     phases_s=dict(map=st[4], align=st[5], pack=st[6], consensus=st[7],
+                                   stitch=st[8], pieces=st[9]))
         return rs, stats
     finally:
         lib.rvnh_polish_free(h)
