@@ -29,6 +29,9 @@
 // band changes nothing. The distances themselves come from the same column
 // kernel with a doubling band.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
 
 #include "engine.cuh"
@@ -51,18 +54,20 @@ struct AlnPair {
 };
 
 __host__ __device__ inline uint64_t PackedWords(uint32_t len) { return (len + 31ULL) / 32 + 2; }
-__host__ __device__ inline uint32_t PeqWords(uint32_t len) { return (len + 63) / 64 + 1; }
+// (+1: funnel shift of the last block, +4: the grouped loads of ColumnsKernel read ahead)
+__host__ __device__ inline uint32_t PeqWords(uint32_t len) { return (len + 63) / 64 + 5; }
 
 struct ColTask {
   uint64_t peq;      // masks of this direction; symbol stride pb
   uint64_t tarr;     // packed target of this direction
   uint64_t scores;   // m + 1 entries in the score scratch, or ~0
+  uint64_t carry;    // cols + 1 entries in the carry scratch (warp kernel)
   uint32_t pb;
   uint32_t q0, m;    // rows: bases [q0, q0 + m) of the (reversed) query
   uint32_t t0, cols; // columns: bases [t0, t0 + cols) of the (reversed) target
   int32_t k;
   uint32_t out;      // dist[out]
-  uint32_t pad;
+  uint32_t mode;     // 1: dist = min over the rows of the last column (prefix estimate)
 };
 
 struct PathTask {
@@ -154,11 +159,13 @@ __device__ __forceinline__ int BandHi(int j, int k, int m) {
 // D[r][cols], r = 0..m, of rows [q0, q0+m) x columns [t0, t0+cols) inside the band
 // |row - column| <= k (block granularity); dist = D[m][cols] if the band reaches
 // it and it is <= k, else -1. Entries <= k are exact.
+template <bool SMEM>
 __global__ void __launch_bounds__(64)
 ColumnsKernel(const ColTask* __restrict__ tasks, uint32_t n_tasks, uint32_t ring,
               const uint64_t* __restrict__ arena, const uint64_t* __restrict__ peq,
               uint64_t* __restrict__ scratch, int32_t* __restrict__ scores,
               int32_t* __restrict__ dist) {
+  extern __shared__ uint64_t sh_vec[];  // SMEM: [2][ring][64]
   const uint32_t tid = blockIdx.x * 64 + threadIdx.x;
   if (tid >= n_tasks) return;
   const ColTask t = tasks[tid];
@@ -169,13 +176,15 @@ ColumnsKernel(const ColTask* __restrict__ tasks, uint32_t n_tasks, uint32_t ring
     dist[t.out] = cols <= k ? cols : -1;
     return;
   }
-  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * 64;
-  uint64_t* pv = scratch + tid;
-  uint64_t* mv = scratch + static_cast<uint64_t>(ring) * stride + tid;
+  // the band's vertical delta vectors: a ring of `ring` blocks, [slot][thread]
+  const uint64_t stride = SMEM ? 64 : static_cast<uint64_t>(gridDim.x) * 64;
+  uint64_t* pv = SMEM ? sh_vec + threadIdx.x : scratch + tid;
+  uint64_t* mv = pv + static_cast<uint64_t>(ring) * stride;
   const uint64_t* P = peq + t.peq;
   const uint64_t* T = arena + t.tarr;
   const int blocks = (m + 63) >> 6;
   const uint64_t last_high = 1ULL << ((m - 1) & 63);
+  const uint32_t sh = t.q0 & 63;  // every block of the task starts at the same bit of a mask word
   auto rows_of = [&](int b) { return min(64, m - (b << 6)); };
 
   int lo = 0;
@@ -195,17 +204,45 @@ ColumnsKernel(const ColTask* __restrict__ tasks, uint32_t n_tasks, uint32_t ring
     }
     lo = max(lo, BandLo(j, k));
     const uint32_t sym = BaseAt(T, static_cast<uint64_t>(t.t0) + j - 1);
-    const uint64_t* Ps = P + static_cast<uint64_t>(sym) * t.pb;
+    // mask words of this column's symbol, four blocks per round of loads
+    const uint64_t* Ps = P + static_cast<uint64_t>(sym) * t.pb + ((t.q0 + (lo << 6)) >> 6);
     int h = 1;  // row 0 for lo == 0; an upper bound once the band has left row 0
-    for (int b = lo; b <= hi; ++b) {
-      const uint64_t at = (b % ring) * stride;
-      uint64_t p = pv[at], q = mv[at];
-      h = Step(RowsEq(Ps, t.q0 + (b << 6), rows_of(b)), h,
-               b == blocks - 1 ? last_high : (1ULL << 63), p, q);
-      pv[at] = p;
-      mv[at] = q;
+    uint32_t slot = static_cast<uint32_t>(lo) % ring;
+    uint64_t x0 = Ps[0];
+    for (int b = lo; b <= hi; b += 4, Ps += 4) {
+      const uint64_t x1 = Ps[1], x2 = Ps[2], x3 = Ps[3], x4 = Ps[4];
+      const uint64_t xs[5] = {x0, x1, x2, x3, x4};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (b + u <= hi) {
+          uint64_t e = xs[u] >> sh;
+          if (sh) e |= xs[u + 1] << (64 - sh);
+          const int rows = rows_of(b + u);
+          if (rows < 64) e &= (1ULL << rows) - 1ULL;
+          const uint64_t at = slot * stride;
+          uint64_t p = pv[at], q = mv[at];
+          h = Step(e, h, b + u == blocks - 1 ? last_high : (1ULL << 63), p, q);
+          pv[at] = p;
+          mv[at] = q;
+          slot = slot + 1 == ring ? 0 : slot + 1;
+        }
+      }
+      x0 = x4;
     }
     score += h;
+  }
+  if (t.mode == 1) {  // smallest value of the column inside the band
+    int best = (lo == 0 && cols <= k) ? cols : kFar;
+    int v = score;
+    for (int b = hi; b >= lo; --b) {
+      const uint64_t p = pv[(b % ring) * stride], q = mv[(b % ring) * stride];
+      for (int bit = rows_of(b) - 1; bit >= 0; --bit) {
+        best = min(best, v);
+        v -= static_cast<int>((p >> bit) & 1) - static_cast<int>((q >> bit) & 1);
+      }
+    }
+    dist[t.out] = best <= k ? best : -1;
+    return;
   }
   dist[t.out] = (hi == blocks - 1 && score <= k) ? score : -1;
   if (S) {
@@ -219,6 +256,128 @@ ColumnsKernel(const ColTask* __restrict__ tasks, uint32_t n_tasks, uint32_t ring
         v -= static_cast<int>((p >> bit) & 1) - static_cast<int>((q >> bit) & 1);
       }
     }
+  }
+}
+
+// The same columns for a WIDE band, one WARP per problem. The band is cut into
+// strips of 32 consecutive blocks; inside a strip lane l owns block 32s + l (its
+// vectors, its bottom value and its four match masks stay in registers) and the
+// strip is swept as a wavefront: at step tau lane l computes column tau - l and
+// hands its horizontal delta and bottom value to lane l + 1 by shuffle. The last
+// lane of a strip leaves both, per column, in global scratch for lane 0 of the next
+// strip. The serial chain of a 10 kb x 10 kb problem shrinks from ~1e6 dependent
+// block steps to ~2.5e4 wavefront steps. Same recurrences as ColumnsKernel, same
+// results: block b is in the band for columns [max(1, 64b+1-k), 64(b+1)+k].
+__global__ void __launch_bounds__(128)
+ColumnsWarpKernel(const ColTask* __restrict__ tasks, uint32_t n_tasks,
+                  const uint64_t* __restrict__ arena, const uint64_t* __restrict__ peq,
+                  int32_t* __restrict__ carry_scratch, int32_t* __restrict__ scores,
+                  int32_t* __restrict__ dist) {
+  const uint32_t wid = (blockIdx.x * 128 + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= n_tasks) return;
+  const ColTask t = tasks[wid];
+  const int m = static_cast<int>(t.m), cols = static_cast<int>(t.cols), k = t.k;
+  int32_t* S = t.scores == ~0ULL ? nullptr : scores + t.scores;
+  if (m == 0) {
+    if (lane == 0) {
+      if (S) S[0] = cols;
+      dist[t.out] = cols <= k ? cols : -1;
+    }
+    return;
+  }
+  const uint64_t* P = peq + t.peq;
+  const uint64_t* T = arena + t.tarr;
+  int32_t* carry = carry_scratch + t.carry;
+  const int blocks = (m + 63) >> 6;
+  const uint64_t last_high = 1ULL << ((m - 1) & 63);
+  const uint32_t sh = t.q0 & 63;
+  const int hi0 = BandHi(0, k, m);
+  const int hi_fin = BandHi(cols, k, m);
+  const int lo_fin = cols > 0 ? BandLo(cols, k) : 0;
+  if (S) {
+    for (int r = lane; r <= m; r += 32) S[r] = kFar;
+  }
+  if (lane == 0) dist[t.out] = -1;
+  __syncwarp();
+  if (S && lane == 0 && cols <= k) S[0] = cols;
+  int best = (lane == 0 && cols <= k) ? cols : kFar;  // mode 1
+
+  for (int s = 0; 32 * s <= hi_fin; ++s) {
+    const int b = 32 * s + lane;
+    const bool valid = b <= hi_fin;
+    const int last_lane = min(31, hi_fin - 32 * s);
+    const bool more = 32 * (s + 1) <= hi_fin;  // another strip follows
+    const int jin = b <= hi0 ? 1 : 64 * b + 1 - k;
+    const int jout = min(cols, 64 * (b + 1) + k);
+    const int above_out = min(cols, 64 * b + k);  // last column with block b - 1 in the band
+    const int rows = valid ? min(64, m - (b << 6)) : 0;
+    const uint64_t high = b == blocks - 1 ? last_high : (1ULL << 63);
+    uint64_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+    if (valid) {
+      const uint32_t w = (t.q0 + (static_cast<uint32_t>(b) << 6)) >> 6;
+      const uint64_t mask = rows < 64 ? (1ULL << rows) - 1ULL : ~0ULL;
+      auto load = [&](uint32_t sym) {
+        const uint64_t* Ps = P + static_cast<uint64_t>(sym) * t.pb + w;
+        uint64_t e = Ps[0] >> sh;
+        if (sh) e |= Ps[1] << (64 - sh);
+        return e & mask;
+      };
+      e0 = load(0);
+      e1 = load(1);
+      e2 = load(2);
+      e3 = load(3);
+    }
+    uint64_t pv = ~0ULL, mv = 0;
+    int bottom = b <= hi0 ? min(m, (b + 1) << 6) : 0;
+    int out_h = 0, out_b = 0;
+    uint64_t tword = 0;
+    const int first_jin = 32 * s <= hi0 ? 1 : 64 * (32 * s) + 1 - k;
+    const int tau1 = min(cols, 64 * (32 * s + last_lane + 1) + k) + last_lane;
+    // lane 0 of a later strip reads what the previous strip left, one step ahead
+    int enc_next = 0;
+    if (s > 0 && lane == 0 && first_jin <= cols) enc_next = carry[first_jin];
+    for (int tau = first_jin; tau <= tau1; ++tau) {
+      const int j = tau - lane;
+      int in_h = __shfl_up_sync(0xFFFFFFFFu, out_h, 1);
+      int in_b = __shfl_up_sync(0xFFFFFFFFu, out_b, 1);
+      if (lane == 0 && s > 0) {
+        in_h = (enc_next & 3) - 1;
+        in_b = enc_next >> 2;
+        if (j + 1 <= cols) enc_next = carry[j + 1];
+      }
+      if (valid && j >= jin && j <= jout) {
+        const uint64_t pos = static_cast<uint64_t>(t.t0) + j - 1;
+        if (j == jin || (pos & 31) == 0) tword = T[pos >> 5];
+        const uint32_t sym = static_cast<uint32_t>(tword >> ((pos & 31) << 1)) & 3u;
+        const uint64_t e = sym == 0 ? e0 : sym == 1 ? e1 : sym == 2 ? e2 : e3;
+        const int h = (b > 0 && j <= above_out) ? in_h : 1;
+        if (j == jin && b > hi0) bottom = in_b - in_h + rows;  // the block enters the band
+        const int hout = Step(e, h, high, pv, mv);
+        bottom += hout;
+        out_h = hout;
+        out_b = bottom;
+        if (more && lane == last_lane) carry[j] = (bottom << 2) | (hout + 1);
+      }
+    }
+    // the last column: rows of the blocks still in the band
+    if (valid && b >= lo_fin) {
+      if (b == blocks - 1) dist[t.out] = bottom <= k ? bottom : -1;
+      if (S || t.mode == 1) {
+        int v = bottom;
+        for (int bit = rows - 1; bit >= 0; --bit) {
+          if (S) S[(b << 6) + bit + 1] = v;
+          best = min(best, v);
+          v -= static_cast<int>((pv >> bit) & 1) - static_cast<int>((mv >> bit) & 1);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (t.mode == 1) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+    if (lane == 0) dist[t.out] = best <= k ? best : -1;
   }
 }
 
@@ -408,7 +567,7 @@ void AlignBreakingPoints(Ctx& c, uint64_t n, const uint32_t* q_read, const uint3
   TimerBegin(c, "align_path");
   DevBuf<AlnPair> d_pairs;
   DevBuf<uint64_t> d_arena, d_peq, d_first, d_last;
-  DevBuf<int32_t> d_dist, d_scores;
+  DevBuf<int32_t> d_dist, d_scores, d_carry;
   DevBuf<ColTask> d_cols;
   DevBuf<SplitTask> d_splits;
   DevBuf<PathTask> d_children;
@@ -416,7 +575,7 @@ void AlignBreakingPoints(Ctx& c, uint64_t n, const uint32_t* q_read, const uint3
   DevBuf<uint32_t> d_err;
   d_pairs.reserve(n);
   d_arena.reserve(arena_words + 4);
-  d_peq.reserve(peq_words + 4);
+  d_peq.reserve(peq_words + 8);
   d_first.reserve(n_slots + 1);
   d_last.reserve(n_slots + 1);
   d_err.reserve(1);
@@ -433,40 +592,120 @@ void AlignBreakingPoints(Ctx& c, uint64_t n, const uint32_t* q_read, const uint3
   RVN_LAUNCH_CHECK();
   c.launches += 2;
 
+  const bool trace = std::getenv("RVN_ALIGN_TRACE") != nullptr;
+  auto t_trace = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    RVN_CUDA(cudaStreamSynchronize(c.stream));
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[rvn::AlignBreakingPoints] %-28s %8.1f ms\n", what,
+                 std::chrono::duration<double, std::milli>(now - t_trace).count());
+    t_trace = now;
+  };
   auto ring_of = [](uint32_t m, int32_t k) {
     const uint32_t blocks = (m + 63) / 64;
     return std::max<uint32_t>(1, std::min<uint32_t>(blocks, (2u * static_cast<uint32_t>(k) >> 6) + 2));
+  };
+  constexpr uint32_t kWarpRing = 24;   // bands of this many blocks or more: warp kernel
+  constexpr uint32_t kSmemRing = 208;  // 208 KB of the 227 KB a CTA may use
+  auto ring_class = [](uint32_t ring) {
+    uint32_t c = 3;  // rings up to 8, 16, 32, ... slots
+    while ((1u << c) < ring) ++c;
+    return c;
   };
   // one launch of the column kernel over `tasks` (sorted by cost so that the lanes
   // of a warp carry similar work); results in h_dist[task.out]
   std::vector<int32_t> h_dist;
   auto run_columns = [&](std::vector<ColTask>& tasks, uint64_t score_entries, uint32_t n_out) {
+    const auto t_enter = std::chrono::steady_clock::now();
     std::sort(tasks.begin(), tasks.end(), [&](const ColTask& a, const ColTask& b) {
       return static_cast<uint64_t>(a.cols) * ring_of(a.m, a.k) >
              static_cast<uint64_t>(b.cols) * ring_of(b.m, b.k);
     });
-    uint32_t ring = 1;
-    for (const auto& t : tasks) ring = std::max(ring, ring_of(t.m, t.k));
     const uint32_t nt = static_cast<uint32_t>(tasks.size());
-    const uint64_t threads = static_cast<uint64_t>(CeilDiv(nt, 64)) * 64;
-    uint64_t* scratch = c.m_scratch64.reserve(2ULL * ring * threads + 16);
+    // wide bands: one warp per problem (ColumnsWarpKernel); the others one thread
+    // per problem, launched by band size class - the vectors of a class live in
+    // shared memory ([2][ring][64] per CTA)
+    const auto wide = [&](const ColTask& t) { return ring_of(t.m, t.k) >= kWarpRing; };
+    const uint32_t nw = static_cast<uint32_t>(
+        std::stable_partition(tasks.begin(), tasks.end(), wide) - tasks.begin());
+    uint64_t carry_entries = 0;
+    for (uint32_t x = 0; x < nw; ++x) {
+      tasks[x].carry = carry_entries;
+      carry_entries += tasks[x].cols + 1ULL;
+    }
+    std::stable_sort(tasks.begin() + nw, tasks.end(), [&](const ColTask& a, const ColTask& b) {
+      return ring_class(ring_of(a.m, a.k)) > ring_class(ring_of(b.m, b.k));
+    });
     d_cols.reserve(nt);
     d_dist.reserve(n_out + 1);
     if (score_entries) d_scores.reserve(score_entries + 1);
+    if (carry_entries) d_carry.reserve(carry_entries + 1);
     RVN_CUDA(cudaMemcpyAsync(d_cols.get(), tasks.data(), nt * sizeof(ColTask),
                              cudaMemcpyHostToDevice, c.stream));
-    ColumnsKernel<<<CeilDiv(nt, 64), 64, 0, c.stream>>>(d_cols.get(), nt, ring, d_arena.get(),
-                                                       d_peq.get(), scratch, d_scores.get(),
-                                                       d_dist.get());
-    RVN_LAUNCH_CHECK();
-    ++c.launches;
+    if (nw) {
+      ColumnsWarpKernel<<<CeilDiv(nw, 4), 128, 0, c.stream>>>(d_cols.get(), nw, d_arena.get(),
+                                                             d_peq.get(), d_carry.get(),
+                                                             d_scores.get(), d_dist.get());
+      RVN_LAUNCH_CHECK();
+      ++c.launches;
+    }
+    uint32_t ring = 1;
+    for (uint32_t x0 = nw; x0 < nt;) {
+      const uint32_t cls = ring_class(ring_of(tasks[x0].m, tasks[x0].k));
+      uint32_t x1 = x0;
+      ring = 1;
+      while (x1 < nt && ring_class(ring_of(tasks[x1].m, tasks[x1].k)) == cls) {
+        ring = std::max(ring, ring_of(tasks[x1].m, tasks[x1].k));
+        ++x1;
+      }
+      const uint32_t cnt = x1 - x0;
+      if (ring <= kSmemRing) {
+        const size_t smem = 2ULL * ring * 64 * sizeof(uint64_t);
+        RVN_CUDA(cudaFuncSetAttribute(ColumnsKernel<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(2ULL * kSmemRing * 64 * sizeof(uint64_t))));
+        ColumnsKernel<true><<<CeilDiv(cnt, 64), 64, smem, c.stream>>>(
+            d_cols.get() + x0, cnt, ring, d_arena.get(), d_peq.get(), nullptr, d_scores.get(),
+            d_dist.get());
+      } else {
+        const uint64_t threads = static_cast<uint64_t>(CeilDiv(cnt, 64)) * 64;
+        uint64_t* scratch = c.m_scratch64.reserve(2ULL * ring * threads + 16);
+        ColumnsKernel<false><<<CeilDiv(cnt, 64), 64, 0, c.stream>>>(
+            d_cols.get() + x0, cnt, ring, d_arena.get(), d_peq.get(), scratch, d_scores.get(),
+            d_dist.get());
+      }
+      RVN_LAUNCH_CHECK();
+      ++c.launches;
+      x0 = x1;
+    }
+    if (trace) {
+      const auto t0 = std::chrono::steady_clock::now();
+      RVN_CUDA(cudaStreamSynchronize(c.stream));
+      uint64_t steps = 0;
+      for (const auto& t : tasks) steps += static_cast<uint64_t>(t.cols) * ring_of(t.m, t.k);
+      std::fprintf(stderr, "[rvn::AlignBreakingPoints]   columns: %u tasks (%u wide), %.2f G block steps, host %.1f ms, kernels %.1f ms\n",
+                   nt, nw, steps * 1e-9,
+                   std::chrono::duration<double, std::milli>(t0 - t_enter).count(),
+                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
   };
 
-  // ---- 1. distances: band doubling (edlib: k = 64, 128, ...) ----
+  lap("stage pairs");
+
+  // ---- 1. distances. edlib doubles the band from k = 64 until the distance fits;
+  // the distance is unique, so any schedule of k gives the same value. To skip the
+  // rounds that cannot succeed, the first k of a long pair is extrapolated from the
+  // error rate of its first kPrefix target columns (a banded, query-end-free run of
+  // the same kernel); pairs whose distance exceeds it double from there. ----
   std::vector<int32_t> dist(n, -1);
   {
+    constexpr uint32_t kPrefix = 384;
+    constexpr int32_t kPrefixBand = 96;
     std::vector<uint32_t> todo;
     std::vector<int64_t> kk(n);
+    std::vector<ColTask> probe;
+    std::vector<uint32_t> probed;
     for (uint64_t i = 0; i < n; ++i) {
       const int64_t m = q_len[i], t = t_len[i];
       if (m == 0 || t == 0) {
@@ -475,14 +714,36 @@ void AlignBreakingPoints(Ctx& c, uint64_t n, const uint32_t* q_read, const uint3
       }
       kk[i] = std::max<int64_t>(64, std::llabs(m - t));
       todo.push_back(static_cast<uint32_t>(i));
+      if (t >= 4 * kPrefix && m >= 4 * kPrefix) {
+        probe.push_back(ColTask{h[i].peq, h[i].arena + 2 * PackedWords(q_len[i]), ~0ULL, 0,
+                                PeqWords(q_len[i]), 0, q_len[i], 0, kPrefix, kPrefixBand,
+                                static_cast<uint32_t>(probed.size()), 1});
+        probed.push_back(static_cast<uint32_t>(i));
+      }
     }
+    if (!probe.empty()) {
+      run_columns(probe, 0, static_cast<uint32_t>(probed.size()));
+      h_dist.resize(probed.size());
+      RVN_CUDA(cudaMemcpyAsync(h_dist.data(), d_dist.get(), probed.size() * 4,
+                               cudaMemcpyDeviceToHost, c.stream));
+      RVN_CUDA(cudaStreamSynchronize(c.stream));
+      for (size_t x = 0; x < probed.size(); ++x) {
+        const uint32_t i = probed[x];
+        const int64_t longest = std::max(q_len[i], t_len[i]);
+        const int64_t guess = h_dist[x] >= 0
+                                  ? (longest * h_dist[x] * 5 / 4) / kPrefix + 48
+                                  : longest / 4;
+        kk[i] = std::max(kk[i], guess);
+      }
+    }
+    lap("distance: prefix estimate");
     std::vector<ColTask> tasks;
     while (!todo.empty()) {
       tasks.clear();
       for (uint32_t x = 0; x < todo.size(); ++x) {
         const uint32_t i = todo[x];
         const int32_t k = static_cast<int32_t>(std::min<int64_t>(kk[i], static_cast<int64_t>(q_len[i]) + t_len[i]));
-        tasks.push_back(ColTask{h[i].peq, h[i].arena + 2 * PackedWords(q_len[i]), ~0ULL,
+        tasks.push_back(ColTask{h[i].peq, h[i].arena + 2 * PackedWords(q_len[i]), ~0ULL, 0,
                                 PeqWords(q_len[i]), 0, q_len[i], 0, t_len[i], k, x, 0});
       }
       run_columns(tasks, 0, static_cast<uint32_t>(todo.size()));
@@ -503,6 +764,7 @@ void AlignBreakingPoints(Ctx& c, uint64_t n, const uint32_t* q_read, const uint3
       todo.swap(next);
     }
   }
+  lap("distance: band rounds");
 
   // ---- 2. Hirschberg levels ----
   std::vector<PathTask> level, children;
@@ -533,9 +795,9 @@ void AlignBreakingPoints(Ctx& c, uint64_t n, const uint32_t* q_read, const uint3
       SplitTask s{t, entries, entries + t.m + 1};
       entries += 2ULL * (t.m + 1);
       const uint32_t x = static_cast<uint32_t>(splits.size());
-      tasks.push_back(ColTask{p.peq, p.arena + 2 * qw, s.fw, pb, t.q0, t.m, t.t0, left, t.score,
+      tasks.push_back(ColTask{p.peq, p.arena + 2 * qw, s.fw, 0, pb, t.q0, t.m, t.t0, left, t.score,
                               2 * x, 0});
-      tasks.push_back(ColTask{p.peq + 4ULL * pb, p.arena + 2 * qw + tw, s.bw, pb,
+      tasks.push_back(ColTask{p.peq + 4ULL * pb, p.arena + 2 * qw + tw, s.bw, 0, pb,
                               p.q_len - t.q0 - t.m, t.m, p.t_len - t.t0 - t.n, right, t.score,
                               2 * x + 1, 0});
       splits.push_back(s);
@@ -543,6 +805,7 @@ void AlignBreakingPoints(Ctx& c, uint64_t n, const uint32_t* q_read, const uint3
     level.clear();
     if (splits.empty()) break;
     if (entries >= (1ULL << 62)) throw LimitError("score scratch");
+    lap("  level: tasks built");
     const uint32_t ns = static_cast<uint32_t>(splits.size());
     run_columns(tasks, entries, 2 * ns);
     d_splits.reserve(ns);
@@ -557,7 +820,10 @@ void AlignBreakingPoints(Ctx& c, uint64_t n, const uint32_t* q_read, const uint3
     RVN_CUDA(cudaMemcpyAsync(level.data(), d_children.get(), 2ULL * ns * sizeof(PathTask),
                              cudaMemcpyDeviceToHost, c.stream));
     RVN_CUDA(cudaStreamSynchronize(c.stream));
+    lap("  level: split rows + children");
   }
+
+  lap("hirschberg levels");
 
   // ---- 3. leaves: stored columns + traceback, in chunks of bounded scratch ----
   std::sort(leaves.begin(), leaves.end(), [](const LeafTask& a, const LeafTask& b) {
@@ -590,6 +856,8 @@ void AlignBreakingPoints(Ctx& c, uint64_t n, const uint32_t* q_read, const uint3
     x0 = x1;
   }
 
+  lap("leaves");
+
   // ---- 4. results ----
   std::vector<uint64_t> h_first(n_slots + 1), h_last(n_slots + 1);
   uint32_t h_err = 0;
@@ -598,6 +866,7 @@ void AlignBreakingPoints(Ctx& c, uint64_t n, const uint32_t* q_read, const uint3
   RVN_CUDA(cudaMemcpyAsync(&h_err, d_err.get(), 4, cudaMemcpyDeviceToHost, c.stream));
   RVN_CUDA(cudaStreamSynchronize(c.stream));
   TimerEnd(c);
+  lap("results");
   if (h_err) throw std::runtime_error("alignment path: no split row on an optimal path");
   for (uint64_t i = 0; i < n; ++i) distance[i] = dist[i];
   for (uint64_t s = 0; s < n_slots; ++s) {
