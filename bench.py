@@ -49,6 +49,10 @@ def parse():
     ap.add_argument("--genome", type=int, default=50_000_000)
     ap.add_argument("--mean-len", type=int, default=10_000)
     ap.add_argument("--cpu-sample-reads", type=int, default=20_000)
+    ap.add_argument("--index-batches", type=int, default=1,
+                    help="C4-shaped run: cut the read set into this many index batches "
+                         "(the reference starts a new batch every 2^32 bases, "
+                         "construct.cc:35; here the batch size is total bases / K)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--poa-windows", type=int, default=8192,
                     help="windows of the POA sub-benchmark (0 = skip)")
@@ -60,6 +64,12 @@ def parse():
 
 
 def workload_name(a):
+    if a.index_batches > 1:
+        return (f"C4-shaped: {a.reads} synthetic ONT reads ~{a.mean_len // 1000} kb over a "
+                f"{a.genome / 1e6:.0f} Mbp genome (40x, 10% error) in {a.index_batches} index "
+                f"batches (batch = total bases / {a.index_batches}; the reference's 2 M-read "
+                f"run has 5 batches of 2^32 bases), k={K} w={W} f={FREQ} "
+                f"kMaxNumOverlaps={KMAX}, stage-1 all-vs-all, -p 0")
     return (f"C2: {a.reads} synthetic ONT reads ~{a.mean_len // 1000} kb over a "
             f"{a.genome / 1e6:.0f} Mbp genome (40x, 10% error), k={K} w={W} f={FREQ} "
             f"kMaxNumOverlaps={KMAX}, stage-1 all-vs-all "
@@ -273,11 +283,18 @@ def main_ours(a):
 
     last = {}
 
+    def batch_bases(r):  # index batch size for --index-batches (0 = the reference's 2^32)
+        if a.index_batches <= 1:
+            return 0
+        return -(-int(r.lens.astype(np.uint64).sum()) // a.index_batches)
+
+    ib = batch_bases(prs)
+
     def step_resident():
         if world > 1:
-            last.update(de.find_overlaps_and_create_piles(FREQ, KMAX, False, fetch=False))
+            last.update(de.find_overlaps_and_create_piles(FREQ, KMAX, False, ib, fetch=False))
         else:
-            eng.find_overlaps_and_create_piles(FREQ, KMAX, False, fetch=False)
+            eng.find_overlaps_and_create_piles(FREQ, KMAX, False, ib, fetch=False)
 
     def step_e2e():
         (de if world > 1 else eng).upload(prs)
@@ -325,13 +342,14 @@ def main_ours(a):
     seng = engine.Engine(device=local)
     seng.configure(K, W)
     seng.upload(srs)
-    s_single = seng.find_overlaps_and_create_piles(FREQ, KMAX, False, fetch=True)
+    s_ib = batch_bases(srs)
+    s_single = seng.find_overlaps_and_create_piles(FREQ, KMAX, False, s_ib, fetch=True)
     parity = {"sample": f"{s_n} reads / {s_g / 1e6:.1f} Mbp genome ({srs.bases / 1e9:.3f} Gbp)",
               "sha256": result_sha256(s_single), "n_mapped": int(s_single["num_mapped"])}
     sample_ms = None
     if world > 1:
         de.upload(srs)
-        s_share = de.find_overlaps_and_create_piles(FREQ, KMAX, False, fetch=True)
+        s_share = de.find_overlaps_and_create_piles(FREQ, KMAX, False, s_ib, fetch=True)
         ok = same_result(s_share, share_of(s_single, rank, world))
         okt = torch.tensor([1 if ok else 0], device="cuda", dtype=torch.int32)
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
@@ -342,7 +360,7 @@ def main_ours(a):
     else:
         def sample_e2e():
             seng.upload(srs)
-            seng.find_overlaps_and_create_piles(FREQ, KMAX, False, fetch=True)
+            seng.find_overlaps_and_create_piles(FREQ, KMAX, False, s_ib, fetch=True)
         for _ in range(2):
             sample_e2e()
         t0 = time.perf_counter()
@@ -386,7 +404,7 @@ def main_ours(a):
             res = distributed.CudaSteps(eng, f"cuda:{local}").stage1_results()  # this rank's share
             d2h = int(res["overlaps"].nbytes + res["ovl_off"].nbytes + res["pile"].nbytes)
         else:
-            res = eng.find_overlaps_and_create_piles(FREQ, KMAX, False, fetch=True)
+            res = eng.find_overlaps_and_create_piles(FREQ, KMAX, False, ib, fetch=True)
             d2h = int(res["overlaps"].nbytes + res["ovl_off"].nbytes + res["pile"].nbytes
                       + n_mapped * 32)
         out = {
@@ -440,7 +458,7 @@ def main_ours(a):
             out["poa"] = dict(out.get("poa", {}), c3=bench_c3(a, not a.no_cpu_baseline))
         if world == 1 and a.c5_reads > 0:
             out["c5"] = bench_c5(a, local, not a.no_cpu_baseline)
-        if world == 1 and not a.no_cpu_baseline:
+        if world == 1 and not a.no_cpu_baseline and a.index_batches <= 1:
             step, n_map_cpu, kind, threads, sample = run_cpu(a, "reference")
             dt, cpu_res = step()
             out["cpu_baseline"] = {"value": n_map_cpu / dt, "unit": "overlaps/s",

@@ -260,7 +260,10 @@ int rvn_get_stats(rvn_ctx* ctx, rvn_stats* out);
 
 /* options: "keep_hits" (0/1); "tier_min_records" (stage 1 splits an index batch of
  * at least that many minimizers into a probe-able tier and bare keys, default
- * 2^18; 0 = always); "reset_stats". Unknown name -> RVN_ERR_INVALID. */
+ * 2^18; 0 = always); "self_join" (0/1, default 1: the seed hits of a stage-1 flush
+ * whose reads are inside the index batch come from a self-join over the sorted
+ * index instead of a probe per micromizer); "reset_stats".
+ * Unknown name -> RVN_ERR_INVALID. */
 int rvn_set_option(rvn_ctx* ctx, const char* name, int64_t value);
 
 /* Device time (ms, CUDA events on the context's stream) of the phases of the

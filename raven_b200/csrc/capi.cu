@@ -65,7 +65,7 @@ void Stage1(Ctx& c, double freq, uint64_t kmax, bool minhash, uint64_t ib,
   c.own_rem = 0;
   // a stage-1 pass owns its intermediates: nothing is carried over from an
   // earlier call (sketches, micromizers and the index are rebuilt)
-  c.s_valid = c.q_valid = c.i_valid = c.r_valid = false;
+  c.s_valid = c.q_valid = c.qt_valid = c.i_valid = c.r_valid = false;
   TimerReset(c);
   std::memset(&c.stats, 0, sizeof(c.stats));
   const uint64_t launches0 = c.launches;
@@ -199,7 +199,7 @@ RVN_API int rvn_engine_configure(rvn_ctx* ctx, uint32_t k, uint32_t w,
     c.prm.chain = chain;
     c.prm.matches = matches;
     c.prm.gap = gap;
-    c.s_valid = c.q_valid = c.i_valid = c.r_valid = false;
+    c.s_valid = c.q_valid = c.qt_valid = c.i_valid = c.r_valid = false;
     c.tiles_k = 0;  // the tile table depends on (k, w)
     c.occurrence = 0xFFFFFFFFu;
   });
@@ -213,7 +213,7 @@ static void UploadReads(Ctx& c, const uint64_t* words, const uint64_t* word_off,
   res_last = std::min(res_last, n_reads);
   if (res_first > res_last) throw InvalidArgument("resident range out of bounds");
   if (n_reads == 0xFFFFFFFFu) throw LimitError("too many reads");
-  c.s_valid = c.q_valid = c.i_valid = c.r_valid = c.st_valid = false;
+  c.s_valid = c.q_valid = c.qt_valid = c.i_valid = c.r_valid = c.st_valid = false;
   c.tiles_k = 0;
   c.n_reads = n_reads;
   c.h_woff.assign(1, 0);
@@ -320,7 +320,7 @@ RVN_API int rvn_map_external(rvn_ctx* ctx, const uint64_t* words, uint32_t len,
     c.h_ids.push_back(id);
     c.h_tile_off.push_back(tile_tail[1]);
     c.n_reads = n + 1;
-    c.s_valid = c.q_valid = false;
+    c.s_valid = c.q_valid = c.qt_valid = false;
     // the rider's bases are resident for the duration of the call (EnsureSketch
     // refuses reads outside [res_first, res_last))
     const uint32_t res_first0 = c.res_first, res_last0 = c.res_last;
@@ -332,7 +332,7 @@ RVN_API int rvn_map_external(rvn_ctx* ctx, const uint64_t* words, uint32_t len,
       c.n_reads = n;
       c.h_woff.pop_back(); c.h_len.pop_back(); c.h_ids.pop_back();
       c.h_tile_off.pop_back();
-      c.s_valid = c.q_valid = false;
+      c.s_valid = c.q_valid = c.qt_valid = false;
     };
     try {
       // an id below an indexed id breaks the "kept postings are a suffix" shortcut
@@ -655,6 +655,8 @@ RVN_API int rvn_set_option(rvn_ctx* ctx, const char* name, int64_t value) {
   return Guard(ctx, [&](Ctx& c) {
     if (name && std::strcmp(name, "keep_hits") == 0) {
       c.keep_hits = value != 0;
+    } else if (name && std::strcmp(name, "self_join") == 0) {
+      c.self_join = value != 0;
     } else if (name && std::strcmp(name, "tier_min_records") == 0) {
       c.tier_min_records = value < 0 ? 0 : static_cast<uint64_t>(value);
     } else if (name && std::strcmp(name, "reset_stats") == 0) {
@@ -772,7 +774,7 @@ RVN_API int rvn_dist_overlaps_split(rvn_ctx* ctx, uint32_t n_parts, uint32_t ran
 
 RVN_API int rvn_dist_stage1_begin(rvn_ctx* ctx, uint32_t n_parts, uint32_t rank) {
   return Guard(ctx, [&](Ctx& c) {
-    c.s_valid = c.q_valid = c.i_valid = c.r_valid = false;
+    c.s_valid = c.q_valid = c.qt_valid = c.i_valid = c.r_valid = false;
     TimerReset(c);
     std::memset(&c.stats, 0, sizeof(c.stats));
     DistStage1Begin(c, n_parts, rank);

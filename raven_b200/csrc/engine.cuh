@@ -75,6 +75,14 @@ struct Ctx {
   DevBuf<uint64_t> q_val, q_org, q_off;
   bool q_is32 = false;  // q_val holds u32 values
   std::vector<uint64_t> h_q_off;
+  // micromizer thresholds of reads [qt_first, qt_last): record (value, position) of read r
+  // is a micromizer iff value < qt_val[r] || (value == qt_val[r] && position < qt_pos[r])
+  bool qt_valid = false;
+  uint32_t qt_first = 0, qt_last = 0;
+  DevBuf<uint64_t> qt_val;
+  DevBuf<uint32_t> qt_pos;
+  bool i_from_sketch = false;  // the index holds the FULL sketches of reads [i_first, i_last)
+  int64_t self_join = 1;       // option: stage-1 hits by a self-join over the index
 
   // ---- index ----
   bool i_valid = false;
@@ -217,6 +225,7 @@ void EnsureSketch(Ctx& c, uint32_t first, uint32_t last);
 // micromizers of reads [first,last) into c.q_* (needs the sketch of a range
 // that contains [first,last))
 void EnsureMicromizers(Ctx& c, uint32_t first, uint32_t last);
+void EnsureThresholds(Ctx& c, uint32_t first, uint32_t last);
 
 // ---- index.cu ----
 // value_limit: records whose value exceeds it are counted (occurrence threshold)

@@ -257,13 +257,13 @@ TierScatterKernel(const uint32_t* __restrict__ val, const uint64_t* __restrict__
   }
 }
 
-__global__ void MaxU32Kernel(const uint32_t* __restrict__ v, uint64_t n,
-                             unsigned int* __restrict__ out) {
-  uint32_t m = 0;
+__global__ void MaxU64Kernel(const uint64_t* __restrict__ v, uint64_t n,
+                             unsigned long long* __restrict__ out) {
+  unsigned long long m = 0;
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += stride) {
-    m = max(m, v[i]);
+    m = max(m, static_cast<unsigned long long>(v[i]));
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, d));
@@ -272,19 +272,20 @@ __global__ void MaxU32Kernel(const uint32_t* __restrict__ v, uint64_t n,
 
 }  // namespace
 
-// largest micromizer value of reads [first, last) (their micromizers in c.q_*)
+// largest micromizer value of reads [first, last): the largest of their selection
+// thresholds (c.qt_val)
 uint64_t MaxMicromizerValue(Ctx& c, uint32_t first, uint32_t last) {
-  EnsureMicromizers(c, first, last);
-  if (c.q_n == 0) return 0;
-  if (!c.q_is32) return ~0ULL;  // (tiers are only built over u32 values)
+  EnsureThresholds(c, first, last);
+  if (last <= first) return 0;
+  if (!c.s_is32) return ~0ULL;  // (tiers are only built over u32 values)
   uint64_t* w = c.m_counter.reserve(8);
   RVN_CUDA(cudaMemsetAsync(w, 0, sizeof(uint64_t), c.stream));
-  MaxU32Kernel<<<std::min<unsigned>(CeilDiv(c.q_n, 256), 148 * 8), 256, 0, c.stream>>>(
-      reinterpret_cast<const uint32_t*>(c.q_val.get()), c.q_n,
-      reinterpret_cast<unsigned int*>(w));
+  const uint64_t n = last - first;
+  MaxU64Kernel<<<std::min<unsigned>(CeilDiv(n, 256), 148 * 8), 256, 0, c.stream>>>(
+      c.qt_val.get(), n, reinterpret_cast<unsigned long long*>(w));
   RVN_LAUNCH_CHECK();
   ++c.launches;
-  return ReadU64(c, w) & 0xFFFFFFFFULL;
+  return ReadU64(c, w);
 }
 
 void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash, uint64_t value_limit) {
@@ -306,12 +307,14 @@ void BuildIndex(Ctx& c, uint32_t first, uint32_t last, bool minhash, uint64_t va
   c.i_last = last;
   BuildIndexFrom(c, src_val, src_org, n, bases, minhash ? ~0ULL : value_limit);
   c.i_sorted_ids = c.ids_ascending;
+  c.i_from_sketch = !minhash;
 }
 
 void BuildIndexFrom(Ctx& c, ValView src_val, const uint64_t* src_org, uint64_t n,
                     uint64_t index_bases, uint64_t value_limit) {
   c.i_valid = false;
   c.i_sorted_ids = false;
+  c.i_from_sketch = false;
   c.occurrence = 0xFFFFFFFFu;
   if (n >= 0xFFFFFFFFULL) {
     throw LimitError("index batch holds 2^32 or more minimizers");

@@ -284,6 +284,96 @@ ExpandWarpKernel(IndexView ix, const uint64_t* __restrict__ q_org, uint64_t q_be
   }
 }
 
+// ---- stage-1 hits by a self-join over the index ----
+// In stage 1 (construct.cc:59-64) the queries of a flush are the micromizers of reads
+// that are themselves in the index, so every query IS a posting of the run of its
+// value: a posting (value v, read r, position p) is a query iff it passes r's
+// selection rule (thr_val, thr_pos; sketch.cu), and its hits are the postings of the
+// same run with a larger read id - the ones that follow it, the run being in read
+// order. No query sort, no table probe, no binary search: two sweeps over the sorted
+// postings (count, then emit through per-read cursors; the order of the hits inside
+// a read is free, see the header). Runs longer than `occurrence` give no hits.
+struct JoinView {
+  ValView val;
+  const uint64_t* org;
+  uint64_t n;
+  uint32_t occurrence;
+  const uint64_t* thr_val;  // of reads [thr_first, ...)
+  const uint32_t* thr_pos;
+  uint32_t thr_first;
+  uint32_t first, last;     // query reads of this flush
+};
+
+// number of hits of posting i (read r, value v) and the offset of the first one
+__device__ __forceinline__ uint32_t JoinKept(const JoinView& jv, uint64_t i, uint64_t v,
+                                             uint32_t r, uint32_t* skip) {
+  uint32_t fw = 0, same = 0;
+  for (uint64_t j = i + 1; j < jv.n && jv.val[j] == v; ++j) {
+    ++fw;
+    if (fw > jv.occurrence) return 0;
+    if (static_cast<uint32_t>(jv.org[j] >> 32) == r) ++same;
+  }
+  if (fw == same) return 0;
+  if (jv.occurrence != 0xFFFFFFFFu) {
+    uint32_t len = fw + 1;
+    for (uint64_t j = i; j > 0 && jv.val[j - 1] == v; --j) {
+      if (++len > jv.occurrence) return 0;
+    }
+  }
+  *skip = same;
+  return fw - same;
+}
+
+__device__ __forceinline__ bool JoinIsQuery(const JoinView& jv, uint64_t v, uint64_t o) {
+  const uint32_t r = static_cast<uint32_t>(o >> 32);
+  if (r < jv.first || r >= jv.last) return false;
+  const uint64_t t = jv.thr_val[r - jv.thr_first];
+  return v < t || (v == t && (static_cast<uint32_t>(o) >> 1) < jv.thr_pos[r - jv.thr_first]);
+}
+
+__global__ void __launch_bounds__(kThreads)
+JoinCountKernel(JoinView jv, uint32_t* __restrict__ read_cnt, unsigned long long* __restrict__ n_queries) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  bool is_q = false;
+  if (i < jv.n) {
+    const uint64_t v = jv.val[i], o = jv.org[i];
+    is_q = JoinIsQuery(jv, v, o);
+    if (is_q) {
+      uint32_t skip;
+      const uint32_t r = static_cast<uint32_t>(o >> 32);
+      const uint32_t kept = JoinKept(jv, i, v, r, &skip);
+      if (kept) atomicAdd(read_cnt + (r - jv.first), kept);
+    }
+  }
+  const uint32_t q = __popc(__ballot_sync(0xFFFFFFFFu, is_q));
+  if ((threadIdx.x & 31) == 0 && q) atomicAdd(n_queries, static_cast<unsigned long long>(q));
+}
+
+__global__ void __launch_bounds__(kThreads)
+JoinEmitKernel(JoinView jv, const uint64_t* __restrict__ read_hit_off,
+               uint32_t* __restrict__ cursor, uint64_t* __restrict__ h_grp,
+               uint64_t* __restrict__ h_pos) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (i >= jv.n) return;
+  const uint64_t v = jv.val[i], lo = jv.org[i];
+  if (!JoinIsQuery(jv, v, lo)) return;
+  const uint32_t r = static_cast<uint32_t>(lo >> 32);
+  uint32_t skip = 0;
+  const uint32_t kept = JoinKept(jv, i, v, r, &skip);
+  if (!kept) return;
+  uint64_t at = read_hit_off[r - jv.first] + atomicAdd(cursor + (r - jv.first), kept);
+  const uint64_t lhs_pos = static_cast<uint32_t>(lo) >> 1;
+  for (uint32_t x = 0; x < kept; ++x, ++at) {
+    const uint64_t o = jv.org[i + 1 + skip + x];
+    const uint64_t rhs_id = o >> 32;
+    const uint64_t strand = (lo & 1) == (o & 1);
+    const uint64_t rhs_pos = static_cast<uint32_t>(o) >> 1;
+    const uint64_t diagonal = !strand ? rhs_pos + lhs_pos : rhs_pos - lhs_pos + (3ULL << 30);
+    h_grp[at] = (((rhs_id << 1) | strand) << 32) | diagonal;
+    h_pos[at] = (lhs_pos << 32) | rhs_pos;
+  }
+}
+
 // per-read offsets out of per-record offsets
 __global__ void GatherU64(const uint64_t* __restrict__ src,
                           const uint64_t* __restrict__ idx, uint64_t idx_base,
@@ -1495,6 +1585,48 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
   c.r_valid = false;
   const uint32_t nr = last - first;
 
+  // ---- stage 1 with the query reads inside the index batch: self-join ----
+  const bool join = c.self_join && minhash && avoid_equal && avoid_symmetric && !want_filtered &&
+                    c.i_from_sketch && c.i_sorted_ids && c.ids_identity && first >= c.i_first &&
+                    last <= c.i_last && c.qt_valid && c.qt_first <= first && last <= c.qt_last;
+  uint64_t n_q = 0, n_hits = 0;
+  uint64_t *hg = nullptr, *hp = nullptr;
+  uint64_t* read_hit_off = c.m_read_hit_off.reserve(nr + 2ULL);
+  std::vector<uint64_t> h_rho(nr + 1ULL);
+  if (join) {
+    JoinView jv{ValView{c.i_val.get(), c.i_is32 ? 1 : 0}, c.i_org.get(), c.i_n, c.occurrence,
+                c.qt_val.get(), c.qt_pos.get(), c.qt_first, first, last};
+    TimerBegin(c, "probe");
+    uint32_t* rcnt = c.m_cnt.reserve(2ULL * nr + 2);
+    uint32_t* cursor = rcnt + nr + 1;
+    uint64_t* counter = c.m_counter.reserve(8);
+    RVN_CUDA(cudaMemsetAsync(rcnt, 0, (2ULL * nr + 2) * sizeof(uint32_t), c.stream));
+    RVN_CUDA(cudaMemsetAsync(counter, 0, sizeof(uint64_t), c.stream));
+    if (c.i_n > 0) {
+      JoinCountKernel<<<CeilDiv(c.i_n, kThreads), kThreads, 0, c.stream>>>(
+          jv, rcnt, reinterpret_cast<unsigned long long*>(counter));
+      RVN_LAUNCH_CHECK();
+      ++c.launches;
+    }
+    ExclusiveScanU32(c, rcnt, read_hit_off, nr);
+    RVN_CUDA(cudaMemcpyAsync(h_rho.data(), read_hit_off, (nr + 1ULL) * sizeof(uint64_t),
+                             cudaMemcpyDeviceToHost, c.stream));
+    n_q = ReadU64(c, counter);
+    n_hits = h_rho[nr];
+    TimerEnd(c);
+    TimerBegin(c, "expand");
+    hg = c.h_grp.reserve(n_hits + 1);
+    hp = c.h_pos.reserve(n_hits + 1);
+    if (n_hits > 0) {
+      JoinEmitKernel<<<CeilDiv(c.i_n, kThreads), kThreads, 0, c.stream>>>(jv, read_hit_off,
+                                                                          cursor, hg, hp);
+      RVN_LAUNCH_CHECK();
+      ++c.launches;
+    }
+    TimerEnd(c);
+    c.r_filt_off.reserve(nr + 2ULL);
+    for (uint32_t i = 0; i <= nr; ++i) c.r_filt_off.get()[i] = 0;
+  } else {
   // ---- query records ----
   const uint64_t *qo, *d_read_off;
   ValView qv;  // query values: u32 for full sketches of k <= 15, else u64
@@ -1520,7 +1652,7 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
     off_base_read = first - c.s_first;
   }
   const uint64_t q_begin = (*h_read_off)[off_base_read];
-  const uint64_t n_q = (*h_read_off)[off_base_read + nr] - q_begin;
+  n_q = (*h_read_off)[off_base_read + nr] - q_begin;
 
   IndexView ix{ValView{c.i_val.get(), c.i_is32 ? 1 : 0}, c.i_org.get(), c.i_bucket.get(), c.i_n,
                c.i_shift, c.occurrence, c.i_limit};
@@ -1531,7 +1663,6 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
   uint32_t* frst = c.m_first.reserve(n_q + 1);
   uint8_t* filt = c.m_filt.reserve(n_q + 1);
   uint64_t* hit_off = c.m_hit_off.reserve(n_q + 2);
-  uint64_t n_hits = 0;
   // kept postings = a suffix of the run (or the whole run): see ProbeSuffixKernel
   const bool suffix = (avoid_equal && avoid_symmetric && c.i_sorted_ids) ||
                       (!avoid_equal && !avoid_symmetric);
@@ -1583,8 +1714,8 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
   }
   TimerEnd(c);
   TimerBegin(c, "expand");
-  uint64_t* hg = c.h_grp.reserve(n_hits + 1);
-  uint64_t* hp = c.h_pos.reserve(n_hits + 1);
+  hg = c.h_grp.reserve(n_hits + 1);
+  hp = c.h_pos.reserve(n_hits + 1);
   if (n_hits > 0) {
     if (suffix) {
       ExpandWarpKernel<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
@@ -1598,12 +1729,10 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
     ++c.launches;
   }
   // per-read hit ranges
-  uint64_t* read_hit_off = c.m_read_hit_off.reserve(nr + 2ULL);
   GatherU64<<<CeilDiv(nr + 1ULL, kThreads), kThreads, 0, c.stream>>>(
       hit_off, d_read_off + off_base_read, q_begin, nr + 1ULL, read_hit_off);
   RVN_LAUNCH_CHECK();
   ++c.launches;
-  std::vector<uint64_t> h_rho(nr + 1ULL);
   RVN_CUDA(cudaMemcpyAsync(h_rho.data(), read_hit_off,
                            (nr + 1ULL) * sizeof(uint64_t),
                            cudaMemcpyDeviceToHost, c.stream));
@@ -1640,6 +1769,8 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
                              cudaMemcpyDeviceToHost, c.stream));
     RVN_CUDA(cudaStreamSynchronize(c.stream));
   }
+
+  }  // (probe path)
 
   if (c.keep_hits) {
     uint64_t* g = c.r_hit_grp.reserve(n_hits + 1);
@@ -1682,7 +1813,6 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
   c.stats.query_records += n_q;
   c.stats.hits += n_hits;
   c.stats.overlaps += n_ovl;
-  (void)n_filtered;
 }
 
 }  // namespace rvn

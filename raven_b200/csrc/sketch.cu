@@ -561,17 +561,23 @@ __global__ void GatherReadOffsets(const uint64_t* __restrict__ tile_off,
 // position, back in position order ("minhash") ----
 constexpr int kMicroThreads = 256;
 
-template <typename ValT>
+// Besides (kWrite) the micromizers themselves, the selection rule of every read is
+// left behind as a pair (thr_val, thr_pos): record (value, position) of the read is
+// one of its micromizers iff value < thr_val || (value == thr_val && position <
+// thr_pos) - what the stage-1 self-join over the index asks of every posting.
+template <typename ValT, bool kWrite>
 __global__ void __launch_bounds__(kMicroThreads)
 MicromizeKernel(const ValT* __restrict__ s_val,
                 const uint64_t* __restrict__ s_org,
                 const uint64_t* __restrict__ s_off,  // per read of the sketch
                 uint32_t s_first, const uint64_t* __restrict__ q_off,
                 uint32_t q_first, uint32_t k,
-                ValT* __restrict__ q_val, uint64_t* __restrict__ q_org) {
+                ValT* __restrict__ q_val, uint64_t* __restrict__ q_org,
+                uint64_t* __restrict__ thr_val, uint32_t* __restrict__ thr_pos) {
   __shared__ uint32_t hist[256];
   __shared__ uint32_t sh_scan[34];
   __shared__ uint32_t sh_digit, sh_want;
+  __shared__ unsigned long long sh_max;
 
   const uint32_t r = q_first + blockIdx.x;
   const uint64_t b = s_off[r - s_first];
@@ -580,11 +586,30 @@ MicromizeKernel(const ValT* __restrict__ s_val,
   const uint32_t m = static_cast<uint32_t>(q_off[blockIdx.x + 1] - ob);
   const ValT* val = s_val + b;
   const uint64_t* org = s_org + b;
-  if (m == 0) return;
+  if (m == 0) {
+    if (threadIdx.x == 0) {
+      thr_val[blockIdx.x] = 0;
+      thr_pos[blockIdx.x] = 0;
+    }
+    return;
+  }
   if (m >= cnt) {  // keep everything
+    if (threadIdx.x == 0) sh_max = 0;
+    __syncthreads();
+    unsigned long long mx = 0;
     for (uint32_t i = threadIdx.x; i < cnt; i += kMicroThreads) {
-      q_val[ob + i] = val[i];
-      q_org[ob + i] = org[i];
+      const ValT v = val[i];
+      mx = max(mx, static_cast<unsigned long long>(v));
+      if (kWrite) {
+        q_val[ob + i] = v;
+        q_org[ob + i] = org[i];
+      }
+    }
+    atomicMax(&sh_max, mx);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      thr_val[blockIdx.x] = sh_max;
+      thr_pos[blockIdx.x] = 0xFFFFFFFFu;
     }
     return;
   }
@@ -641,11 +666,16 @@ MicromizeKernel(const ValT* __restrict__ s_val,
     const uint32_t eq_kept_before =
         min(eq_before, need_eq) - min(eq_seen, need_eq);
     const bool keep = is_lt || (is_eq && eq_before < need_eq);
-    if (keep) {
+    if (kWrite && keep) {
       const uint64_t d = ob + kept + lt_before + eq_kept_before;
       q_val[d] = static_cast<ValT>(v);
       q_org[d] = o;
     }
+    if (is_eq && eq_before + 1 == need_eq) {  // the last tie that is kept
+      thr_val[blockIdx.x] = T;
+      thr_pos[blockIdx.x] = (static_cast<uint32_t>(o) >> 1) + 1;
+    }
+    if (!kWrite && eq_seen + (tot >> 16) >= need_eq) break;  // (uniform) nothing left to learn
     const uint32_t eq_tot = tot >> 16, lt_tot = tot & 0xFFFF;
     kept += lt_tot + (min(eq_seen + eq_tot, need_eq) - min(eq_seen, need_eq));
     eq_seen += eq_tot;
@@ -782,12 +812,15 @@ void EnsureSketch(Ctx& c, uint32_t first, uint32_t last) {
   c.s_valid = true;
 }
 
-void EnsureMicromizers(Ctx& c, uint32_t first, uint32_t last) {
-  if (c.q_valid && c.q_first == first && c.q_last == last) return;
+namespace {
+
+// write == true: micromizers (c.q_*) and thresholds (c.qt_*); false: thresholds only
+void Micromize(Ctx& c, uint32_t first, uint32_t last, bool write) {
   if (!c.s_valid || first < c.s_first || last > c.s_last) {
     EnsureSketch(c, first, last);
   }
-  c.q_valid = false;
+  if (write) c.q_valid = false;
+  c.qt_valid = false;
   const uint32_t nr = last - first;
   c.h_q_off.assign(nr + 1ULL, 0);
   for (uint32_t i = 0; i < nr; ++i) {
@@ -801,29 +834,64 @@ void EnsureMicromizers(Ctx& c, uint32_t first, uint32_t last) {
   RVN_CUDA(cudaMemcpyAsync(qoff, c.h_q_off.data(),
                            (nr + 1ULL) * sizeof(uint64_t),
                            cudaMemcpyHostToDevice, c.stream));
-  uint64_t* qv = c.q_val.reserve(total);
-  uint64_t* qo = c.q_org.reserve(total);
-  if (nr > 0 && total > 0) {
+  uint64_t* qv = write ? c.q_val.reserve(total) : c.q_val.get();
+  uint64_t* qo = write ? c.q_org.reserve(total) : c.q_org.get();
+  uint64_t* tv = c.qt_val.reserve(nr + 1ULL);
+  uint32_t* tp = c.qt_pos.reserve(nr + 1ULL);
+  if (nr > 0) {
     TimerBegin(c, "micromize");
+    RVN_CUDA(cudaMemsetAsync(tv, 0, (nr + 1ULL) * sizeof(uint64_t), c.stream));
+    RVN_CUDA(cudaMemsetAsync(tp, 0, (nr + 1ULL) * sizeof(uint32_t), c.stream));
     if (c.s_is32) {  // micromizer values stay u32 like the sketch's
-      MicromizeKernel<uint32_t><<<nr, kMicroThreads, 0, c.stream>>>(
-          reinterpret_cast<const uint32_t*>(c.s_val.get()), c.s_org.get(), c.s_off.get(),
-          c.s_first, qoff, first, c.prm.k, reinterpret_cast<uint32_t*>(qv), qo);
+      auto* sv = reinterpret_cast<const uint32_t*>(c.s_val.get());
+      auto* q32 = reinterpret_cast<uint32_t*>(qv);
+      if (write) {
+        MicromizeKernel<uint32_t, true><<<nr, kMicroThreads, 0, c.stream>>>(
+            sv, c.s_org.get(), c.s_off.get(), c.s_first, qoff, first, c.prm.k, q32, qo, tv, tp);
+      } else {
+        MicromizeKernel<uint32_t, false><<<nr, kMicroThreads, 0, c.stream>>>(
+            sv, c.s_org.get(), c.s_off.get(), c.s_first, qoff, first, c.prm.k, q32, qo, tv, tp);
+      }
+    } else if (write) {
+      MicromizeKernel<uint64_t, true><<<nr, kMicroThreads, 0, c.stream>>>(
+          c.s_val.get(), c.s_org.get(), c.s_off.get(), c.s_first, qoff, first, c.prm.k, qv, qo,
+          tv, tp);
     } else {
-      MicromizeKernel<uint64_t><<<nr, kMicroThreads, 0, c.stream>>>(
-          c.s_val.get(), c.s_org.get(), c.s_off.get(), c.s_first, qoff, first, c.prm.k, qv,
-          qo);
+      MicromizeKernel<uint64_t, false><<<nr, kMicroThreads, 0, c.stream>>>(
+          c.s_val.get(), c.s_org.get(), c.s_off.get(), c.s_first, qoff, first, c.prm.k, qv, qo,
+          tv, tp);
     }
     RVN_LAUNCH_CHECK();
     ++c.launches;
     TimerEnd(c);
   }
   RVN_CUDA(cudaStreamSynchronize(c.stream));  // h_q_off staging is reusable
-  c.q_first = first;
-  c.q_last = last;
-  c.q_n = total;
-  c.q_is32 = c.s_is32;
-  c.q_valid = true;
+  if (write) {
+    c.q_first = first;
+    c.q_last = last;
+    c.q_n = total;
+    c.q_is32 = c.s_is32;
+    c.q_valid = true;
+  } else if (c.q_valid) {
+    // (q_off / h_q_off now describe [first, last): an older micromizer set is gone)
+    c.q_valid = c.q_first == first && c.q_last == last;
+  }
+  c.qt_first = first;
+  c.qt_last = last;
+  c.qt_valid = true;
+}
+
+}  // namespace
+
+void EnsureMicromizers(Ctx& c, uint32_t first, uint32_t last) {
+  if (c.q_valid && c.q_first == first && c.q_last == last) return;
+  Micromize(c, first, last, true);
+}
+
+// only the per-read selection rule (c.qt_*) and the counts (c.h_q_off)
+void EnsureThresholds(Ctx& c, uint32_t first, uint32_t last) {
+  if (c.qt_valid && c.qt_first == first && c.qt_last == last) return;
+  Micromize(c, first, last, false);
 }
 
 }  // namespace rvn

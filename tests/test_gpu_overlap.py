@@ -298,6 +298,35 @@ def test_stage1_tiered_index(gpu_engine, oracle, lambda_reads):
         gpu_engine.set_option("tier_min_records", 1 << 18)
 
 
+def test_stage1_probe_path_without_self_join(gpu_engine, oracle, lambda_reads):
+    """By default the seed hits of a stage-1 flush inside the index batch come from the
+    self-join over the sorted index (map.cu); with the option off every flush probes
+    the table per micromizer like flushes outside the batch do. Same results, with
+    repeats (low frequency cut), several index batches and flushes, both tier modes."""
+    rs = synth.make_reads(30_000, 160, 3000, seed=9)
+    for tiers in (0, 1 << 18):
+        gpu_engine.set_option("tier_min_records", tiers)
+        try:
+            for join in (0, 1):
+                gpu_engine.set_option("self_join", join)
+                gpu_engine.configure(k=15, w=5)
+                gpu_engine.upload(lambda_reads)
+                got = gpu_engine.find_overlaps_and_create_piles(0.001, 32, False)
+                for k in ("overlaps", "ovl_off", "pile", "pile_off"):
+                    assert np.array_equal(got[k], GOLD[f"stage1_plain_{k}"]), (join, k)
+                gpu_engine.upload(rs)
+                for freq, ib, qb in ((0.001, 0, 0), (0.02, 150_000, 60_000), (0.3, 0, 100_000)):
+                    got = gpu_engine.find_overlaps_and_create_piles(freq, 8, False, ib, qb)
+                    want = oracle.stage1(oracle.engine(15, 5, threads=4), oracle.reads(rs), freq,
+                                         8, False, ib or 1 << 32, qb or 1 << 30)
+                    for k in ("overlaps", "ovl_off", "pile", "pile_off"):
+                        assert np.array_equal(got[k], want[k]), (tiers, join, freq, ib, k)
+                    assert got["num_mapped"] == int(want["num_mapped"][0])
+        finally:
+            gpu_engine.set_option("self_join", 1)
+            gpu_engine.set_option("tier_min_records", 1 << 18)
+
+
 def test_stage1_hifi_params(gpu_engine, oracle):
     rs = synth.make_reads(60_000, 120, 6000, seed=6, sub=0.002, ins=0.0015, dele=0.0015)
     gpu_engine.configure(k=19, w=10)
