@@ -316,6 +316,7 @@ __device__ __forceinline__ uint32_t JoinKept(const JoinView& jv, uint64_t i, uin
   if (fw == same) return 0;
   if (jv.occurrence != 0xFFFFFFFFu) {
     uint32_t len = fw + 1;
+    if (len > jv.occurrence) return 0;
     for (uint64_t j = i; j > 0 && jv.val[j - 1] == v; --j) {
       if (++len > jv.occurrence) return 0;
     }
@@ -331,46 +332,81 @@ __device__ __forceinline__ bool JoinIsQuery(const JoinView& jv, uint64_t v, uint
   return v < t || (v == t && (static_cast<uint32_t>(o) >> 1) < jv.thr_pos[r - jv.thr_first]);
 }
 
+// sweep over the sorted postings: every query posting with hits takes the next free
+// slot of its read (slots [q_off[r], q_off[r + 1]) - one per micromizer - in any
+// order) and leaves (posting index, number of hits) there
 __global__ void __launch_bounds__(kThreads)
-JoinCountKernel(JoinView jv, uint32_t* __restrict__ read_cnt, unsigned long long* __restrict__ n_queries) {
-  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
-  bool is_q = false;
-  if (i < jv.n) {
-    const uint64_t v = jv.val[i], o = jv.org[i];
-    is_q = JoinIsQuery(jv, v, o);
-    if (is_q) {
-      uint32_t skip;
-      const uint32_t r = static_cast<uint32_t>(o >> 32);
-      const uint32_t kept = JoinKept(jv, i, v, r, &skip);
-      if (kept) atomicAdd(read_cnt + (r - jv.first), kept);
-    }
-  }
-  const uint32_t q = __popc(__ballot_sync(0xFFFFFFFFu, is_q));
-  if ((threadIdx.x & 31) == 0 && q) atomicAdd(n_queries, static_cast<unsigned long long>(q));
-}
-
-__global__ void __launch_bounds__(kThreads)
-JoinEmitKernel(JoinView jv, const uint64_t* __restrict__ read_hit_off,
-               uint32_t* __restrict__ cursor, uint64_t* __restrict__ h_grp,
-               uint64_t* __restrict__ h_pos) {
+JoinProbeKernel(JoinView jv, const uint64_t* __restrict__ q_off, uint64_t q_begin,
+                uint32_t* __restrict__ cursor, uint64_t* __restrict__ packed) {
   const uint64_t i = static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x;
   if (i >= jv.n) return;
-  const uint64_t v = jv.val[i], lo = jv.org[i];
-  if (!JoinIsQuery(jv, v, lo)) return;
-  const uint32_t r = static_cast<uint32_t>(lo >> 32);
-  uint32_t skip = 0;
+  const uint64_t v = jv.val[i], o = jv.org[i];
+  if (!JoinIsQuery(jv, v, o)) return;
+  const uint32_t r = static_cast<uint32_t>(o >> 32);
+  uint32_t skip;
   const uint32_t kept = JoinKept(jv, i, v, r, &skip);
   if (!kept) return;
-  uint64_t at = read_hit_off[r - jv.first] + atomicAdd(cursor + (r - jv.first), kept);
-  const uint64_t lhs_pos = static_cast<uint32_t>(lo) >> 1;
-  for (uint32_t x = 0; x < kept; ++x, ++at) {
-    const uint64_t o = jv.org[i + 1 + skip + x];
-    const uint64_t rhs_id = o >> 32;
-    const uint64_t strand = (lo & 1) == (o & 1);
-    const uint64_t rhs_pos = static_cast<uint32_t>(o) >> 1;
-    const uint64_t diagonal = !strand ? rhs_pos + lhs_pos : rhs_pos - lhs_pos + (3ULL << 30);
-    h_grp[at] = (((rhs_id << 1) | strand) << 32) | diagonal;
-    h_pos[at] = (lhs_pos << 32) | rhs_pos;
+  const uint64_t slot = q_off[r - jv.thr_first] - q_begin + atomicAdd(cursor + (r - jv.first), 1u);
+  packed[slot] = (i << 32) | kept;
+}
+
+__global__ void UnpackJoin(const uint64_t* __restrict__ packed, uint64_t n,
+                           uint32_t* __restrict__ cnt) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) cnt[i] = static_cast<uint32_t>(packed[i]);
+}
+
+// ExpandWarpKernel over the slots of JoinProbeKernel: the query's own posting gives
+// its origin, its hits follow it in the run (after the postings of the same read)
+__global__ void __launch_bounds__(kThreads)
+ExpandJoinKernel(const uint64_t* __restrict__ i_org, const uint64_t* __restrict__ packed,
+                 uint64_t n_q, const uint64_t* __restrict__ hit_off,
+                 uint64_t* __restrict__ h_grp, uint64_t* __restrict__ h_pos) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t i = (static_cast<uint64_t>(blockIdx.x) * kThreads + threadIdx.x);
+  const bool valid = i < n_q;
+  const uint64_t pk = valid ? packed[i] : 0;
+  const uint32_t my_cnt = static_cast<uint32_t>(pk);
+  uint32_t my_first = 0;
+  uint64_t my_org = 0;
+  if (my_cnt) {
+    const uint32_t post = static_cast<uint32_t>(pk >> 32);
+    my_org = i_org[post];
+    my_first = post + 1;
+    while ((i_org[my_first] >> 32) == (my_org >> 32)) ++my_first;  // same read: not a hit
+  }
+  const uint64_t my_off = valid ? hit_off[i] : 0;
+  const uint64_t base = __shfl_sync(0xFFFFFFFFu, my_off, 0);
+  uint32_t rel = valid ? static_cast<uint32_t>(my_off - base) : 0;
+  uint32_t run = valid ? rel + my_cnt : 0;
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, run, d);
+    if (lane >= d && o > run) run = o;
+  }
+  if (!valid) rel = run;
+  const uint32_t total = __shfl_sync(0xFFFFFFFFu, run, 31);
+  for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+    const uint32_t t = t0 + lane;
+    uint32_t q = 0;
+#pragma unroll
+    for (uint32_t step = 16; step > 0; step >>= 1) {
+      const uint32_t r = __shfl_sync(0xFFFFFFFFu, rel, q + step);
+      if (r <= t) q += step;
+    }
+    const uint32_t qrel = __shfl_sync(0xFFFFFFFFu, rel, q);
+    const uint32_t qfirst = __shfl_sync(0xFFFFFFFFu, my_first, q);
+    const uint64_t lo = __shfl_sync(0xFFFFFFFFu, my_org, q);
+    if (t < total) {
+      const uint64_t o = i_org[qfirst + (t - qrel)];
+      const uint64_t lhs_pos = static_cast<uint32_t>(lo) >> 1;
+      const uint64_t rhs_id = o >> 32;
+      const uint64_t strand = (lo & 1) == (o & 1);
+      const uint64_t rhs_pos = static_cast<uint32_t>(o) >> 1;
+      const uint64_t diagonal =
+          !strand ? rhs_pos + lhs_pos : rhs_pos - lhs_pos + (3ULL << 30);
+      h_grp[base + t] = (((rhs_id << 1) | strand) << 32) | diagonal;
+      h_pos[base + t] = (lhs_pos << 32) | rhs_pos;
+    }
   }
 }
 
@@ -1597,32 +1633,45 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
     JoinView jv{ValView{c.i_val.get(), c.i_is32 ? 1 : 0}, c.i_org.get(), c.i_n, c.occurrence,
                 c.qt_val.get(), c.qt_pos.get(), c.qt_first, first, last};
     TimerBegin(c, "probe");
-    uint32_t* rcnt = c.m_cnt.reserve(2ULL * nr + 2);
-    uint32_t* cursor = rcnt + nr + 1;
-    uint64_t* counter = c.m_counter.reserve(8);
-    RVN_CUDA(cudaMemsetAsync(rcnt, 0, (2ULL * nr + 2) * sizeof(uint32_t), c.stream));
-    RVN_CUDA(cudaMemsetAsync(counter, 0, sizeof(uint64_t), c.stream));
-    if (c.i_n > 0) {
-      JoinCountKernel<<<CeilDiv(c.i_n, kThreads), kThreads, 0, c.stream>>>(
-          jv, rcnt, reinterpret_cast<unsigned long long*>(counter));
+    const uint64_t b0 = first - c.qt_first;
+    const uint64_t q_begin = c.h_q_off[b0];
+    n_q = c.h_q_off[b0 + nr] - q_begin;
+    uint32_t* cnt = c.m_cnt.reserve(n_q + 1);
+    uint32_t* cursor = c.m_first.reserve(nr + 1ULL);
+    uint64_t* packed = c.m_sq_key.reserve(n_q + 2);
+    uint64_t* hit_off = c.m_hit_off.reserve(n_q + 2);
+    RVN_CUDA(cudaMemsetAsync(cursor, 0, (nr + 1ULL) * sizeof(uint32_t), c.stream));
+    RVN_CUDA(cudaMemsetAsync(packed, 0, (n_q + 1) * sizeof(uint64_t), c.stream));
+    if (c.i_n > 0 && n_q > 0) {
+      JoinProbeKernel<<<CeilDiv(c.i_n, kThreads), kThreads, 0, c.stream>>>(
+          jv, c.q_off.get(), q_begin, cursor, packed);
+      UnpackJoin<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(packed, n_q, cnt);
       RVN_LAUNCH_CHECK();
-      ++c.launches;
+      c.launches += 2;
     }
-    ExclusiveScanU32(c, rcnt, read_hit_off, nr);
-    RVN_CUDA(cudaMemcpyAsync(h_rho.data(), read_hit_off, (nr + 1ULL) * sizeof(uint64_t),
-                             cudaMemcpyDeviceToHost, c.stream));
-    n_q = ReadU64(c, counter);
-    n_hits = h_rho[nr];
+    if (n_q > 0) {
+      ExclusiveScanU32(c, cnt, hit_off, n_q);
+      n_hits = ReadU64(c, hit_off + n_q);
+    } else {
+      RVN_CUDA(cudaMemsetAsync(hit_off, 0, sizeof(uint64_t), c.stream));
+    }
     TimerEnd(c);
     TimerBegin(c, "expand");
     hg = c.h_grp.reserve(n_hits + 1);
     hp = c.h_pos.reserve(n_hits + 1);
     if (n_hits > 0) {
-      JoinEmitKernel<<<CeilDiv(c.i_n, kThreads), kThreads, 0, c.stream>>>(jv, read_hit_off,
-                                                                          cursor, hg, hp);
+      ExpandJoinKernel<<<CeilDiv(n_q, kThreads), kThreads, 0, c.stream>>>(
+          c.i_org.get(), packed, n_q, hit_off, hg, hp);
       RVN_LAUNCH_CHECK();
       ++c.launches;
     }
+    GatherU64<<<CeilDiv(nr + 1ULL, kThreads), kThreads, 0, c.stream>>>(
+        hit_off, c.q_off.get() + b0, q_begin, nr + 1ULL, read_hit_off);
+    RVN_LAUNCH_CHECK();
+    ++c.launches;
+    RVN_CUDA(cudaMemcpyAsync(h_rho.data(), read_hit_off, (nr + 1ULL) * sizeof(uint64_t),
+                             cudaMemcpyDeviceToHost, c.stream));
+    RVN_CUDA(cudaStreamSynchronize(c.stream));
     TimerEnd(c);
     c.r_filt_off.reserve(nr + 2ULL);
     for (uint32_t i = 0; i <= nr; ++i) c.r_filt_off.get()[i] = 0;
