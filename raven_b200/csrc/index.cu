@@ -230,6 +230,10 @@ TierScatterKernel(const uint32_t* __restrict__ val, const uint64_t* __restrict__
   for (uint32_t i = 0; i < kWarpSpan / 32; ++i) {
     const uint64_t idx = warp_base + i * 32 + lane;
     v[i] = idx < n ? val[idx] : 0xFFFFFFFFu;
+  }
+#pragma unroll
+  for (uint32_t i = 0; i < kWarpSpan / 32; ++i) {
+    const uint64_t idx = warp_base + i * 32 + lane;
     cnt += __popc(__ballot_sync(0xFFFFFFFFu, idx < n && v[i] <= limit));
   }
   if (lane == 0) warp_a[warp] = cnt;
@@ -237,23 +241,34 @@ TierScatterKernel(const uint32_t* __restrict__ val, const uint64_t* __restrict__
   uint64_t a_at = tile_off_a[blockIdx.x];
   for (uint32_t w = 0; w < warp; ++w) a_at += warp_a[w];
   uint64_t b_at = warp_base - a_at;  // records before this warp that are not in tier A
+  // origins in batches of 8 independent loads (all 16 at once cost too many registers)
 #pragma unroll
-  for (uint32_t i = 0; i < kWarpSpan / 32; ++i) {
-    const uint64_t idx = warp_base + i * 32 + lane;
-    const bool in = idx < n;
-    const bool is_a = in && v[i] <= limit;
-    const uint32_t ma = __ballot_sync(0xFFFFFFFFu, is_a);
-    const uint32_t mb = __ballot_sync(0xFFFFFFFFu, in && !is_a);
-    const uint32_t below = (1u << lane) - 1u;
-    if (is_a) {
-      const uint64_t d = a_at + __popc(ma & below);
-      a_val[d] = v[i];
-      a_org[d] = org[idx];
-    } else if (in) {
-      b_val[b_at + __popc(mb & below)] = v[i];
+  for (uint32_t h = 0; h < kWarpSpan / 32; h += 8) {
+    uint64_t o[8];
+#pragma unroll
+    for (uint32_t u = 0; u < 8; ++u) {
+      const uint64_t idx = warp_base + (h + u) * 32 + lane;
+      o[u] = (idx < n && v[h + u] <= limit) ? org[idx] : 0;
     }
-    a_at += __popc(ma);
-    b_at += __popc(mb);
+#pragma unroll
+    for (uint32_t u = 0; u < 8; ++u) {
+      const uint32_t i = h + u;
+      const uint64_t idx = warp_base + i * 32 + lane;
+      const bool in = idx < n;
+      const bool is_a = in && v[i] <= limit;
+      const uint32_t ma = __ballot_sync(0xFFFFFFFFu, is_a);
+      const uint32_t mb = __ballot_sync(0xFFFFFFFFu, in && !is_a);
+      const uint32_t below = (1u << lane) - 1u;
+      if (is_a) {
+        const uint64_t d = a_at + __popc(ma & below);
+        a_val[d] = v[i];
+        a_org[d] = o[u];
+      } else if (in) {
+        b_val[b_at + __popc(mb & below)] = v[i];
+      }
+      a_at += __popc(ma);
+      b_at += __popc(mb);
+    }
   }
 }
 
@@ -268,6 +283,120 @@ __global__ void MaxU64Kernel(const uint64_t* __restrict__ v, uint64_t n,
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, d));
   if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+// Multiplicities of bare keys that are sorted by their bits above `low` only (two
+// radix passes instead of three at k = 15): the keys of one group (equal upper bits,
+// ~600 keys at C2) are contiguous, a warp counts a group's low bits in 1024 shared
+// counters and reads the run lengths off them - the histogram IndexTableKernel<.,
+// false> takes from fully sorted keys, without the third pass. A warp owns the
+// groups that START in its chunk.
+constexpr uint32_t kGroupChunk = 4096;
+constexpr int kGroupLowBits = 10;
+
+__global__ void __launch_bounds__(kThreads)
+GroupCountKernel(const uint32_t* __restrict__ key, uint64_t n, unsigned long long* __restrict__ hist) {
+  __shared__ uint32_t sh[kSmemBins];
+  __shared__ __align__(16) uint32_t cnt[kThreads / 32][1u << kGroupLowBits];
+  __shared__ uint32_t keys_total;
+  for (uint32_t i = threadIdx.x; i < kSmemBins; i += kThreads) sh[i] = 0;
+  if (threadIdx.x == 0) keys_total = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t* my = cnt[wid];
+  const uint32_t low_mask = (1u << kGroupLowBits) - 1;
+  uint32_t h1 = 0, h2 = 0, h3 = 0, h4 = 0, nkeys = 0;
+  const uint64_t n_chunks = (n + kGroupChunk - 1) / kGroupChunk;
+  for (uint64_t chunk = static_cast<uint64_t>(blockIdx.x) * (kThreads / 32) + wid; chunk < n_chunks;
+       chunk += static_cast<uint64_t>(gridDim.x) * (kThreads / 32)) {
+    const uint64_t start = chunk * kGroupChunk;
+    const uint64_t end = min(n, start + kGroupChunk);
+    uint64_t pos = start;
+    if (start > 0) {  // the group that began before the chunk is the previous warp's
+      const uint32_t gprev = key[start - 1] >> kGroupLowBits;
+      while (true) {
+        const uint64_t idx = pos + lane;
+        const bool in = idx < n && (key[idx] >> kGroupLowBits) == gprev;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, in);
+        const uint32_t c = m == 0xFFFFFFFFu ? 32u : static_cast<uint32_t>(__ffs(~m) - 1);
+        pos += c;
+        if (c < 32) break;
+      }
+    }
+    while (pos < end) {
+      const uint32_t g = key[pos] >> kGroupLowBits;
+      uint4* my4 = reinterpret_cast<uint4*>(my);
+#pragma unroll
+      for (uint32_t t = 0; t < (1u << kGroupLowBits) / 128; ++t) my4[t * 32 + lane] = make_uint4(0, 0, 0, 0);
+      __syncwarp();
+      bool open = true;
+      while (open) {  // 128 keys per round: four independent loads per lane
+        uint32_t k4[4];
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) {
+          const uint64_t idx = pos + u * 32 + lane;
+          k4[u] = idx < n ? key[idx] : ~(g << kGroupLowBits);
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) {
+          if (open) {
+            const bool in = (k4[u] >> kGroupLowBits) == g;
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, in);
+            if (in) atomicAdd(&my[k4[u] & low_mask], 1u);
+            const uint32_t c = m == 0xFFFFFFFFu ? 32u : static_cast<uint32_t>(__ffs(~m) - 1);
+            pos += c;
+            open = c == 32;
+          }
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (uint32_t t = 0; t < (1u << kGroupLowBits) / 128; ++t) {
+        const uint4 q = my4[t * 32 + lane];
+        if ((q.x | q.y | q.z | q.w) == 0) continue;
+        const uint32_t cs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const uint32_t c = cs[x];
+          if (c == 0) continue;
+          ++nkeys;
+          if (c <= 4) {
+            h1 += c == 1;
+            h2 += c == 2;
+            h3 += c == 3;
+            h4 += c == 4;
+          } else if (c < kSmemBins) {
+            atomicAdd(&sh[c], 1u);
+          } else {
+            atomicAdd(&hist[min(c, kHistBins - 1)], 1ULL);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    h1 += __shfl_xor_sync(0xFFFFFFFFu, h1, d);
+    h2 += __shfl_xor_sync(0xFFFFFFFFu, h2, d);
+    h3 += __shfl_xor_sync(0xFFFFFFFFu, h3, d);
+    h4 += __shfl_xor_sync(0xFFFFFFFFu, h4, d);
+    nkeys += __shfl_xor_sync(0xFFFFFFFFu, nkeys, d);
+  }
+  if (lane == 0) {
+    atomicAdd(&sh[1], h1);
+    atomicAdd(&sh[2], h2);
+    atomicAdd(&sh[3], h3);
+    atomicAdd(&sh[4], h4);
+    atomicAdd(&keys_total, nkeys);
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < kSmemBins; i += kThreads) {
+    if (sh[i]) atomicAdd(&hist[i], static_cast<unsigned long long>(sh[i]));
+  }
+  if (threadIdx.x == 0 && keys_total) {
+    atomicAdd(&hist[kHistBins], static_cast<unsigned long long>(keys_total));
+  }
 }
 
 }  // namespace
@@ -384,8 +513,11 @@ void BuildIndexFrom(Ctx& c, ValView src_val, const uint64_t* src_org, uint64_t n
     // the rest: bare keys, only their multiplicities matter
     uint32_t* b1 = reinterpret_cast<uint32_t*>(c.t_b1.reserve(n_b / 2 + 2));
     uint32_t* b2 = reinterpret_cast<uint32_t*>(c.t_b2.reserve(n_b / 2 + 2));
+    // (sorted above their low bits only: GroupCountKernel reads the multiplicities
+    //  off groups of equal upper bits)
+    c.t_b_low = key_bits > 2 * kGroupLowBits ? kGroupLowBits : 0;
     if (n_b > 0) {
-      const int where = RadixSortKeys(c, b_src, b1, b2, n_b, 0, key_bits);
+      const int where = RadixSortKeys(c, b_src, b1, b2, n_b, c.t_b_low, key_bits);
       sorted_b = where < 0 ? b_src : (where == 0 ? b1 : b2);
     }
     c.t_sorted_b = sorted_b;
@@ -447,9 +579,15 @@ void BuildIndexFrom(Ctx& c, ValView src_val, const uint64_t* src_org, uint64_t n
         reinterpret_cast<const uint32_t*>(kv), n_a, shift, n_buckets, bucket,
         reinterpret_cast<unsigned long long*>(hist), gaps);
     if (tiered && n_b > 0) {  // multiplicities of the keys beyond the limit
-      IndexTableKernel<uint32_t, false>
-          <<<std::min<unsigned>(CeilDiv(n_b + 1, kThreads), 148 * 8), kThreads, 0, c.stream>>>(
-              sorted_b, n_b, 0, 0, nullptr, reinterpret_cast<unsigned long long*>(hist), nullptr);
+      if (c.t_b_low) {
+        GroupCountKernel<<<std::min<unsigned>(CeilDiv(n_b, kGroupChunk * (kThreads / 32)), 148 * 6),
+                           kThreads, 0, c.stream>>>(sorted_b, n_b,
+                                                    reinterpret_cast<unsigned long long*>(hist));
+      } else {
+        IndexTableKernel<uint32_t, false>
+            <<<std::min<unsigned>(CeilDiv(n_b + 1, kThreads), 148 * 8), kThreads, 0, c.stream>>>(
+                sorted_b, n_b, 0, 0, nullptr, reinterpret_cast<unsigned long long*>(hist), nullptr);
+      }
       ++c.launches;
     }
   } else {
@@ -529,6 +667,20 @@ uint32_t FilterIndex(Ctx& c, double frequency) {
       CollectLongRuns<uint32_t><<<CeilDiv(c.i_n, kThreads), kThreads, 0, c.stream>>>(
           reinterpret_cast<const uint32_t*>(c.i_val.get()), c.i_n,
           reinterpret_cast<unsigned long long*>(counter), out);
+      if (c.t_sorted_b && c.t_nb && c.t_b_low) {  // (runs of >= 65535: order the low bits too)
+        uint32_t* bufs[3] = {reinterpret_cast<uint32_t*>(c.t_b0.get()),
+                             reinterpret_cast<uint32_t*>(c.t_b1.get()),
+                             reinterpret_cast<uint32_t*>(c.t_b2.get())};
+        uint32_t* free_buf[2];
+        int nf = 0;
+        for (uint32_t* p : bufs) {
+          if (p != c.t_sorted_b && nf < 2) free_buf[nf++] = p;
+        }
+        const int where = RadixSortKeys(c, c.t_sorted_b, free_buf[0], free_buf[1], c.t_nb, 0,
+                                        static_cast<int>(2 * c.prm.k));
+        c.t_sorted_b = where < 0 ? c.t_sorted_b : (where == 0 ? free_buf[0] : free_buf[1]);
+        c.t_b_low = 0;
+      }
       if (c.t_sorted_b && c.t_nb) {  // tiered build: the keys beyond the limit too
         CollectLongRuns<uint32_t><<<CeilDiv(c.t_nb, kThreads), kThreads, 0, c.stream>>>(
             c.t_sorted_b, c.t_nb, reinterpret_cast<unsigned long long*>(counter), out);
