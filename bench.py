@@ -723,7 +723,7 @@ PHASE_KERNELS = {
                   "index.cu: TierCount/TierScatter)",
     "sketch": "sketch (SketchFastKernel<5>)",
     "chain": "chain (SplitKernel + GroupChainKernel + PairChainKernel)",
-    "probe": "probe (query radix sort + ProbeSortedKernel)",
+    "probe": "probe (JoinProbeKernel: self-join over the sorted postings)",
 }
 
 
