@@ -19,11 +19,14 @@
 // along a path).
 //
 // Formulation: the recursion is run level by level over ALL pairs of the batch.
-// Every level is one launch of ColumnsKernel (one thread per half problem: Myers/
-// Hyyro bit-vector blocks inside the Ukkonen band of the KNOWN distance of the
-// problem, the band's vectors in a ring in global scratch, coalesced across the
-// warp, the query's match masks precomputed once per pair and funnel-shifted to
-// the sub-problem's row offset) and one of SplitKernel (one warp per problem).
+// Every level computes the forward and the backward score column of each open
+// problem (Myers/Hyyro bit-vector blocks inside the Ukkonen band of the KNOWN
+// distance of the problem; the query's match masks are precomputed once per pair
+// and funnel-shifted to the sub-problem's row offset) - one WARP per problem for
+// wide bands (ColumnsWarpKernel: a wavefront over strips of 32 blocks, state in
+// registers), one thread per problem for the small ones (ColumnsKernel: the band's
+// vectors in a shared-memory ring) - and then the split rows (SplitRowKernel, one
+// warp per problem).
 // Leaves (one thread each) store their banded columns and walk back. Every value
 // the rules compare is exact inside the band (cells of value <= distance), so the
 // band changes nothing. The distances themselves come from the same column
@@ -606,7 +609,8 @@ void AlignBreakingPoints(Ctx& c, uint64_t n, const uint32_t* q_read, const uint3
     const uint32_t blocks = (m + 63) / 64;
     return std::max<uint32_t>(1, std::min<uint32_t>(blocks, (2u * static_cast<uint32_t>(k) >> 6) + 2));
   };
-  constexpr uint32_t kWarpRing = 24;   // bands of this many blocks or more: warp kernel
+  constexpr uint32_t kWarpRing = 24;   // bands of this many blocks or more: warp kernel,
+  constexpr uint64_t kWarpSteps = 16384;  // and any problem of this many block steps
   constexpr uint32_t kSmemRing = 208;  // 208 KB of the 227 KB a CTA may use
   auto ring_class = [](uint32_t ring) {
     uint32_t c = 3;  // rings up to 8, 16, 32, ... slots
@@ -626,7 +630,10 @@ void AlignBreakingPoints(Ctx& c, uint64_t n, const uint32_t* q_read, const uint3
     // wide bands: one warp per problem (ColumnsWarpKernel); the others one thread
     // per problem, launched by band size class - the vectors of a class live in
     // shared memory ([2][ring][64] per CTA)
-    const auto wide = [&](const ColTask& t) { return ring_of(t.m, t.k) >= kWarpRing; };
+    const auto wide = [&](const ColTask& t) {
+      const uint32_t ring = ring_of(t.m, t.k);
+      return ring >= kWarpRing || static_cast<uint64_t>(t.cols) * ring >= kWarpSteps;
+    };
     const uint32_t nw = static_cast<uint32_t>(
         std::stable_partition(tasks.begin(), tasks.end(), wide) - tasks.begin());
     uint64_t carry_entries = 0;
