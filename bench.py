@@ -269,11 +269,13 @@ def main_ours(a):
     if world > 1:
         de = distributed.DistEngine(f"cuda:{local}", k=K, w=W)
         stream, eng = de.stream, de.engine
+        eng.set_option("async_upload", 1)   # pinned host buffers that outlive every step
         de.upload(prs)
     else:
         stream = torch.cuda.current_stream()
         eng = engine.Engine(device=local, stream=stream.cuda_stream)
         eng.configure(K, W)
+        eng.set_option("async_upload", 1)   # pinned host buffers that outlive every step
         eng.upload(prs)
 
     def barrier():

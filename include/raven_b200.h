@@ -262,7 +262,11 @@ int rvn_get_stats(rvn_ctx* ctx, rvn_stats* out);
  * at least that many minimizers into a probe-able tier and bare keys, default
  * 2^18; 0 = always); "self_join" (0/1, default 1: the seed hits of a stage-1 flush
  * whose reads are inside the index batch come from a self-join over the sorted
- * index instead of a probe per micromizer); "reset_stats".
+ * index instead of a probe per micromizer); "async_upload" (0/1, default 0: with 1,
+ * rvn_reads_upload* returns while the packed bases still travel - in chunks, on a
+ * copy stream - and the sketch kernel of the next call starts on the reads that
+ * have arrived; the caller must keep `words` unchanged until the next call on the
+ * context has returned; meant for pinned host memory); "reset_stats".
  * Unknown name -> RVN_ERR_INVALID. */
 int rvn_set_option(rvn_ctx* ctx, const char* name, int64_t value);
 

@@ -15,10 +15,13 @@ struct rvn_ctx {
 namespace {
 
 template <typename F>
-int Guard(rvn_ctx* ctx, F&& f) {
+int Guard(rvn_ctx* ctx, F&& f, bool sketches_first = false) {
   if (!ctx) return RVN_ERR_INVALID;
   try {
     RVN_CUDA(cudaSetDevice(ctx->c.device));
+    // an asynchronous upload in flight: calls that begin with the sketch kernel
+    // consume it chunk by chunk (EnsureSketch), everything else waits for all of it
+    if (!sketches_first) WaitUpload(ctx->c);
     f(ctx->c);
     ctx->c.err.clear();
     return RVN_OK;
@@ -39,6 +42,18 @@ int Guard(rvn_ctx* ctx, F&& f) {
     return RVN_ERR_CUDA;
   }
 }
+
+}  // namespace
+
+namespace rvn {
+void WaitUpload(Ctx& c) {
+  if (!c.up_pending) return;
+  RVN_CUDA(cudaStreamWaitEvent(c.stream, c.up_events[c.up_chunks - 1], 0));
+  c.up_pending = false;
+}
+}  // namespace rvn
+
+namespace {
 
 void CheckRange(const Ctx& c, uint32_t first, uint32_t last) {
   if (first > last || last > c.n_reads) {
@@ -80,8 +95,10 @@ void Stage1(Ctx& c, double freq, uint64_t kmax, bool minhash, uint64_t ib,
   uint16_t* d_pile = c.p_data.reserve(total_bins + 1);
   uint64_t* d_poff = c.p_off.reserve(n + 1ULL);
   RVN_CUDA(cudaMemsetAsync(d_pile, 0, (total_bins + 1) * sizeof(uint16_t), c.stream));
-  RVN_CUDA(cudaMemcpyAsync(d_poff, c.st_pile_off.data(), (n + 1ULL) * 8,
-                           cudaMemcpyHostToDevice, c.stream));
+  if (!c.p_off_uploaded) {  // (an asynchronous upload has sent them ahead of the bases)
+    RVN_CUDA(cudaMemcpyAsync(d_poff, c.st_pile_off.data(), (n + 1ULL) * 8,
+                             cudaMemcpyHostToDevice, c.stream));
+  }
 
   GatherReset(c);
   c.st_mapped = 0;
@@ -179,6 +196,12 @@ RVN_API void rvn_ctx_destroy(rvn_ctx* ctx) {
   }
   for (auto e : ctx->c.timer.pool) cudaEventDestroy(e);
   ArenaRelease(ctx->c);
+  if (ctx->c.copy_stream) {
+    cudaStreamSynchronize(ctx->c.copy_stream);
+    cudaStreamDestroy(ctx->c.copy_stream);
+  }
+  for (auto e : ctx->c.up_events) cudaEventDestroy(e);
+  if (ctx->c.up_fence) cudaEventDestroy(ctx->c.up_fence);
   if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
   delete ctx;
 }
@@ -242,11 +265,8 @@ static void UploadReads(Ctx& c, const uint64_t* words, const uint64_t* word_off,
   // own range; lengths and ids of all reads are always resident)
   c.res_first = res_first;
   c.res_last = res_last;
-  const uint64_t w0 = c.h_woff[res_first], w1 = c.h_woff[res_last];
-  if (w1 > w0) {
-    RVN_CUDA(cudaMemcpyAsync(dw + w0, words + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice,
-                             c.stream));
-  }
+  // offsets, lengths, ids first (small, from pageable memory: behind the bases they
+  // would wait for the copy engine)
   RVN_CUDA(cudaMemcpyAsync(dwo, c.h_woff.data(), (n_reads + 1ULL) * 8,
                            cudaMemcpyHostToDevice, c.stream));
   if (n_reads) {
@@ -256,6 +276,61 @@ static void UploadReads(Ctx& c, const uint64_t* words, const uint64_t* word_off,
                              cudaMemcpyHostToDevice, c.stream));
   }
   RVN_CUDA(cudaStreamSynchronize(c.stream));
+  const uint64_t w0 = c.h_woff[res_first], w1 = c.h_woff[res_last];
+  c.up_pending = false;
+  c.p_off_uploaded = false;
+  if (w1 > w0 && c.async_upload && res_last - res_first >= 1024) {
+    // everything small the next call would send host-to-device goes first: behind the
+    // bases it would wait for the copy engine (tile tables, pile offsets of stage 1)
+    EnsureTiles(c);
+    {
+      c.st_pile_off.assign(n_reads + 1ULL, 0);
+      for (uint32_t i = 0; i < n_reads; ++i) c.st_pile_off[i + 1] = c.st_pile_off[i] + (lens[i] >> 4);
+      uint64_t* d_poff = c.p_off.reserve(n_reads + 1ULL);
+      RVN_CUDA(cudaMemcpyAsync(d_poff, c.st_pile_off.data(), (n_reads + 1ULL) * 8,
+                               cudaMemcpyHostToDevice, c.stream));
+      RVN_CUDA(cudaStreamSynchronize(c.stream));
+      c.p_off_uploaded = true;
+    }
+    // chunks that end at read boundaries, on the copy stream; the caller keeps
+    // `words` alive until the next call on this context has returned
+    constexpr uint32_t kChunks = 8;
+    if (!c.copy_stream) {
+      RVN_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+      RVN_CUDA(cudaEventCreateWithFlags(&c.up_fence, cudaEventDisableTiming));
+    }
+    while (c.up_events.size() < kChunks) {
+      cudaEvent_t ev;
+      RVN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      c.up_events.push_back(ev);
+    }
+    // (kernels of earlier calls may still read the old bases)
+    RVN_CUDA(cudaEventRecord(c.up_fence, c.stream));
+    RVN_CUDA(cudaStreamWaitEvent(c.copy_stream, c.up_fence, 0));
+    c.up_read_end.clear();
+    uint32_t r_prev = res_first;
+    for (uint32_t i = 1; i <= kChunks && r_prev < res_last; ++i) {
+      const uint64_t target = w0 + (w1 - w0) * i / kChunks;
+      uint32_t r = static_cast<uint32_t>(
+          std::lower_bound(c.h_woff.begin() + r_prev + 1, c.h_woff.begin() + res_last + 1, target) -
+          c.h_woff.begin());
+      if (i == kChunks || r > res_last) r = res_last;
+      const uint64_t a = c.h_woff[r_prev], b = c.h_woff[r];
+      if (b > a) {
+        RVN_CUDA(cudaMemcpyAsync(dw + a, words + a, (b - a) * 8, cudaMemcpyHostToDevice,
+                                 c.copy_stream));
+      }
+      RVN_CUDA(cudaEventRecord(c.up_events[c.up_read_end.size()], c.copy_stream));
+      c.up_read_end.push_back(r);
+      r_prev = r;
+    }
+    c.up_chunks = static_cast<uint32_t>(c.up_read_end.size());
+    c.up_pending = c.up_chunks > 0;
+  } else if (w1 > w0) {
+    RVN_CUDA(cudaMemcpyAsync(dw + w0, words + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice,
+                             c.stream));
+    RVN_CUDA(cudaStreamSynchronize(c.stream));
+  }
 }
 
 RVN_API int rvn_reads_upload(rvn_ctx* ctx, const uint64_t* words,
@@ -263,7 +338,7 @@ RVN_API int rvn_reads_upload(rvn_ctx* ctx, const uint64_t* words,
                              uint32_t n_reads) {
   return Guard(ctx, [&](Ctx& c) {
     UploadReads(c, words, word_off, lens, nullptr, n_reads);
-  });
+  }, /*sketches_first=*/true);
 }
 
 RVN_API int rvn_reads_upload_range(rvn_ctx* ctx, const uint64_t* words,
@@ -271,7 +346,7 @@ RVN_API int rvn_reads_upload_range(rvn_ctx* ctx, const uint64_t* words,
                                    uint32_t n_reads, uint32_t first, uint32_t last) {
   return Guard(ctx, [&](Ctx& c) {
     UploadReads(c, words, word_off, lens, nullptr, n_reads, first, last);
-  });
+  }, /*sketches_first=*/true);
 }
 
 RVN_API int rvn_reads_upload_ids(rvn_ctx* ctx, const uint64_t* words,
@@ -279,7 +354,7 @@ RVN_API int rvn_reads_upload_ids(rvn_ctx* ctx, const uint64_t* words,
                                  const uint32_t* ids, uint32_t n_reads) {
   return Guard(ctx, [&](Ctx& c) {
     UploadReads(c, words, word_off, lens, ids, n_reads);
-  });
+  }, /*sketches_first=*/true);
 }
 
 // Map one read that is not part of the uploaded set (it rides in the spare
@@ -353,7 +428,7 @@ RVN_API int rvn_minimize(rvn_ctx* ctx, uint32_t first, uint32_t last,
   return Guard(ctx, [&](Ctx& c) {
     CheckRange(c, first, last);
     BuildIndex(c, first, last, minhash != 0);
-  });
+  }, /*sketches_first=*/true);
 }
 
 RVN_API int rvn_filter(rvn_ctx* ctx, double frequency, uint32_t* occurrence) {
@@ -397,6 +472,7 @@ RVN_API int rvn_pile_add_layers(rvn_ctx* ctx, uint16_t* data,
     if (!data || !bin_off) throw InvalidArgument("null piles");
     const uint64_t bins = bin_off[n_piles];
     uint16_t* d = c.p_data.reserve(bins + 1);
+    c.p_off_uploaded = false;
     uint64_t* off = c.p_off.reserve(n_piles + 1ULL);
     rvn_overlap* o = c.p_ovl.reserve(n_overlaps + 1);
     RVN_CUDA(cudaMemcpyAsync(d, data, bins * 2, cudaMemcpyHostToDevice, c.stream));
@@ -462,7 +538,7 @@ RVN_API int rvn_find_overlaps_and_create_piles(rvn_ctx* ctx, double frequency,
   return Guard(ctx, [&](Ctx& c) {
     Stage1(c, frequency, max_overlaps, minhash != 0, index_batch_bases,
            query_batch_bases);
-  });
+  }, /*sketches_first=*/true);
 }
 
 RVN_API int rvn_stage1_results(rvn_ctx* ctx, const rvn_overlap** overlaps,
@@ -517,7 +593,7 @@ RVN_API int rvn_sketch(rvn_ctx* ctx, uint32_t first, uint32_t last, int minhash,
     if (origin) *origin = ho;
     if (offsets) *offsets = hf;
     if (n_records) *n_records = total;
-  });
+  }, /*sketches_first=*/true);
 }
 
 RVN_API int rvn_index_records(rvn_ctx* ctx, const uint64_t** value,
@@ -648,13 +724,15 @@ RVN_API int rvn_get_stats(rvn_ctx* ctx, rvn_stats* out) {
     *out = c.stats;
     out->occurrence = c.occurrence;
     out->kernel_launches = c.launches;
-  });
+  }, /*sketches_first=*/true);
 }
 
 RVN_API int rvn_set_option(rvn_ctx* ctx, const char* name, int64_t value) {
   return Guard(ctx, [&](Ctx& c) {
     if (name && std::strcmp(name, "keep_hits") == 0) {
       c.keep_hits = value != 0;
+    } else if (name && std::strcmp(name, "async_upload") == 0) {
+      c.async_upload = value != 0;
     } else if (name && std::strcmp(name, "self_join") == 0) {
       c.self_join = value != 0;
     } else if (name && std::strcmp(name, "tier_min_records") == 0) {
@@ -666,7 +744,7 @@ RVN_API int rvn_set_option(rvn_ctx* ctx, const char* name, int64_t value) {
     } else {
       throw InvalidArgument("unknown option");
     }
-  });
+  }, /*sketches_first=*/true);
 }
 
 RVN_API int rvn_get_timings(rvn_ctx* ctx, const char* const** names,
@@ -676,7 +754,7 @@ RVN_API int rvn_get_timings(rvn_ctx* ctx, const char* const** names,
     if (names) *names = c.timer.names.data();
     if (ms) *ms = c.timer.ms.data();
     if (n) *n = static_cast<uint32_t>(c.timer.names.size());
-  });
+  }, /*sketches_first=*/true);
 }
 
 // ---- multi-GPU building blocks (dist.cu); device pointers in and out ----
@@ -688,7 +766,7 @@ RVN_API int rvn_dist_sketch_split(rvn_ctx* ctx, uint32_t first, uint32_t last,
     CheckRange(c, first, last);
     if (!d_value || !d_origin || !counts) throw InvalidArgument("null output");
     DistSketchSplit(c, first, last, minhash ? 1 : 0, n_parts, d_value, d_origin, counts);
-  });
+  }, /*sketches_first=*/true);
 }
 
 RVN_API int rvn_dist_index(rvn_ctx* ctx, const uint64_t* d_value,

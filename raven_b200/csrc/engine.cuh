@@ -38,6 +38,16 @@ struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // option "async_upload": the packed bases travel on a copy stream in chunks; the
+  // sketch kernel of the next call starts on the reads that have arrived
+  int64_t async_upload = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t up_fence = nullptr;
+  std::vector<cudaEvent_t> up_events;   // one per chunk (reused)
+  std::vector<uint32_t> up_read_end;    // reads [.., up_read_end[i]) are complete after chunk i
+  uint32_t up_chunks = 0;
+  bool up_pending = false;
+  bool p_off_uploaded = false;  // stage-1 pile offsets already on the device
   std::string err;
   Params prm;
   bool keep_hits = false;
@@ -225,6 +235,7 @@ void EnsureTiles(Ctx& c);
 void EnsureSketch(Ctx& c, uint32_t first, uint32_t last);
 // micromizers of reads [first,last) into c.q_* (needs the sketch of a range
 // that contains [first,last))
+void WaitUpload(Ctx& c);  // the context's stream waits for an asynchronous upload
 void EnsureMicromizers(Ctx& c, uint32_t first, uint32_t last);
 void EnsureThresholds(Ctx& c, uint32_t first, uint32_t last);
 

@@ -766,13 +766,35 @@ void EnsureSketch(Ctx& c, uint32_t first, uint32_t last) {
       uint64_t* val = c.s_val.reserve(k32 ? cap / 2 + 1 : cap);
       uint64_t* org = c.s_org.reserve(cap);
       RVN_CUDA(cudaMemsetAsync(status, 0, (n_tiles + 2) * sizeof(uint64_t), c.stream));
+      if (!(k32 && c.prm.w == 5)) WaitUpload(c);
       if (k32 && c.prm.w == 5) {  // raven's default window: the fast kernel
         // (status words of this kernel: one per group of kFastGroup tiles)
-        SketchFastKernel<5><<<static_cast<unsigned>((n_tiles + kFastGroup - 1) / kFastGroup),
-                              kSketchThreads, 0, c.stream>>>(
-            c.d_words.get(), c.d_woff.get(), c.d_len.get(), c.d_ids.get(),
-            c.d_tile_off.get(), c.d_tile_read.get(), first, last, c.prm.k, ticket, status, tout,
-            n_tiles, cap, reinterpret_cast<uint32_t*>(val), org);
+        const uint64_t n_groups = (n_tiles + kFastGroup - 1) / kFastGroup;
+        // An asynchronous upload still in flight: the groups of the reads a chunk
+        // completes are launched behind that chunk's event (groups take tickets, and
+        // the look-back chain runs on across launches)
+        uint64_t launched = 0;
+        const uint32_t pieces = c.up_pending ? c.up_chunks : 1;
+        for (uint32_t p = 0; p < pieces; ++p) {
+          uint64_t upto = n_groups;
+          if (c.up_pending) {
+            RVN_CUDA(cudaStreamWaitEvent(c.stream, c.up_events[p], 0));
+            if (p + 1 < pieces) {
+              const uint32_t r = std::min(std::max(c.up_read_end[p], first), last);
+              upto = (c.h_tile_off[r] - c.h_tile_off[first]) / kFastGroup;
+            }
+          }
+          if (upto <= launched) continue;
+          SketchFastKernel<5><<<static_cast<unsigned>(upto - launched), kSketchThreads, 0,
+                                c.stream>>>(
+              c.d_words.get(), c.d_woff.get(), c.d_len.get(), c.d_ids.get(),
+              c.d_tile_off.get(), c.d_tile_read.get(), first, last, c.prm.k, ticket, status, tout,
+              n_tiles, cap, reinterpret_cast<uint32_t*>(val), org);
+          launched = upto;
+          ++c.launches;
+        }
+        --c.launches;  // (counted once more below)
+        c.up_pending = false;
       } else if (k32) {
         SketchKernel<uint32_t><<<static_cast<unsigned>(n_tiles), kSketchThreads, smem,
                                  c.stream>>>(
@@ -802,6 +824,7 @@ void EnsureSketch(Ctx& c, uint32_t first, uint32_t last) {
                              cudaMemcpyDeviceToHost, c.stream));
     RVN_CUDA(cudaStreamSynchronize(c.stream));
   } else {
+    WaitUpload(c);
     RVN_CUDA(cudaMemsetAsync(read_off, 0, (nr + 1ULL) * sizeof(uint64_t),
                              c.stream));
   }

@@ -327,6 +327,34 @@ def test_stage1_probe_path_without_self_join(gpu_engine, oracle, lambda_reads):
             gpu_engine.set_option("tier_min_records", 1 << 18)
 
 
+def test_stage1_async_upload(gpu_engine, lambda_reads):
+    """Option async_upload: the bases travel in chunks on a copy stream and the sketch
+    kernel is launched piecewise behind them - same result, also when the upload is
+    followed by a call that does not start with the sketch."""
+    rs = synth.make_reads(200_000, 2400, 4000, seed=12)   # > 1024 reads: chunked
+    gpu_engine.configure(k=15, w=5)
+    gpu_engine.upload(rs)
+    want = gpu_engine.find_overlaps_and_create_piles(0.001, 16, False)
+    gpu_engine.set_option("async_upload", 1)
+    try:
+        for _ in range(2):
+            gpu_engine.upload(rs)
+            got = gpu_engine.find_overlaps_and_create_piles(0.001, 16, False)
+            for k in ("overlaps", "ovl_off", "pile", "pile_off"):
+                assert np.array_equal(got[k], want[k]), k
+        gpu_engine.upload(rs)
+        d = gpu_engine.edit_distance_batch([0], [0], [500], [0], [0], [500], [1])
+        assert d.tolist() == [0]
+        gpu_engine.upload(rs, resident=(100, 2000))
+        a = gpu_engine.sketch(100, 2000, False)
+        gpu_engine.set_option("async_upload", 0)
+        gpu_engine.upload(rs, resident=(100, 2000))
+        b = gpu_engine.sketch(100, 2000, False)
+        assert all(np.array_equal(a[k], b[k]) for k in ("value", "origin", "offsets"))
+    finally:
+        gpu_engine.set_option("async_upload", 0)
+
+
 def test_stage1_hifi_params(gpu_engine, oracle):
     rs = synth.make_reads(60_000, 120, 6000, seed=6, sub=0.002, ins=0.0015, dele=0.0015)
     gpu_engine.configure(k=19, w=10)
