@@ -327,6 +327,34 @@ def test_stage1_probe_path_without_self_join(gpu_engine, oracle, lambda_reads):
             gpu_engine.set_option("tier_min_records", 1 << 18)
 
 
+def test_filter_with_very_long_runs(gpu_engine, oracle):
+    """Keys that occur 65535 times or more fall out of the run-length histogram and are
+    ranked by their exact lengths (CollectLongRuns) - in the tiered build this first
+    finishes the sort of the upper tier's keys. 70 000 copies of one short read: its
+    keys are that long. Stage 1 runs with a frequency that filters them (no hits); the
+    thresholds of other frequencies are then asked of the SAME tiered index."""
+    rng = np.random.default_rng(31)
+    one = rng.integers(0, 4, 90, dtype=np.uint8)
+    seqs = [one] * 70_000 + [rng.integers(0, 4, 400, dtype=np.uint8) for _ in range(50)]
+    rs = seqio.pack_codes(seqs)
+    eng = oracle.engine(15, 5, threads=8)
+    reads = oracle.reads(rs)
+    oracle.minimize(eng, reads, 0, rs.n, False)
+    gpu_engine.configure(15, 5)
+    gpu_engine.upload(rs)
+    gpu_engine.set_option("tier_min_records", 0)
+    try:
+        gpu_engine.find_overlaps_and_create_piles(0.5, 8, False)
+        assert gpu_engine.stats()["occurrence"] == oracle.filter(eng, 0.5)
+        for freq in (0.0005, 0.002, 0.5, 0.001):   # the first ones rank the long runs
+            assert gpu_engine.filter(freq) == oracle.filter(eng, freq), freq
+    finally:
+        gpu_engine.set_option("tier_min_records", 1 << 18)
+    gpu_engine.minimize(0, rs.n, False)
+    for freq in (0.0005, 0.5):
+        assert gpu_engine.filter(freq) == oracle.filter(eng, freq), freq
+
+
 def test_stage1_async_upload(gpu_engine, lambda_reads):
     """Option async_upload: the bases travel in chunks on a copy stream and the sketch
     kernel is launched piecewise behind them - same result, also when the upload is
