@@ -214,7 +214,7 @@ TierCountKernel(const uint32_t* __restrict__ val, uint64_t n, uint32_t limit,
   if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 TierScatterKernel(const uint32_t* __restrict__ val, const uint64_t* __restrict__ org, uint64_t n,
                   uint32_t limit, const uint64_t* __restrict__ tile_off_a,
                   uint32_t* __restrict__ a_val, uint64_t* __restrict__ a_org,

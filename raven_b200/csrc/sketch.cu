@@ -628,14 +628,15 @@ MicromizeKernel(const ValT* __restrict__ s_val,
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t cum = 0, d = 0;
-      for (; d < 256; ++d) {
-        if (cum + hist[d] > want) break;
-        cum += hist[d];
+    {  // the digit whose cumulative count first exceeds `want`: one block scan
+      static_assert(kMicroThreads == 256, "one thread per digit");
+      const uint32_t h = hist[threadIdx.x];
+      uint32_t tot;
+      const uint32_t ex = BlockExclusiveSum<uint32_t, kMicroThreads>(h, sh_scan, &tot);
+      if (ex <= want && want < ex + h) {
+        sh_digit = threadIdx.x;
+        sh_want = want - ex;
       }
-      sh_digit = d;
-      sh_want = want - cum;
     }
     __syncthreads();
     prefix |= static_cast<uint64_t>(sh_digit) << shift;
