@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <future>
 #include <stdexcept>
@@ -174,10 +175,25 @@ std::vector<std::unique_ptr<biosoup::NucleicAcid>> Polisher::Polish(
   const std::size_t A = a_read.size();
   std::vector<std::int32_t> a_dist(A);
   std::vector<std::uint32_t> bp(4 * bp_off.back() + 4);
-  Check(ctx_, rvn_align_breaking_points(ctx_, A, a_qread.data(), a_qbegin.data(), a_qlen.data(),
-                                        a_strand.data(), a_tread.data(), a_tbegin.data(),
-                                        a_tlen.data(), w_, bp_off.data(), a_dist.data(),
-                                        bp.data()));
+  // (batches of about 2^29 query bases bound the device scratch of the alignment:
+  //  score columns, match masks and stored leaf columns grow with the bases in flight)
+  std::uint64_t batch_bases = 1ULL << 29;
+  if (const char* env = std::getenv("RVN_POLISH_BATCH_BASES")) {  // (tests: several batches)
+    batch_bases = std::max<std::uint64_t>(1, std::strtoull(env, nullptr, 10));
+  }
+  for (std::size_t a0 = 0; a0 < A;) {
+    std::size_t a1 = a0;
+    std::uint64_t bases = 0;
+    while (a1 < A && (a1 == a0 || bases + a_qlen[a1] <= batch_bases)) bases += a_qlen[a1++];
+    std::vector<std::uint64_t> off(bp_off.begin() + a0, bp_off.begin() + a1 + 1);
+    for (auto& x : off) x -= bp_off[a0];
+    Check(ctx_, rvn_align_breaking_points(
+                    ctx_, a1 - a0, a_qread.data() + a0, a_qbegin.data() + a0, a_qlen.data() + a0,
+                    a_strand.data() + a0, a_tread.data() + a0, a_tbegin.data() + a0,
+                    a_tlen.data() + a0, w_, off.data(), a_dist.data() + a0,
+                    bp.data() + 4 * bp_off[a0]));
+    a0 = a1;
+  }
   phase_seconds_[1] = Seconds(t_phase);
 
   std::vector<std::future<std::vector<Piece>>> futures;

@@ -127,3 +127,10 @@ def test_polisher_facade_equals_oracle_polisher(oracle):
         assert [got.ascii(i) for i in range(got.n)] == seqs
         assert st["windows"] == int(ost[0]) and st["polished_windows"] == int(ost[1])
         assert st["polished_windows"] > 100
+    # the alignment batches of the facade (here forced small) change nothing
+    os.environ["RVN_POLISH_BATCH_BASES"] = "150000"
+    try:
+        again, _ = polish.polish(draft, reads, q=10.0, threads=4)
+    finally:
+        del os.environ["RVN_POLISH_BATCH_BASES"]
+    assert [again.ascii(i) for i in range(again.n)] == seqs
