@@ -2,7 +2,9 @@
 //
 // CPU restatement of ram::MinimizerEngine (un-vendored).
 // Every routine cites the reference call site that pins its contract.
-// PARITY UNPINNED per stage (no upstream golden vectors for this path).
+// Parity: upstream holds no per-stage vectors for ram; the restatement is pinned END TO END -
+// RavenTest.Assemble over this engine reproduces the reference's golden value 1137
+// (tests/test_oracle.py::test_end_to_end_pin_against_reference_golden).
 
 #include "ram/minimizer_engine.hpp"
 
