@@ -19,6 +19,9 @@
  *                          edlibAlign(lhs, rhs, edlibDefaultAlignConfig()) of the
  *                          identity filter      RavenLib/src/construct.cc:176-199,
  *                                                                        :393-416
+ *   rvn_stage1_pile_regions
+ *                          raven::Pile::FindValidRegion + FindMedian of
+ *                          raven::TrimAndAnnotatePiles RavenLib/src/construct.cc:123-152
  *   rvn_align_breaking_points
  *                          edlibAlign(read, unitig, NW, EDLIB_TASK_PATH) + the window
  *                          breaking points of racon::Polisher::Polish
@@ -171,6 +174,18 @@ int rvn_edit_distance_batch(rvn_ctx* ctx, uint64_t n_pairs, const uint32_t* lhs_
                             const uint32_t* rhs_read, const uint32_t* rhs_begin,
                             const uint32_t* rhs_len, const uint8_t* strand,
                             const int32_t* limit, int32_t* distance);
+
+/* raven::TrimAndAnnotatePiles' first two steps for every pile (RavenLib/src/construct.cc:
+ * 123-152: Pile::FindValidRegion(coverage) and Pile::FindMedian, pile.cc:122-172), on
+ * the piles the last rvn_find_overlaps_and_create_piles call left on the device - no
+ * round trip of the histograms. Per read i: invalid[i] = 1 if the reference marks the
+ * pile invalid (no run of bins >= coverage followed by a lower bin, or one shorter than
+ * 1260 >> 4 bins; begin/end then stay 0 / bins like the reference's fields); else
+ * [begin[i], end[i]) is the valid region in bins and median[i] the element of rank
+ * size/2 of it. The caller zeroes the bins outside the region like UpdateValidRegion.
+ * RVN_ERR_STATE if another call has replaced the device piles since. */
+int rvn_stage1_pile_regions(rvn_ctx* ctx, uint32_t coverage, uint32_t* begin, uint32_t* end,
+                            uint16_t* median, uint8_t* invalid);
 
 /* The read-to-target alignments of racon::Polisher::Polish (RavenLib/src/polish.cc:43-51:
  * edlibAlign(query, target, EDLIB_MODE_NW, EDLIB_TASK_PATH) per read) and the walk along

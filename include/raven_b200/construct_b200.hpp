@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <iostream>
+#include <future>
 #include <memory>
 #include <stdexcept>
 #include <vector>
@@ -93,6 +94,77 @@ inline void FindOverlapsAndCreatePiles(
   }
   std::cerr << "[raven::Graph::Construct] minimized + mapped sequences (B200) "
             << std::fixed << timer.Stop() << "s" << std::endl;
+}
+
+namespace detail {
+
+// the result of Pile::FindValidRegion + FindMedian into a pile, the way
+// UpdateValidRegion (pile.cc:144-157) and FindMedian (pile.cc:168-172) leave it
+struct PileTrimDoor {
+  std::uint32_t begin, end;
+  std::uint16_t median;
+  bool invalid;
+  template <typename... Ts>
+  void operator()(std::uint32_t&, std::uint32_t& b, std::uint32_t& e, std::uint16_t& m,
+                  bool& is_invalid, bool&, bool&, bool&, std::vector<std::uint16_t>& data,
+                  Ts&...) {
+    if (invalid) {
+      is_invalid = true;
+      return;
+    }
+    for (std::uint32_t i = b; i < begin; ++i) data[i] = 0;
+    for (std::uint32_t i = end; i < e; ++i) data[i] = 0;
+    b = begin;
+    e = end;
+    m = median;
+  }
+};
+
+}  // namespace detail
+
+// raven::TrimAndAnnotatePiles (construct.cc:123-152) right after
+// raven_b200::FindOverlapsAndCreatePiles: the valid regions and medians of ALL piles come
+// from the histograms that call left on the device (rvn_stage1_pile_regions); the host
+// pool applies them and runs the reference's own FindChimericRegions.
+inline void TrimAndAnnotatePiles(
+    const std::shared_ptr<thread_pool::ThreadPool>& thread_pool,
+    const std::vector<std::unique_ptr<raven::Pile>>& piles,
+    std::vector<std::vector<biosoup::Overlap>>& overlaps,
+    ram::MinimizerEngine& minimizer_engine) {
+  biosoup::Timer timer;
+  timer.Start();
+  const std::size_t n = piles.size();
+  std::vector<std::uint32_t> begin(n), end(n);
+  std::vector<std::uint16_t> median(n);
+  std::vector<std::uint8_t> invalid(n);
+  {
+    std::lock_guard<std::mutex> lock(minimizer_engine.mutex());
+    rvn_ctx* ctx = minimizer_engine.context();
+    const int rc = rvn_stage1_pile_regions(ctx, 4, begin.data(), end.data(), median.data(),
+                                           invalid.data());
+    if (rc != RVN_OK) throw std::runtime_error(rvn_last_error(ctx));
+  }
+  std::vector<std::future<void>> futures;
+  const std::size_t chunk = std::max<std::size_t>(64, n / 1024 + 1);
+  for (std::size_t i0 = 0; i0 < n; i0 += chunk) {
+    futures.emplace_back(thread_pool->Submit(
+        [&](std::size_t i0, std::size_t i1) {
+          for (std::size_t i = i0; i < i1; ++i) {
+            detail::PileTrimDoor door{begin[i], end[i], median[i], invalid[i] != 0};
+            auto visit = cereal::fields(door);
+            cereal::access::member_serialize(visit, *piles[i]);
+            if (piles[i]->is_invalid()) {
+              std::vector<biosoup::Overlap>().swap(overlaps[i]);
+            } else {
+              piles[i]->FindChimericRegions();
+            }
+          }
+        },
+        i0, std::min(n, i0 + chunk)));
+  }
+  for (auto& f : futures) f.wait();
+  std::cerr << "[raven::Graph::Construct] annotated piles (B200) " << std::fixed
+            << timer.Stop() << "s" << std::endl;
 }
 
 namespace detail {

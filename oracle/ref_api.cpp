@@ -57,6 +57,34 @@ struct PileProbe {
   }
 };
 
+struct PileDataSetter {  // a given histogram into a fresh pile
+  const std::uint16_t* src;
+  std::size_t n;
+  template <typename... Ts>
+  void operator()(std::uint32_t&, std::uint32_t&, std::uint32_t&,
+                  std::uint16_t&, bool&, bool&, bool&, bool&,
+                  std::vector<std::uint16_t>& d, Ts&...) {
+    d.assign(src, src + n);
+  }
+};
+
+struct PileFieldsProbe {
+  std::uint32_t begin = 0, end = 0;
+  std::uint16_t median = 0;
+  bool invalid = false;
+  std::vector<std::uint16_t> data;
+  template <typename... Ts>
+  void operator()(std::uint32_t&, std::uint32_t& b, std::uint32_t& e,
+                  std::uint16_t& m, bool& inv, bool&, bool&, bool&,
+                  std::vector<std::uint16_t>& d, Ts&...) {
+    begin = b;
+    end = e;
+    median = m;
+    invalid = inv;
+    data = d;
+  }
+};
+
 }  // namespace
 
 ORC_BAG_ACCESSORS(ref)
@@ -120,6 +148,32 @@ ORC_EXPORT orc_bag* ref_pile_add_layers(std::uint32_t id, std::uint32_t len,
   auto* bag = new orc_bag();
   bag->Put("pile", probe.data);
   return bag;
+}
+
+// raven::Pile::FindValidRegion(coverage) + FindMedian (TrimAndAnnotatePiles,
+// construct.cc:134-139) on piles with the given histograms: fields afterwards,
+// and the histograms as UpdateValidRegion left them
+ORC_EXPORT void ref_pile_trim(const std::uint16_t* data, const std::uint64_t* off,
+                              std::uint32_t n, std::uint32_t coverage, std::uint32_t* begin,
+                              std::uint32_t* end, std::uint16_t* median,
+                              std::uint8_t* invalid, std::uint16_t* data_out) {
+  for (std::uint32_t i = 0; i < n; ++i) {
+    const std::size_t bins = off[i + 1] - off[i];
+    raven::Pile p(i, static_cast<std::uint32_t>(bins << 4));
+    PileDataSetter set{data + off[i], bins};
+    auto put = cereal::fields(set);
+    cereal::access::member_serialize(put, p);
+    p.FindValidRegion(static_cast<std::uint16_t>(coverage));
+    if (!p.is_invalid()) p.FindMedian();
+    PileFieldsProbe probe;
+    auto get = cereal::fields(probe);
+    cereal::access::member_serialize(get, p);
+    begin[i] = probe.begin;
+    end[i] = probe.end;
+    median[i] = probe.median;
+    invalid[i] = probe.invalid ? 1 : 0;
+    std::copy(probe.data.begin(), probe.data.end(), data_out + off[i]);
+  }
 }
 
 // raven::Pile::AddKmers on a fresh pile of read `index`: which positions mark

@@ -73,6 +73,8 @@ SIGNATURES = {
     "rvn_edit_distance_batch": (C.c_int, [C.c_void_p, C.c_uint64, U32P, U32P, U32P, U32P, U32P,
                                           U32P, C.POINTER(C.c_uint8), C.POINTER(C.c_int32),
                                           C.POINTER(C.c_int32)]),
+    "rvn_stage1_pile_regions": (C.c_int, [C.c_void_p, C.c_uint32, U32P, U32P, U16P,
+                                          C.POINTER(C.c_uint8)]),
     "rvn_align_breaking_points": (C.c_int, [C.c_void_p, C.c_uint64, U32P, U32P, U32P,
                                             C.POINTER(C.c_uint8), U32P, U32P, U32P, C.c_uint32,
                                             U64P, C.POINTER(C.c_int32), U32P]),

@@ -147,6 +147,7 @@ void Stage1(Ctx& c, double freq, uint64_t kmax, bool minhash, uint64_t ib,
   c.stats.kernel_launches = c.launches - launches0;
   c.stats.occurrence = c.occurrence;
   c.st_valid = true;
+  c.st_piles_on_device = true;
 }
 
 }  // namespace
@@ -237,6 +238,7 @@ static void UploadReads(Ctx& c, const uint64_t* words, const uint64_t* word_off,
   if (res_first > res_last) throw InvalidArgument("resident range out of bounds");
   if (n_reads == 0xFFFFFFFFu) throw LimitError("too many reads");
   c.s_valid = c.q_valid = c.qt_valid = c.i_valid = c.r_valid = c.st_valid = false;
+  c.st_piles_on_device = false;
   c.tiles_k = 0;
   c.n_reads = n_reads;
   c.h_woff.assign(1, 0);
@@ -473,6 +475,7 @@ RVN_API int rvn_pile_add_layers(rvn_ctx* ctx, uint16_t* data,
     const uint64_t bins = bin_off[n_piles];
     uint16_t* d = c.p_data.reserve(bins + 1);
     c.p_off_uploaded = false;
+    c.st_piles_on_device = false;
     uint64_t* off = c.p_off.reserve(n_piles + 1ULL);
     rvn_overlap* o = c.p_ovl.reserve(n_overlaps + 1);
     RVN_CUDA(cudaMemcpyAsync(d, data, bins * 2, cudaMemcpyHostToDevice, c.stream));
@@ -643,6 +646,16 @@ RVN_API int rvn_edit_distance_batch(rvn_ctx* ctx, uint64_t n_pairs, const uint32
     }
     EditDistanceBatch(c, n_pairs, lhs_read, lhs_begin, lhs_len, rhs_read, rhs_begin, rhs_len,
                       strand, limit, distance);
+    TimerCollect(c);
+  });
+}
+
+RVN_API int rvn_stage1_pile_regions(rvn_ctx* ctx, uint32_t coverage, uint32_t* begin,
+                                    uint32_t* end, uint16_t* median, uint8_t* invalid) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (c.n_reads && (!begin || !end || !median || !invalid)) throw InvalidArgument("null argument");
+    if (coverage > 0xFFFF) throw InvalidArgument("coverage beyond 65535");
+    StagePileRegions(c, coverage, begin, end, median, invalid);
     TimerCollect(c);
   });
 }

@@ -188,6 +188,7 @@ struct Ctx {
   std::vector<uint64_t> st_pile_off;
   uint64_t st_mapped = 0;
   bool st_valid = false;
+  bool st_piles_on_device = false;  // c.p_data / c.p_off still hold the piles of that call
 
   // ---- read ownership of the stage-1 tail: read r is owned iff r % own_mod ==
   // own_rem (1 / 0 = every read: the single-GPU path) ----
@@ -321,6 +322,8 @@ void ArenaFlush(Ctx& c);
 void ArenaRelease(Ctx& c);
 
 // ---- editdist.cu ---- batched global edit distance of read substrings
+void StagePileRegions(Ctx& c, uint32_t coverage, uint32_t* h_begin, uint32_t* h_end,
+                      uint16_t* h_median, uint8_t* h_invalid);
 void AlignBreakingPoints(Ctx& c, uint64_t n, const uint32_t* q_read, const uint32_t* q_begin,
                          const uint32_t* q_len, const uint8_t* strand, const uint32_t* t_read,
                          const uint32_t* t_begin, const uint32_t* t_len, uint32_t window,

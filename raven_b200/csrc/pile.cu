@@ -177,6 +177,73 @@ __global__ void KmerComplexityKernel(const uint64_t* __restrict__ words,
   keep[t] = ok ? 1 : 0;
 }
 
+// Pile::FindValidRegion(coverage) + Pile::FindMedian (pile.cc:122-172) of fresh piles
+// (begin_ = 0, end_ = bins), one warp per pile. The region is the first longest run of
+// bins >= coverage that is FOLLOWED by a bin below it (the reference's scan never
+// records a run that reaches the last bin); it is valid from 1260 >> 4 bins on. The
+// median is the element of rank size / 2 of the region (std::nth_element): the
+// largest r with #{x < r} <= size / 2, found bit by bit.
+__global__ void __launch_bounds__(128)
+PileRegionsKernel(const uint16_t* __restrict__ data, const uint64_t* __restrict__ off,
+                  uint32_t n_piles, uint32_t coverage, uint32_t* __restrict__ out_begin,
+                  uint32_t* __restrict__ out_end, uint16_t* __restrict__ out_median,
+                  uint8_t* __restrict__ out_invalid) {
+  const uint32_t p = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (p >= n_piles) return;
+  const uint16_t* d = data + off[p];
+  const uint32_t nb = static_cast<uint32_t>(off[p + 1] - off[p]);
+  uint32_t begin = 0, end = 0;
+  long long run = -1;  // start of the run the scan is in
+  for (uint32_t base = 0; base < nb; base += 32) {
+    const uint32_t i = base + lane;
+    const uint32_t bits = min(32u, nb - base);
+    const uint32_t live = bits == 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, i < nb && d[i] >= coverage) & live;
+    uint32_t pos = 0;
+    while (pos < bits) {
+      if (run < 0) {  // next bin at or above the coverage
+        const uint32_t mm = m >> pos;
+        if (mm == 0) break;
+        const uint32_t s = __ffs(mm) - 1;
+        run = static_cast<long long>(base) + pos + s;
+        pos += s + 1;
+      } else {  // next bin below it
+        const uint32_t mm = (~m & live) >> pos;
+        if (mm == 0) break;
+        const uint32_t e = __ffs(mm) - 1;
+        const uint32_t j = base + pos + e;
+        if (end - begin < j - static_cast<uint32_t>(run)) {
+          begin = static_cast<uint32_t>(run);
+          end = j;
+        }
+        run = -1;
+        pos += e + 1;
+      }
+    }
+  }
+  const bool invalid = begin >= end || end - begin < (1260u >> 4);
+  uint32_t median = 0;
+  if (!invalid) {
+    const uint32_t size = end - begin, k = size / 2;
+    uint32_t r = 0;
+    for (int bit = 15; bit >= 0; --bit) {
+      const uint32_t cand = r | (1u << bit);
+      uint32_t c = 0;
+      for (uint32_t i = begin + lane; i < end; i += 32) c += d[i] < cand;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+      if (c <= k) r = cand;
+    }
+    median = r;
+  }
+  if (lane == 0) {
+    out_begin[p] = invalid ? 0 : begin;
+    out_end[p] = invalid ? nb : end;
+    out_median[p] = static_cast<uint16_t>(median);
+    out_invalid[p] = invalid ? 1 : 0;
+  }
+}
+
 }  // namespace
 
 void KmerComplexity(Ctx& c, const uint32_t* h_read_idx, const uint32_t* h_pos,
@@ -192,6 +259,31 @@ void KmerComplexity(Ctx& c, const uint32_t* h_read_idx, const uint32_t* h_pos,
   RVN_LAUNCH_CHECK();
   ++c.launches;
   RVN_CUDA(cudaMemcpyAsync(h_keep, d_keep, n, cudaMemcpyDeviceToHost, c.stream));
+  RVN_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+// valid regions and medians of the piles the last stage-1 call left on the device
+void StagePileRegions(Ctx& c, uint32_t coverage, uint32_t* h_begin, uint32_t* h_end,
+                      uint16_t* h_median, uint8_t* h_invalid) {
+  if (!c.st_valid || !c.st_piles_on_device) {
+    throw StateError("no stage-1 piles on the device (run rvn_find_overlaps_and_create_piles first)");
+  }
+  const uint32_t n = c.n_reads;
+  if (n == 0) return;
+  uint32_t* d_b = c.m_cnt.reserve(2ULL * n + 2);
+  uint32_t* d_e = d_b + n + 1;
+  uint16_t* d_m = reinterpret_cast<uint16_t*>(c.m_first.reserve(n / 2 + 2));
+  uint8_t* d_i = c.m_filt.reserve(n + 1ULL);
+  TimerBegin(c, "pile_regions");
+  PileRegionsKernel<<<CeilDiv(n, 4), 128, 0, c.stream>>>(c.p_data.get(), c.p_off.get(), n, coverage,
+                                                       d_b, d_e, d_m, d_i);
+  RVN_LAUNCH_CHECK();
+  ++c.launches;
+  TimerEnd(c);
+  RVN_CUDA(cudaMemcpyAsync(h_begin, d_b, n * 4ULL, cudaMemcpyDeviceToHost, c.stream));
+  RVN_CUDA(cudaMemcpyAsync(h_end, d_e, n * 4ULL, cudaMemcpyDeviceToHost, c.stream));
+  RVN_CUDA(cudaMemcpyAsync(h_median, d_m, n * 2ULL, cudaMemcpyDeviceToHost, c.stream));
+  RVN_CUDA(cudaMemcpyAsync(h_invalid, d_i, n, cudaMemcpyDeviceToHost, c.stream));
   RVN_CUDA(cudaStreamSynchronize(c.stream));
 }
 

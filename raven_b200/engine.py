@@ -230,6 +230,17 @@ class Engine:
             out.ctypes.data_as(C.POINTER(C.c_int32))))
         return out
 
+    def stage1_pile_regions(self, coverage=4):
+        """Pile::FindValidRegion(coverage) + FindMedian (pile.cc:122-172) of the piles the
+        last stage-1 call left on the device: begin, end (bins), median, invalid per read."""
+        n = self.n_reads
+        b, e = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        m, inv = np.zeros(n, np.uint16), np.zeros(n, np.uint8)
+        self._check(self.lib.rvn_stage1_pile_regions(
+            self.h, coverage, b.ctypes.data_as(U32P), e.ctypes.data_as(U32P),
+            m.ctypes.data_as(U16P), inv.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return dict(begin=b, end=e, median=m, invalid=inv)
+
     def align_breaking_points(self, q_read, q_begin, q_len, strand, t_read, t_begin, t_len,
                               window=500):
         """racon's read-to-target alignments + window cuts (polish.cc:43-51): distances,

@@ -101,7 +101,11 @@ int main(int argc, char** argv) {
       std::vector<std::unique_ptr<raven::Pile>> piles;
       std::vector<std::vector<biosoup::Overlap>> overlaps(seqs.size());
       raven_b200::FindOverlapsAndCreatePiles(pool, engine, seqs, freq, piles, overlaps, 32, false);
-      raven::TrimAndAnnotatePiles(pool, piles, overlaps);
+      if (mode == 0) {
+        raven::TrimAndAnnotatePiles(pool, piles, overlaps);
+      } else {
+        raven_b200::TrimAndAnnotatePiles(pool, piles, overlaps, engine);
+      }
       if (mode == 0) {
         raven::ResolveContainedReads(piles, overlaps, seqs, pool, identity);
       } else {

@@ -277,6 +277,23 @@ class Reference(_Flat):
         return self.unbag(bag, dict(pile=np.uint16))["pile"]
 
 
+def ref_pile_trim(ref, pile, pile_off, coverage=4):
+    """Pile::FindValidRegion(coverage) + FindMedian of the compiled reference (oracle/_ref)
+    on the given histograms: begin, end, median, invalid per pile and the trimmed data."""
+    d = np.ascontiguousarray(pile, dtype=np.uint16)
+    off = np.ascontiguousarray(pile_off, dtype=np.uint64)
+    n = off.size - 1
+    b, e = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    m, inv = np.zeros(n, np.uint16), np.zeros(n, np.uint8)
+    out = np.zeros_like(d)
+    ref.lib.ref_pile_trim.restype = None
+    ref.lib.ref_pile_trim.argtypes = [_U16P, _U64P, C.c_uint32, C.c_uint32, _U32P, _U32P, _U16P,
+                                      _U8P, _U16P]
+    ref.lib.ref_pile_trim(_ptr(d, _U16P), _ptr(off, _U64P), n, coverage, _ptr(b, _U32P),
+                          _ptr(e, _U32P), _ptr(m, _U16P), _ptr(inv, _U8P), _ptr(out, _U16P))
+    return dict(begin=b, end=e, median=m, invalid=inv, data=out)
+
+
 def ref_assemble(ref, rs, minhash=True, rounds=2, threads=4):
     """RavenTest.Assemble through the compiled reference sources (oracle/_ref)."""
     ref.lib.ref_assemble.restype = C.c_void_p

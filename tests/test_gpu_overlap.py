@@ -327,6 +327,31 @@ def test_stage1_probe_path_without_self_join(gpu_engine, oracle, lambda_reads):
             gpu_engine.set_option("tier_min_records", 1 << 18)
 
 
+def test_stage1_pile_regions_equal_reference(gpu_engine, lambda_reads):
+    """rvn_stage1_pile_regions (Pile::FindValidRegion(4) + FindMedian on the piles stage 1
+    left on the device, construct.cc:134-139) against the reference's own pile.cc compiled
+    in place (oracle/_ref): begin, end, median, invalid of every pile - the lambda reads,
+    a deep synthetic set, other coverages; and the state check."""
+    import oracle_lib
+    if not oracle_lib.Reference.available():
+        pytest.skip("oracle/_ref not built")
+    ref = oracle_lib.Reference()
+    for rs in (lambda_reads, synth.make_reads(40_000, 300, 5000, seed=14)):
+        gpu_engine.configure(15, 5)
+        gpu_engine.upload(rs)
+        res = gpu_engine.find_overlaps_and_create_piles(0.001, 32, False)
+        for cov in (4, 1, 9, 30):
+            got = gpu_engine.stage1_pile_regions(cov)
+            want = oracle_lib.ref_pile_trim(ref, res["pile"], res["pile_off"], cov)
+            for k in ("invalid", "begin", "end", "median"):
+                assert np.array_equal(got[k], want[k]), (cov, k)
+        assert (got["invalid"] == 0).any() or rs is lambda_reads
+    assert (gpu_engine.stage1_pile_regions(4)["invalid"] == 0).sum() > 100
+    gpu_engine.upload(rs)
+    with pytest.raises(RuntimeError):   # no stage-1 piles on the device any more
+        gpu_engine.stage1_pile_regions(4)
+
+
 def test_filter_with_very_long_runs(gpu_engine, oracle):
     """Keys that occur 65535 times or more fall out of the run-length histogram and are
     ranked by their exact lengths (CollectLongRuns) - in the tiered build this first
