@@ -1624,7 +1624,10 @@ void MapRange(Ctx& c, uint32_t first, uint32_t last, bool avoid_equal,
   // ---- stage 1 with the query reads inside the index batch: self-join ----
   const bool join = c.self_join && minhash && avoid_equal && avoid_symmetric && !want_filtered &&
                     c.i_from_sketch && c.i_sorted_ids && c.ids_identity && first >= c.i_first &&
-                    last <= c.i_last && c.qt_valid && c.qt_first <= first && last <= c.qt_last;
+                    last <= c.i_last;
+  if (join && !(c.qt_valid && c.qt_first <= first && last <= c.qt_last)) {
+    EnsureThresholds(c, first, last);  // (e.g. after a flush of reads outside the batch)
+  }
   uint64_t n_q = 0, n_hits = 0;
   uint64_t *hg = nullptr, *hp = nullptr;
   uint64_t* read_hit_off = c.m_read_hit_off.reserve(nr + 2ULL);
