@@ -364,3 +364,57 @@ def test_oracle_spoa_simd_fill_equals_scalar(oracle):
                 oracle.lib.orc_spoa_use_simd(0)
             for k in ("consensus", "cons_off", "coverage", "status", "cells"):
                 assert np.array_equal(a[k], b[k]), k
+
+
+def test_reference_pile_trim_rule(reference):
+    """Pile::FindValidRegion + FindMedian of the compiled reference (pile.cc:122-172)
+    against the rule the device kernel implements (PileRegionsKernel): the first longest
+    run of bins >= coverage that is FOLLOWED by a lower bin (a run that reaches the last
+    bin is never recorded), valid from 1260 >> 4 bins on; the median is the element of
+    rank size / 2. Pins the rule on CPU; the GPU test compares the kernel itself."""
+    import oracle_lib
+    rng = np.random.default_rng(1)
+    piles, off = [], [0]
+    for t in range(300):
+        nb = int(rng.integers(1, 400))
+        kind = t % 5
+        if kind == 0:
+            d = rng.integers(0, 10, nb)
+        elif kind == 1:
+            d = np.full(nb, 7)
+        elif kind == 2:
+            d = rng.integers(3, 40, nb)
+            d[rng.integers(0, nb, max(1, nb // 50))] = 0
+        elif kind == 3:
+            d = rng.integers(4, 9, nb)
+            if nb > 3:
+                d[-1] = 0
+                d[nb // 2] = 1
+        else:
+            d = rng.integers(0, 70000, nb).clip(0, 65535)
+        piles.append(d.astype(np.uint16))
+        off.append(off[-1] + nb)
+    got = oracle_lib.ref_pile_trim(reference, np.concatenate(piles), np.array(off, np.uint64), 4)
+    for i, d in enumerate(piles):
+        begin = end = 0
+        run = -1
+        for j, v in enumerate(d.tolist()):
+            if run < 0:
+                if v >= 4:
+                    run = j
+            elif v < 4:
+                if end - begin < j - run:
+                    begin, end = run, j
+                run = -1
+        invalid = begin >= end or end - begin < (1260 >> 4)
+        if invalid:
+            want = (0, len(d), 0, 1)
+        else:
+            want = (begin, end, int(np.sort(d[begin:end])[(end - begin) // 2]), 0)
+        assert (int(got["begin"][i]), int(got["end"][i]), int(got["median"][i]),
+                int(got["invalid"][i])) == want, i
+        if not invalid:   # UpdateValidRegion zeroes the bins outside the region
+            trimmed = got["data"][off[i]:off[i + 1]]
+            assert not trimmed[:begin].any() and not trimmed[end:].any()
+            assert np.array_equal(trimmed[begin:end], d[begin:end])
+    assert (got["invalid"] == 0).sum() > 20
