@@ -418,7 +418,7 @@ def main_ours(a):
             "config": {"workload": workload_name(a), "reads_per_gpu": rs.n // world,
                        "bases_per_gpu": int(rs.bases) // world,
                        "reads_total": rs.n, "overlaps_per_step": int(total_mapped),
-                       "l2": "inputs (0.5 GB packed reads, 10.7 GB minimizer records) "
+                       "l2": "inputs (0.5 GB packed reads, 8.1 GB minimizer records) "
                              "exceed the 126 MB L2; no explicit flush",
                        "parallelism": "1 GPU" if world == 1 else
                        f"{world} ranks: reads sharded by id, index keys by value mod "
