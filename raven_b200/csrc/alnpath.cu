@@ -554,7 +554,7 @@ void AlignBreakingPoints(Ctx& c, uint64_t n, const uint32_t* q_read, const uint3
         static_cast<uint64_t>(t_begin[i]) + t_len[i] > c.h_len[b]) {
       throw InvalidArgument("substring beyond the end of its read");
     }
-    if (q_len[i] >= (1u << 30) || t_len[i] >= (1u << 30)) throw LimitError("substring of 2^30 bases");
+    if (q_len[i] >= (1u << 28) || t_len[i] >= (1u << 28)) throw LimitError("substring of 2^28 bases");
     const uint64_t windows =
         t_len[i] ? (static_cast<uint64_t>(t_begin[i]) + t_len[i] - 1) / window - t_begin[i] / window + 1
                  : 0;
