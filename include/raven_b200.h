@@ -310,6 +310,14 @@ int rvn_dist_sketch_split(rvn_ctx* ctx, uint32_t first, uint32_t last, int minha
                           const uint64_t** d_origin, uint64_t* counts);
 int rvn_dist_index(rvn_ctx* ctx, const uint64_t* d_value, const uint64_t* d_origin,
                    uint64_t n_records, uint64_t index_bases);
+/* The same with the tiers of stage 1 (index.cu): records whose value exceeds
+ * value_limit - the largest micromizer value of ANY read that can query this batch,
+ * i.e. the maximum over the ranks of rvn_dist_max_threshold - are only counted for
+ * the occurrence threshold. ~0: no tiers. */
+int rvn_dist_index_limited(rvn_ctx* ctx, const uint64_t* d_value, const uint64_t* d_origin,
+                           uint64_t n_records, uint64_t index_bases, uint64_t value_limit);
+/* Largest micromizer value of the reads [first, last) this rank sketches (0 if empty). */
+int rvn_dist_max_threshold(rvn_ctx* ctx, uint32_t first, uint32_t last, uint64_t* value);
 /* run-length histogram of this rank's keys (u64 bins; bin i = keys with i
  * postings, last bin = longer runs) */
 int rvn_dist_histogram(rvn_ctx* ctx, const uint64_t** d_hist, uint32_t* n_bins,

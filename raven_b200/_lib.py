@@ -87,6 +87,9 @@ SIGNATURES = {
     "rvn_dist_sketch_split": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
                                         C.c_uint32, C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_void_p), U64P]),
+    "rvn_dist_index_limited": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                         C.c_uint64, C.c_uint64]),
+    "rvn_dist_max_threshold": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, U64P]),
     "rvn_dist_index": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                  C.c_uint64]),
     "rvn_dist_histogram": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), U32P, U64P]),

@@ -782,16 +782,34 @@ RVN_API int rvn_dist_sketch_split(rvn_ctx* ctx, uint32_t first, uint32_t last,
   }, /*sketches_first=*/true);
 }
 
-RVN_API int rvn_dist_index(rvn_ctx* ctx, const uint64_t* d_value,
-                           const uint64_t* d_origin, uint64_t n_records,
-                           uint64_t index_bases) {
+RVN_API int rvn_dist_index_limited(rvn_ctx* ctx, const uint64_t* d_value,
+                                   const uint64_t* d_origin, uint64_t n_records,
+                                   uint64_t index_bases, uint64_t value_limit) {
   return Guard(ctx, [&](Ctx& c) {
     if (n_records && (!d_value || !d_origin)) throw InvalidArgument("null records");
     c.i_first = c.i_last = 0;
-    BuildIndexFrom(c, ValView{d_value, 0}, d_origin, n_records, index_bases);
+    BuildIndexFrom(c, ValView{d_value, 0}, d_origin, n_records, index_bases, value_limit);
     // (records of a partitioned run arrive in read order: the caller's contract)
     c.i_sorted_ids = c.ids_ascending;
     RVN_CUDA(cudaStreamSynchronize(c.stream));
+  });
+}
+
+RVN_API int rvn_dist_index(rvn_ctx* ctx, const uint64_t* d_value,
+                           const uint64_t* d_origin, uint64_t n_records,
+                           uint64_t index_bases) {
+  return rvn_dist_index_limited(ctx, d_value, d_origin, n_records, index_bases, ~0ULL);
+}
+
+RVN_API int rvn_dist_max_threshold(rvn_ctx* ctx, uint32_t first, uint32_t last,
+                                   uint64_t* value) {
+  return Guard(ctx, [&](Ctx& c) {
+    if (!value) throw InvalidArgument("null output");
+    if (first > last) throw InvalidArgument("empty range");
+    *value = 0;
+    if (first == last) return;
+    CheckRange(c, first, last);
+    *value = MaxMicromizerValue(c, first, last);
   });
 }
 

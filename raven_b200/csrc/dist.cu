@@ -127,10 +127,16 @@ struct IndexView2 {
   uint64_t n;
   int shift;
   uint32_t occurrence;
+  uint64_t limit;  // values beyond it are not indexed (tiered build)
 };
 
 __device__ __forceinline__ void Lookup2(const IndexView2& ix, uint64_t v, uint32_t* first,
                                         uint32_t* count) {
+  if (v > ix.limit) {
+    *first = 0;
+    *count = 0;
+    return;
+  }
   const uint64_t b = v >> ix.shift;
   uint32_t lo = ix.bucket[b], hi = ix.bucket[b + 1];
   while (hi - lo > 8) {
@@ -571,7 +577,7 @@ void DistHitsSplit(Ctx& c, const uint64_t* d_qval, const uint64_t* d_qorg, uint6
   CheckParts(parts, 0);
   if (n_query > c.n_reads) throw InvalidArgument("query range out of bounds");
   IndexView2 ix{ValView{c.i_val.get(), c.i_is32 ? 1 : 0}, c.i_org.get(), c.i_bucket.get(), c.i_n,
-                c.i_shift, c.occurrence};
+                c.i_shift, c.occurrence, c.i_limit};
   const uint32_t per_part = CeilDiv(n_query, parts);
   const uint64_t slots = static_cast<uint64_t>(per_part) * parts;
   uint32_t* cnt = c.m_cnt.reserve(n_q + 1);

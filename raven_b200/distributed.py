@@ -115,6 +115,10 @@ class TorchComm:
         dist.all_reduce(t, group=self.group)
         return t
 
+    def all_reduce_max(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
     def begin_step(self):
         pass
 
@@ -279,8 +283,17 @@ def find_overlaps_and_create_piles(steps, lens, frequency=0.001, max_overlaps=32
             (qval, qorg), _ = comm.all_to_all_v([val, org], cnt)
             tick("a2a query records")
 
-        # -- 2. index slice + ONE global occurrence threshold
-        steps.build_index(ival, iorg, int(lens[j:i1].astype(np.uint64).sum()))
+        # -- 2. index slice + ONE global occurrence threshold. Queries are micromizers
+        # only: index records above the largest micromizer value of ANY read that can
+        # query this batch are counted but not probe-able (the tiers of index.cu); the
+        # bound is the maximum over the ranks (every rank knows its own query reads)
+        limit = None
+        if not use_minhash:
+            local = min(steps.max_threshold(qlo, qhi), (1 << 62))
+            t = torch.tensor([local], dtype=torch.int64, device=getattr(steps, "device", "cpu"))
+            limit = int(comm.all_reduce_max(t).item())
+            tick("index limit (all-reduce)")
+        steps.build_index(ival, iorg, int(lens[j:i1].astype(np.uint64).sum()), limit)
         tick("build_index")
         hist, n_keys = steps.histogram()
         tot = torch.cat([hist, torch.tensor([n_keys], dtype=torch.int64,
@@ -432,10 +445,16 @@ class CudaSteps:
         return (DevArray(v.value, (n,), torch.int64, self.device),
                 DevArray(o.value, (n,), torch.int64, self.device), cnt)
 
-    def build_index(self, val, org, bases):
+    def build_index(self, val, org, bases, limit=None):
         self._keep_index = (val, org)
-        self.e._check(self.lib.rvn_dist_index(self.h, self._p(val), self._p(org),
-                                              val.numel(), bases))
+        lim = 0xFFFFFFFFFFFFFFFF if limit is None else int(limit)
+        self.e._check(self.lib.rvn_dist_index_limited(self.h, self._p(val), self._p(org),
+                                                      val.numel(), bases, lim))
+
+    def max_threshold(self, first, last):
+        v = C.c_uint64(0)
+        self.e._check(self.lib.rvn_dist_max_threshold(self.h, first, last, C.byref(v)))
+        return int(v.value)
 
     def histogram(self):
         d, nb, nk = C.c_void_p(), C.c_uint32(0), C.c_uint64(0)

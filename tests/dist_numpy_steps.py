@@ -33,7 +33,14 @@ class NumpySteps:
         cnt = np.bincount(owner, minlength=parts).tolist()
         return _t(val[order], np.int64), _t(org[order], np.int64), cnt
 
-    def build_index(self, val, org, bases):
+    def max_threshold(self, first, last):
+        if last <= first:
+            return 0
+        s = self.o.sketch(self.eng, self.oreads, first, last, True)
+        return int(s["value"].max()) if s["value"].size else 0
+
+    def build_index(self, val, org, bases, limit=None):
+        # (the tiers are an implementation detail of the device index: same results)
         v = val.numpy().view(np.uint64)
         o = org.numpy().view(np.uint64)
         order = np.argsort(v, kind="stable")

@@ -56,6 +56,10 @@ class ThreadComm:
         got = self._swap(t.clone())
         return torch.stack(got).sum(0)
 
+    def all_reduce_max(self, t):
+        got = self._swap(t.clone())
+        return torch.stack(got).max(0).values
+
     def gather_objects(self, obj):
         return self._swap(obj)
 
@@ -63,13 +67,15 @@ class ThreadComm:
         pass
 
 
-def run_virtual(rs, world, freq, kmax, ib, qb, params=None, minhash=True):
+def run_virtual(rs, world, freq, kmax, ib, qb, params=None, minhash=True, tiers=False):
     shared = ThreadComm.Shared(world)
     res, err = [None] * world, [None] * world
 
     def work(rank):
         try:
             de = distributed.DistEngine("cuda:0", ThreadComm(shared, rank), **(params or {}))
+            if tiers:  # the tiered index also on inputs below its default size
+                de.engine.set_option("tier_min_records", 0)
             de.upload(rs)
             share = de.find_overlaps_and_create_piles(freq, kmax, minhash, ib, qb)
             assert share["ovl_off"].size - 1 == len(range(rank, rs.n, world))
@@ -118,6 +124,24 @@ def test_virtual_ranks_multi_batch_schedule(oracle, world, minhash):
     want = oracle.stage1(oracle.engine(15, 5), oracle.reads(rs), 0.01, 8, minhash, ib, qb)
     assert len(want["occurrences"]) >= 3
     res = run_virtual(rs, world, 0.01, 8, ib, qb, minhash=minhash)
+    check(res, want)
+    assert list(res[0]["occurrences"]) == list(want["occurrences"])
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_virtual_ranks_tiered_index(oracle, world):
+    """The index slices of the partitioned run with the tiers of stage 1: the bound is
+    the maximum over the ranks of their largest micromizer value (one all-reduce per
+    index batch). Single batch and the multi-batch schedule, low frequency cut."""
+    rs = synth.make_reads(60_000, 150, 6000, seed=11)
+    want = oracle.stage1(oracle.engine(15, 5), oracle.reads(rs), 0.001, 16, False)
+    res = run_virtual(rs, world, 0.001, 16, 0, 0, minhash=False, tiers=True)
+    check(res, want)
+    assert list(res[0]["occurrences"]) == list(want["occurrences"])
+    rs = synth.make_reads(40_000, 160, 4000, seed=12)
+    ib, qb = 200_000, 70_000
+    want = oracle.stage1(oracle.engine(15, 5), oracle.reads(rs), 0.02, 8, False, ib, qb)
+    res = run_virtual(rs, world, 0.02, 8, ib, qb, minhash=False, tiers=True)
     check(res, want)
     assert list(res[0]["occurrences"]) == list(want["occurrences"])
 
