@@ -788,7 +788,16 @@ RVN_API int rvn_dist_index_limited(rvn_ctx* ctx, const uint64_t* d_value,
   return Guard(ctx, [&](Ctx& c) {
     if (n_records && (!d_value || !d_origin)) throw InvalidArgument("null records");
     c.i_first = c.i_last = 0;
-    BuildIndexFrom(c, ValView{d_value, 0}, d_origin, n_records, index_bases, value_limit);
+    // (a rank owns 1/N of the keys of every group of equal upper bits: from about four
+    //  ranks on, counting inside groups costs more than a third pass over the bare keys)
+    c.group_count_min = 256;
+    try {
+      BuildIndexFrom(c, ValView{d_value, 0}, d_origin, n_records, index_bases, value_limit);
+    } catch (...) {
+      c.group_count_min = 0;
+      throw;
+    }
+    c.group_count_min = 0;
     // (records of a partitioned run arrive in read order: the caller's contract)
     c.i_sorted_ids = c.ids_ascending;
     RVN_CUDA(cudaStreamSynchronize(c.stream));

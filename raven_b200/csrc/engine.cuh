@@ -92,6 +92,7 @@ struct Ctx {
   DevBuf<uint64_t> qt_val;
   DevBuf<uint32_t> qt_pos;
   int t_b_low = 0;  // the bare keys of the upper tier are sorted above this many low bits
+  uint64_t group_count_min = 0;  // fewer keys per group of equal upper bits: full sort instead
   bool i_from_sketch = false;  // the index holds the FULL sketches of reads [i_first, i_last)
   int64_t self_join = 1;       // option: stage-1 hits by a self-join over the index
 

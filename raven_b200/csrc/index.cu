@@ -515,7 +515,13 @@ void BuildIndexFrom(Ctx& c, ValView src_val, const uint64_t* src_org, uint64_t n
     uint32_t* b2 = reinterpret_cast<uint32_t*>(c.t_b2.reserve(n_b / 2 + 2));
     // (sorted above their low bits only: GroupCountKernel reads the multiplicities
     //  off groups of equal upper bits)
-    c.t_b_low = key_bits > 2 * kGroupLowBits ? kGroupLowBits : 0;
+    // - while a group holds a few hundred keys: the rank of a partitioned run owns
+    // 1/N of the keys of every group, and zeroing and reading 1024 counters per
+    // group then costs more than the third pass
+    const uint64_t n_groups = ((value_mask - value_limit) >> kGroupLowBits) + 1;
+    c.t_b_low = (key_bits > 2 * kGroupLowBits && n_b / n_groups >= c.group_count_min)
+                    ? kGroupLowBits
+                    : 0;
     if (n_b > 0) {
       const int where = RadixSortKeys(c, b_src, b1, b2, n_b, c.t_b_low, key_bits);
       sorted_b = where < 0 ? b_src : (where == 0 ? b1 : b2);
