@@ -790,7 +790,7 @@ RVN_API int rvn_dist_index_limited(rvn_ctx* ctx, const uint64_t* d_value,
     c.i_first = c.i_last = 0;
     // (a rank owns 1/N of the keys of every group of equal upper bits: from about four
     //  ranks on, counting inside groups costs more than a third pass over the bare keys)
-    c.group_count_min = 256;
+    c.group_count_min = n_records >= (1ULL << 22) ? 256 : 0;  // (small slices: not worth deciding)
     try {
       BuildIndexFrom(c, ValView{d_value, 0}, d_origin, n_records, index_bases, value_limit);
     } catch (...) {
